@@ -1,0 +1,432 @@
+// b200vq.cu -- C ABI (include/b200vq.h) of the B200-native VectorQuantizer hot path.
+// Host launchers only; kernels live in kernels_simt.cuh / kernels_tc.cuh.  No torch, no CPU fallback.
+#include "../../include/b200vq.h"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "kernels_simt.cuh"
+#include "kernels_tc.cuh"
+
+using namespace b200vq;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess) return fail(VQ_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define LAUNCH_CHECK(name)                                                                         \
+    do {                                                                                           \
+        cudaError_t e__ = cudaGetLastError();                                                      \
+        if (e__ != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                        \
+    } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- device gate: this library only runs on sm_100 ------------------------------------------------
+int check_device() {
+    static thread_local int cached_dev = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(VQ_ERR_NO_DEVICE, "no CUDA device: %s (b200vq has no CPU fallback)", cudaGetErrorString(e));
+    if (dev == cached_dev) return VQ_OK;
+    int major = 0, minor = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    if (major != 10) return fail(VQ_ERR_NO_DEVICE, "device %d is sm_%d%d; b200vq kernels are built for sm_100a only", dev, major, minor);
+    cached_dev = dev;
+    return VQ_OK;
+}
+
+// ---- TMA descriptors ---------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+// (rows, D) fp32 row-major matrix; box = 32 floats (128 B) x 128 rows, 128-byte swizzle.
+int make_tmap(CUtensorMap* out, const float* base, long long rows, int D) {
+    auto fn = get_encode_fn();
+    if (fn == nullptr) return fail(VQ_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(D) * sizeof(float)};
+    cuuint32_t box[2] = {TC_SLAB_FLOATS, TC_ROWS};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(VQ_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    return VQ_OK;
+}
+
+// ---- path selection ------------------------------------------------------------------------------------
+bool tensor_path_ok(long long N, int K, int D, int flags, const float* z = nullptr, const float* ehi = nullptr,
+                    const float* elo = nullptr, bool check_ptrs = false) {
+    if (flags & VQ_FLAG_EXACT) return false;
+    if (N < 1 || N >= (1ll << 31) - TC_ROWS) return false;
+    if (D % TC_SLAB_FLOATS != 0 || D < 32 || D > 128) return false;
+    if (K % TC_CODES != 0 || K < TC_CODES) return false;
+    if (check_ptrs && (ehi == nullptr || elo == nullptr || !aligned16(z) || !aligned16(ehi) || !aligned16(elo))) return false;
+    return true;
+}
+
+// number of codebook splits per row tile: fill the 148 SMs when there are few row tiles.
+// cost(s) ~ waves(s) * (code tiles per CTA + fixed per-CTA overhead of ~1 tile)
+int choose_splits(long long row_tiles, int code_tiles, int max_splits) {
+    int best_s = 1;
+    double best_cost = 1e30;
+    for (int s = 1; s <= code_tiles && s <= max_splits; ++s) {
+        if (code_tiles % s != 0) continue;
+        const long long ctas = row_tiles * s;
+        const long long waves = (ctas + kNumSMs - 1) / kNumSMs;
+        const double cost = static_cast<double>(waves) * (static_cast<double>(code_tiles / s) + 1.0);
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best_s = s;
+        }
+    }
+    return best_s;
+}
+
+struct WsLayout {
+    size_t partials_off, counter_off, keys_off, total;
+    int rows_grid;
+};
+
+int rows_grid_for(long long N) {
+    long long g = (N + 7) / 8;
+    const long long cap = static_cast<long long>(kNumSMs) * 8;   // 8 CTAs of 256 threads per SM
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+
+WsLayout ws_layout(long long N) {
+    WsLayout w;
+    w.rows_grid = rows_grid_for(N);
+    w.partials_off = 0;
+    w.counter_off = static_cast<size_t>(kNumSMs) * 8 * sizeof(double);
+    w.keys_off = w.counter_off + 256;
+    w.total = w.keys_off + static_cast<size_t>(N) * sizeof(unsigned long long);
+    return w;
+}
+
+template <int NSLAB, int NSTAGE>
+int launch_tc(const CUtensorMap& tz, const CUtensorMap& thi, const CUtensorMap& tlo, const float* e_norm2, long long N,
+              int K, int codes_per_split, int splits, int* idx, unsigned long long* keys, float* hist,
+              unsigned int* counter, cudaStream_t st) {
+    constexpr int smem = tc_smem_bytes(NSLAB, NSTAGE);
+    static bool configured = false;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(argmin_tc_kernel<NSLAB, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    dim3 grid(static_cast<unsigned>((N + TC_ROWS - 1) / TC_ROWS), static_cast<unsigned>(splits));
+    argmin_tc_kernel<NSLAB, NSTAGE><<<grid, TC_THREADS, smem, st>>>(tz, thi, tlo, e_norm2, N, K, codes_per_split, idx,
+                                                                    keys, hist, counter);
+    LAUNCH_CHECK("argmin_tc_kernel");
+    return VQ_OK;
+}
+
+}  // namespace
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+extern "C" {
+
+int vq_abi_version(void) { return VQ_ABI_VERSION; }
+const char* vq_last_error(void) { return g_err; }
+int vq_device_check(void) { return check_device(); }
+int64_t vq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int vq_forward_uses_tensor_path(int64_t n_rows, int K, int D, int flags) {
+    return tensor_path_ok(n_rows, K, D, flags) ? 1 : 0;
+}
+
+size_t vq_workspace_bytes(int64_t n_rows, int K, int D, int flags) {
+    (void)K; (void)D; (void)flags;
+    if (n_rows < 0) n_rows = 0;
+    return ws_layout(n_rows).total;
+}
+
+int vq_prepare_codebook(const float* E, int K, int D, float* e_norm2, float* E_hi, float* E_lo, vq_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    if (E == nullptr || e_norm2 == nullptr || K < 1 || D < 1) return fail(VQ_ERR_ARG, "vq_prepare_codebook: bad argument (K=%d D=%d)", K, D);
+    if ((E_hi == nullptr) != (E_lo == nullptr)) return fail(VQ_ERR_ARG, "vq_prepare_codebook: E_hi and E_lo must both be given or both be NULL");
+    const int blocks = (K + 7) / 8;
+    prep_codebook_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(E, K, D, e_norm2, E_hi, E_lo);
+    LAUNCH_CHECK("prep_codebook_kernel");
+    return VQ_OK;
+}
+
+int vq_forward(const float* z, const float* E, const float* e_norm2, const float* E_hi, const float* E_lo,
+               int64_t n_rows, int K, int D, float beta, int flags, float* q_out, int32_t* idx, float* onehot,
+               float* hist, float* sse, float* loss, float* perplexity, void* workspace, size_t workspace_bytes,
+               vq_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    const long long N = n_rows;
+    const bool want_onehot = (flags & VQ_FLAG_ONEHOT) != 0;
+    const bool quant = (flags & VQ_FLAG_NO_QUANT) == 0;
+    const bool defer = (flags & VQ_FLAG_DEFER_STATS) != 0;
+    if (K < 1 || D < 1 || N < 0) return fail(VQ_ERR_ARG, "vq_forward: bad shape N=%lld K=%d D=%d", N, K, D);
+    if (z == nullptr || E == nullptr || e_norm2 == nullptr || idx == nullptr || hist == nullptr || sse == nullptr)
+        return fail(VQ_ERR_ARG, "vq_forward: null pointer among z/E/e_norm2/idx/hist/sse");
+    if (quant && q_out == nullptr) return fail(VQ_ERR_ARG, "vq_forward: q_out is NULL without VQ_FLAG_NO_QUANT");
+    if (want_onehot && onehot == nullptr) return fail(VQ_ERR_ARG, "vq_forward: VQ_FLAG_ONEHOT with onehot == NULL");
+    if (!defer && (perplexity == nullptr || (quant && loss == nullptr))) return fail(VQ_ERR_ARG, "vq_forward: loss/perplexity NULL without VQ_FLAG_DEFER_STATS");
+    const WsLayout w = ws_layout(N);
+    if (workspace == nullptr || workspace_bytes < w.total)
+        return fail(VQ_ERR_WORKSPACE, "vq_forward: workspace %zu B < required %zu B", workspace_bytes, w.total);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    double* partials = reinterpret_cast<double*>(ws + w.partials_off);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(ws + w.counter_off);
+    unsigned long long* keys_buf = reinterpret_cast<unsigned long long*>(ws + w.keys_off);
+
+    if (N == 0) {   // empty batch: statistics of nothing
+        CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(float) * K, st));
+        CUDA_TRY(cudaMemsetAsync(sse, 0, sizeof(float), st));
+        return VQ_OK;
+    }
+
+    // ---- 1. argmin ----------------------------------------------------------------------------------------
+    unsigned long long* keys = nullptr;
+    if (tensor_path_ok(N, K, D, flags, z, E_hi, E_lo, true)) {
+        const long long row_tiles = (N + TC_ROWS - 1) / TC_ROWS;
+        const int code_tiles = K / TC_CODES;
+        const int splits = choose_splits(row_tiles, code_tiles, 65535);
+        const int cps = K / splits;
+        if (splits > 1) {
+            keys = keys_buf;
+            CUDA_TRY(cudaMemsetAsync(keys, 0xFF, sizeof(unsigned long long) * N, st));
+        }
+        CUtensorMap tz, thi, tlo;
+        if (int rc = make_tmap(&tz, z, N, D)) return rc;
+        if (int rc = make_tmap(&thi, E_hi, K, D)) return rc;
+        if (int rc = make_tmap(&tlo, E_lo, K, D)) return rc;
+        int rc = VQ_OK;
+        switch (D / TC_SLAB_FLOATS) {
+            case 1: rc = launch_tc<1, 8>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
+            case 2: rc = launch_tc<2, 8>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
+            case 3: rc = launch_tc<3, 6>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
+            case 4: rc = launch_tc<4, 6>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
+            default: return fail(VQ_ERR_ARG, "vq_forward: unsupported D=%d on the tensor path", D);
+        }
+        if (rc) return rc;
+    } else {
+        const long long row_tiles = (N + S_TM - 1) / S_TM;
+        if (row_tiles > 2147483647ll) return fail(VQ_ERR_ARG, "vq_forward: N=%lld too large", N);
+        const int code_tiles = (K + S_TN - 1) / S_TN;
+        int splits = 1;
+        if (K % S_TN == 0) splits = choose_splits(row_tiles, code_tiles, 65535);
+        const int cps = (K + splits - 1) / splits;
+        if (splits > 1) {
+            keys = keys_buf;
+            CUDA_TRY(cudaMemsetAsync(keys, 0xFF, sizeof(unsigned long long) * N, st));
+        }
+        dim3 grid(static_cast<unsigned>(row_tiles), static_cast<unsigned>(splits));
+        argmin_simt_kernel<<<grid, 256, 0, st>>>(z, E, e_norm2, N, K, D, cps, idx, keys, hist, counter);
+        LAUNCH_CHECK("argmin_simt_kernel");
+    }
+
+    // ---- 2. rows: gather / straight-through value / SSE / histogram / one-hot / loss / perplexity ----------
+    const int vec_ok = (D % 4 == 0) && aligned16(z) && aligned16(E) && (!quant || aligned16(q_out));
+    const int oh_vec_ok = want_onehot && (K % 4 == 0) && aligned16(onehot);
+    const int fin = defer ? 0 : 1;
+#define ROWS_ARGS z, E, idx, keys, N, K, D, beta, q_out, idx, onehot, hist, partials, counter, sse, loss, perplexity, fin, vec_ok, oh_vec_ok
+    if (want_onehot && quant) quantize_rows_kernel<true, true><<<w.rows_grid, 256, 0, st>>>(ROWS_ARGS);
+    else if (want_onehot) quantize_rows_kernel<true, false><<<w.rows_grid, 256, 0, st>>>(ROWS_ARGS);
+    else if (quant) quantize_rows_kernel<false, true><<<w.rows_grid, 256, 0, st>>>(ROWS_ARGS);
+    else quantize_rows_kernel<false, false><<<w.rows_grid, 256, 0, st>>>(ROWS_ARGS);
+#undef ROWS_ARGS
+    LAUNCH_CHECK("quantize_rows_kernel");
+    return VQ_OK;
+}
+
+int vq_finalize_stats(const float* hist, const float* sse, int64_t n_rows_global, int K, int D, float beta,
+                      float* loss, float* perplexity, vq_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    if (hist == nullptr || perplexity == nullptr || K < 1 || D < 1 || n_rows_global < 1)
+        return fail(VQ_ERR_ARG, "vq_finalize_stats: bad argument");
+    finalize_stats_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(hist, sse, n_rows_global, K, D, beta, loss, perplexity);
+    LAUNCH_CHECK("finalize_stats_kernel");
+    return VQ_OK;
+}
+
+int vq_onehot(const int32_t* idx, int64_t n_rows, int K, float* onehot, vq_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    if (idx == nullptr || onehot == nullptr || K < 1 || n_rows < 0) return fail(VQ_ERR_ARG, "vq_onehot: bad argument");
+    if (n_rows == 0) return VQ_OK;
+    const int vec_ok = (K % 4 == 0) && aligned16(onehot);
+    onehot_kernel<<<rows_grid_for(n_rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(idx, n_rows, K, onehot, vec_ok);
+    LAUNCH_CHECK("onehot_kernel");
+    return VQ_OK;
+}
+
+int vq_backward(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx,
+                int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags, float* dz,
+                float* dE, vq_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    const long long N = n_rows;
+    const bool train = (flags & VQ_FLAG_TRAIN_VQ) != 0 && dE != nullptr;
+    if (z == nullptr || E == nullptr || idx == nullptr || dz == nullptr || K < 1 || D < 1 || N < 0 || n_rows_dz < 1 ||
+        n_rows_dE < 1)
+        return fail(VQ_ERR_ARG, "vq_backward: bad argument");
+    if (N == 0) return VQ_OK;
+    const float denom_dz = static_cast<float>(static_cast<double>(n_rows_dz) * static_cast<double>(D));
+    const float denom_dE = static_cast<float>(static_cast<double>(n_rows_dE) * static_cast<double>(D));
+    const int vec_ok = (D % 4 == 0) && aligned16(z) && aligned16(E) && aligned16(dz) && (g_q == nullptr || aligned16(g_q)) &&
+                       (!train || aligned16(dE));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = rows_grid_for(N);
+#define BWD_ARGS g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, D, beta, dz, dE, vec_ok
+    if (train && g_q) backward_kernel<true, true><<<grid, 256, 0, st>>>(BWD_ARGS);
+    else if (train) backward_kernel<true, false><<<grid, 256, 0, st>>>(BWD_ARGS);
+    else if (g_q) backward_kernel<false, true><<<grid, 256, 0, st>>>(BWD_ARGS);
+    else backward_kernel<false, false><<<grid, 256, 0, st>>>(BWD_ARGS);
+#undef BWD_ARGS
+    LAUNCH_CHECK("backward_kernel");
+    return VQ_OK;
+}
+
+// =========================================================================================================
+// host-buffer context: two lanes (stream + staging) so the H2D copy of step i+1 overlaps the kernels of step i
+// =========================================================================================================
+struct vq_host_ctx {
+    long long max_rows;
+    int K, D;
+    float *E, *e_norm2, *E_hi, *E_lo;
+    struct Lane {
+        cudaStream_t st;
+        float *z, *gq, *q, *dz, *dE, *hist, *scal;   // scal: [sse, loss, perplexity, g_loss]
+        int32_t* idx;
+        void* ws;
+        size_t ws_bytes;
+        bool gq_is_ones;
+    } lane[2];
+};
+
+static void host_ctx_free(vq_host_ctx* c) {
+    if (c == nullptr) return;
+    cudaFree(c->E); cudaFree(c->e_norm2); cudaFree(c->E_hi); cudaFree(c->E_lo);
+    for (auto& l : c->lane) {
+        cudaFree(l.z); cudaFree(l.gq); cudaFree(l.q); cudaFree(l.dz); cudaFree(l.dE); cudaFree(l.hist);
+        cudaFree(l.scal); cudaFree(l.idx); cudaFree(l.ws);
+        if (l.st) cudaStreamDestroy(l.st);
+    }
+    delete c;
+}
+
+int vq_host_ctx_create(int64_t max_rows, int K, int D, vq_host_ctx** out) {
+    if (int rc = check_device()) return rc;
+    if (out == nullptr || max_rows < 1 || K < 1 || D < 1) return fail(VQ_ERR_ARG, "vq_host_ctx_create: bad argument");
+    vq_host_ctx* c = new (std::nothrow) vq_host_ctx();
+    if (c == nullptr) return fail(VQ_ERR_ARG, "vq_host_ctx_create: out of host memory");
+    memset(c, 0, sizeof(*c));
+    c->max_rows = max_rows; c->K = K; c->D = D;
+    const size_t kd = sizeof(float) * K * D, nd = sizeof(float) * max_rows * D;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    A(reinterpret_cast<void**>(&c->E), kd); A(reinterpret_cast<void**>(&c->e_norm2), sizeof(float) * K);
+    A(reinterpret_cast<void**>(&c->E_hi), kd); A(reinterpret_cast<void**>(&c->E_lo), kd);
+    for (auto& l : c->lane) {
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking);
+        A(reinterpret_cast<void**>(&l.z), nd); A(reinterpret_cast<void**>(&l.gq), nd);
+        A(reinterpret_cast<void**>(&l.q), nd); A(reinterpret_cast<void**>(&l.dz), nd);
+        A(reinterpret_cast<void**>(&l.dE), kd); A(reinterpret_cast<void**>(&l.hist), sizeof(float) * K);
+        A(reinterpret_cast<void**>(&l.scal), sizeof(float) * 4);
+        A(reinterpret_cast<void**>(&l.idx), sizeof(int32_t) * max_rows);
+        l.ws_bytes = vq_workspace_bytes(max_rows, K, D, 0);
+        A(&l.ws, l.ws_bytes);
+    }
+    if (e != cudaSuccess) {
+        host_ctx_free(c);
+        return fail(VQ_ERR_CUDA, "vq_host_ctx_create: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return VQ_OK;
+}
+
+void vq_host_ctx_destroy(vq_host_ctx* ctx) { host_ctx_free(ctx); }
+
+int vq_host_set_codebook(vq_host_ctx* c, const float* E_host) {
+    if (c == nullptr || E_host == nullptr) return fail(VQ_ERR_ARG, "vq_host_set_codebook: null");
+    cudaStream_t st = c->lane[0].st;
+    CUDA_TRY(cudaMemcpyAsync(c->E, E_host, sizeof(float) * c->K * c->D, cudaMemcpyHostToDevice, st));
+    if (int rc = vq_prepare_codebook(c->E, c->K, c->D, c->e_norm2, c->E_hi, c->E_lo, st)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return VQ_OK;
+}
+
+int vq_host_step_async(vq_host_ctx* c, int lane, const float* z_host, const float* gq_host, int64_t n_rows, float beta,
+                       int flags, float* loss_host, float* perplexity_host, int32_t* idx_host, float* q_host,
+                       float* dz_host, float* dE_host) {
+    if (c == nullptr || z_host == nullptr || lane < 0 || lane > 1) return fail(VQ_ERR_ARG, "vq_host_step_async: bad argument");
+    if (n_rows < 1 || n_rows > c->max_rows) return fail(VQ_ERR_ARG, "vq_host_step_async: n_rows=%lld outside [1, %lld]", (long long)n_rows, c->max_rows);
+    auto& l = c->lane[lane];
+    const size_t nd = sizeof(float) * n_rows * c->D, kd = sizeof(float) * c->K * c->D;
+    const bool train = (flags & VQ_FLAG_TRAIN_VQ) != 0;
+    CUDA_TRY(cudaMemcpyAsync(l.z, z_host, nd, cudaMemcpyHostToDevice, l.st));
+    if (gq_host != nullptr) {
+        CUDA_TRY(cudaMemcpyAsync(l.gq, gq_host, nd, cudaMemcpyHostToDevice, l.st));
+        l.gq_is_ones = false;
+    } else if (!l.gq_is_ones) {
+        fill_kernel<<<kNumSMs * 4, 256, 0, l.st>>>(l.gq, 1.0f, static_cast<long long>(c->max_rows) * c->D);
+        LAUNCH_CHECK("fill_kernel");
+        l.gq_is_ones = true;
+    }
+    if (int rc = vq_forward(l.z, c->E, c->e_norm2, c->E_hi, c->E_lo, n_rows, c->K, c->D, beta, flags & ~(VQ_FLAG_ONEHOT | VQ_FLAG_DEFER_STATS | VQ_FLAG_NO_QUANT),
+                            l.q, l.idx, nullptr, l.hist, l.scal + 0, l.scal + 1, l.scal + 2, l.ws, l.ws_bytes, l.st))
+        return rc;
+    if (train) CUDA_TRY(cudaMemsetAsync(l.dE, 0, kd, l.st));
+    // gq_host == NULL: the lane's g_q buffer still holds the ones written at context creation, i.e. the
+    // `(loss + quantized.sum()).backward()` workload; the kernel reads it like any upstream gradient.
+    if (int rc = vq_backward(l.gq, nullptr, l.z, c->E, l.idx, n_rows, n_rows, n_rows, c->K, c->D, beta, flags, l.dz,
+                             train ? l.dE : nullptr, l.st))
+        return rc;
+    if (loss_host) CUDA_TRY(cudaMemcpyAsync(loss_host, l.scal + 1, sizeof(float), cudaMemcpyDeviceToHost, l.st));
+    if (perplexity_host) CUDA_TRY(cudaMemcpyAsync(perplexity_host, l.scal + 2, sizeof(float), cudaMemcpyDeviceToHost, l.st));
+    if (idx_host) CUDA_TRY(cudaMemcpyAsync(idx_host, l.idx, sizeof(int32_t) * n_rows, cudaMemcpyDeviceToHost, l.st));
+    if (q_host) CUDA_TRY(cudaMemcpyAsync(q_host, l.q, nd, cudaMemcpyDeviceToHost, l.st));
+    if (dz_host) CUDA_TRY(cudaMemcpyAsync(dz_host, l.dz, nd, cudaMemcpyDeviceToHost, l.st));
+    if (dE_host && train) CUDA_TRY(cudaMemcpyAsync(dE_host, l.dE, kd, cudaMemcpyDeviceToHost, l.st));
+    return VQ_OK;
+}
+
+int vq_host_wait(vq_host_ctx* c, int lane) {
+    if (c == nullptr || lane < 0 || lane > 1) return fail(VQ_ERR_ARG, "vq_host_wait: bad argument");
+    CUDA_TRY(cudaStreamSynchronize(c->lane[lane].st));
+    return VQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,386 @@
+// kernels_simt.cuh -- CUDA-core kernels of the VQ hot path:
+//   prep_codebook_kernel   |E_k|^2 and the tf32 hi/lo split of E        (vector_quantizer.py:35)
+//   argmin_simt_kernel     exact fp32 distances + first-index argmin    (vector_quantizer.py:34-38)
+//   quantize_rows_kernel   gather, straight-through value, SSE, usage histogram, one-hot,
+//                          loss / perplexity                             (vector_quantizer.py:39-56)
+//   finalize_stats_kernel  loss / perplexity from all-reduced statistics (data parallel)
+//   onehot_kernel          dense one-hot from indices                    (vector_quantizer.py:39-40)
+//   backward_kernel        dz and the scatter-add into dE                (autograd of :46-54)
+// Arithmetic order is the one oracle/vq_oracle.c documents.
+#pragma once
+#include "common.cuh"
+
+namespace b200vq {
+
+__global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ p, float v, long long n) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// prep: one warp per codeword
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_codebook_kernel(const float* __restrict__ E, int K, int D,
+                                                            float* __restrict__ e_norm2, float* __restrict__ E_hi,
+                                                            float* __restrict__ E_lo) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= K) return;
+    const float* row = E + static_cast<size_t>(warp) * D;
+    if (E_hi != nullptr) {
+        for (int d = lane; d < D; d += 32) {
+            const float v = row[d];
+            const float hi = tf32_rna(v);
+            E_hi[static_cast<size_t>(warp) * D + d] = hi;
+            E_lo[static_cast<size_t>(warp) * D + d] = tf32_rna(v - hi);
+        }
+    }
+    if (lane == 0) {
+        // sequential FMA chain: the order oracle/vq_oracle.c:norm2_chain fixes
+        float acc = 0.0f;
+        for (int d = 0; d < D; ++d) {
+            const float v = row[d];
+            acc = fmaf(v, v, acc);
+        }
+        e_norm2[warp] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact argmin: 64 rows x 64 codes per CTA tile, 4 x 4 per thread, D streamed in chunks of 32.
+// Every (row, code) dot product is ONE sequential fmaf chain over d = 0..D-1 (zero padding past D
+// adds exact zeros), so results are bit-identical to oracle/vq_oracle.c for any tiling.
+// grid = (ceil(N/64), splits); with splits > 1 partial minima meet in `keys` via 64-bit atomicMin.
+// ---------------------------------------------------------------------------------------------
+constexpr int S_TM = 64, S_TN = 64, S_TD = 32, S_LD = 68;
+
+__global__ void __launch_bounds__(256) argmin_simt_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                                                          const float* __restrict__ e_norm2, long long N, int K, int D,
+                                                          int codes_per_split, int* __restrict__ idx_out,
+                                                          unsigned long long* __restrict__ keys,
+                                                          float* __restrict__ hist_to_zero,
+                                                          unsigned int* __restrict__ counter_to_zero) {
+    __shared__ __align__(16) float zs[S_TD][S_LD];
+    __shared__ __align__(16) float es[S_TD][S_LD];
+    __shared__ float a_s[S_TM];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const long long row0 = static_cast<long long>(blockIdx.x) * S_TM;
+    const int k_begin = blockIdx.y * codes_per_split;
+    const int k_end = min(K, k_begin + codes_per_split);
+
+    if (blockIdx.x == 0 && blockIdx.y == 0) {  // forward-state reset rides along (consumed by the next kernel)
+        for (int k = tid; k < K; k += blockDim.x) hist_to_zero[k] = 0.0f;
+        if (tid == 0) *counter_to_zero = 0u;
+    }
+    if (tid < S_TM) {
+        const long long r = row0 + tid;
+        float a = 0.0f;
+        if (r < N) {
+            const float* zr = z + r * D;
+            for (int d = 0; d < D; ++d) {
+                const float v = zr[d];
+                a = fmaf(v, v, a);
+            }
+        }
+        a_s[tid] = a;
+    }
+    float best[4];
+    int bi[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        best[i] = INFINITY;
+        bi[i] = k_begin;
+    }
+    for (int k0 = k_begin; k0 < k_end; k0 += S_TN) {
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+        for (int d0 = 0; d0 < D; d0 += S_TD) {
+            __syncthreads();
+            {
+                const int d = tid & 31, gd = d0 + d;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = i * 8 + (tid >> 5);
+                    const long long gr = row0 + r;
+                    zs[d][r] = (gr < N && gd < D) ? z[gr * D + gd] : 0.0f;
+                    const int k = k0 + r;
+                    es[d][r] = (k < k_end && gd < D) ? E[static_cast<size_t>(k) * D + gd] : 0.0f;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int d = 0; d < S_TD; ++d) {
+                const float4 zv = *reinterpret_cast<const float4*>(&zs[d][ty * 4]);
+                const float4 ev = *reinterpret_cast<const float4*>(&es[d][tx * 4]);
+                const float zr[4] = {zv.x, zv.y, zv.z, zv.w};
+                const float er[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(zr[i], er[j], acc[i][j]);
+            }
+        }
+        // dist = fl(fl(a_n + b_k) - 2 c): vector_quantizer.py:34-36 evaluation order (2c is exact)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + tx * 4 + j;
+            if (k < k_end) {
+                const float b = __ldg(e_norm2 + k);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float t = a_s[ty * 4 + i] + b;
+                    const float dist = fmaf(-2.0f, acc[i][j], t);
+                    if (dist < best[i]) {
+                        best[i] = dist;
+                        bi[i] = k;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        unsigned long long key = pack_key(best[i], bi[i]);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other < key ? other : key;
+        }
+        const long long r = row0 + ty * 4 + i;
+        if (tx == 0 && r < N) {
+            if (keys != nullptr)
+                atomicMin(keys + r, key);
+            else
+                idx_out[r] = static_cast<int>(key & 0xffffffffu);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rows: one warp per row, lanes along D.  HBM-bound streaming kernel.
+//   q_out = fl(z + fl(E[idx] - z)); sse += (E[idx]-z)^2; hist[idx] += 1; optional one-hot row.
+// The last CTA to finish reduces the per-CTA partial sums in a fixed order and (unless deferred)
+// writes loss and perplexity, so a single-GPU forward needs no further launch.
+// ---------------------------------------------------------------------------------------------
+template <bool ONEHOT, bool QUANT>
+__global__ void __launch_bounds__(256) quantize_rows_kernel(
+    const float* __restrict__ z, const float* __restrict__ E, const int* __restrict__ idx_in,
+    const unsigned long long* __restrict__ keys, long long N, int K, int D, float beta, float* __restrict__ q_out,
+    int* __restrict__ idx_out, float* __restrict__ onehot, float* __restrict__ hist, double* __restrict__ partials,
+    unsigned int* __restrict__ counter, float* __restrict__ sse_out, float* __restrict__ loss,
+    float* __restrict__ perplexity, int finalize, int vec_ok, int onehot_vec_ok) {
+    __shared__ double red[8];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long warp0 = static_cast<long long>(blockIdx.x) * 8 + wib;
+    const long long nwarps = static_cast<long long>(gridDim.x) * 8;
+    float sse = 0.0f;
+    for (long long r = warp0; r < N; r += nwarps) {
+        int code;
+        if (keys != nullptr) {
+            code = static_cast<int>(keys[r] & 0xffffffffu);
+            if (lane == 0) idx_out[r] = code;
+        } else {
+            code = idx_in[r];
+        }
+        if (lane == 0) atomicAdd(hist + code, 1.0f);
+        if (QUANT) {
+            const float* zr = z + r * D;
+            const float* er = E + static_cast<size_t>(code) * D;
+            float* qr = q_out + r * D;
+            if (vec_ok) {
+                for (int c = lane; c < (D >> 2); c += 32) {
+                    const float4 zv = __ldcs(reinterpret_cast<const float4*>(zr) + c);
+                    const float4 ev = __ldg(reinterpret_cast<const float4*>(er) + c);
+                    float4 df, qv;
+                    df.x = ev.x - zv.x; df.y = ev.y - zv.y; df.z = ev.z - zv.z; df.w = ev.w - zv.w;
+                    qv.x = zv.x + df.x; qv.y = zv.y + df.y; qv.z = zv.z + df.z; qv.w = zv.w + df.w;
+                    __stcs(reinterpret_cast<float4*>(qr) + c, qv);
+                    sse = fmaf(df.x, df.x, sse); sse = fmaf(df.y, df.y, sse);
+                    sse = fmaf(df.z, df.z, sse); sse = fmaf(df.w, df.w, sse);
+                }
+            } else {
+                for (int d = lane; d < D; d += 32) {
+                    const float zv = zr[d];
+                    const float df = __ldg(er + d) - zv;
+                    qr[d] = zv + df;
+                    sse = fmaf(df, df, sse);
+                }
+            }
+        }
+        if (ONEHOT) {
+            float* orow = onehot + r * K;
+            if (onehot_vec_ok) {
+                for (int c = lane; c < (K >> 2); c += 32) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c == (code >> 2)) {
+                        const int w = code & 3;
+                        v.x = w == 0 ? 1.f : 0.f; v.y = w == 1 ? 1.f : 0.f;
+                        v.z = w == 2 ? 1.f : 0.f; v.w = w == 3 ? 1.f : 0.f;
+                    }
+                    __stcs(reinterpret_cast<float4*>(orow) + c, v);
+                }
+            } else {
+                for (int k = lane; k < K; k += 32) orow[k] = (k == code) ? 1.0f : 0.0f;
+            }
+        }
+    }
+    // block partial (double), then last-CTA-done reduction in a fixed order
+    double s = warp_sum_d(static_cast<double>(sse));
+    if (lane == 0) red[wib] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        partials[blockIdx.x] = t;
+        __threadfence();
+        const unsigned int done = atomicAdd(counter, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double t = 0.0;
+    for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += blockDim.x) t += __ldcg(partials + i);
+    t = warp_sum_d(t);
+    __syncthreads();
+    if (lane == 0) red[wib] = t;
+    __syncthreads();
+    double total = 0.0;
+    for (int w = 0; w < 8; ++w) total += red[w];
+    if (threadIdx.x == 0) {
+        *sse_out = static_cast<float>(total);
+        *counter = 0u;
+    }
+    if (finalize) {
+        if (QUANT && threadIdx.x == 0) {
+            const float m = static_cast<float>(total / (static_cast<double>(N) * static_cast<double>(D)));
+            *loss = __fadd_rn(m, __fmul_rn(beta, m));   // vector_quantizer.py:52 with q_latent == e_latent == m
+        }
+        double ent = 0.0;
+        const float nf = static_cast<float>(N);
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            const float p = __fdiv_rn(__ldcg(hist + k), nf);   // vector_quantizer.py:55
+            ent += static_cast<double>(p * logf(p + 1e-10f));   // :56
+        }
+        ent = warp_sum_d(ent);
+        __syncthreads();
+        if (lane == 0) red[wib] = ent;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double e = 0.0;
+            for (int w = 0; w < 8; ++w) e += red[w];
+            *perplexity = expf(static_cast<float>(-e));
+        }
+    }
+}
+
+// loss / perplexity from (all-reduced) statistics: one CTA
+__global__ void __launch_bounds__(256) finalize_stats_kernel(const float* __restrict__ hist,
+                                                             const float* __restrict__ sse, long long N_global, int K,
+                                                             int D, float beta, float* __restrict__ loss,
+                                                             float* __restrict__ perplexity) {
+    __shared__ double red[8];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double ent = 0.0;
+    const float nf = static_cast<float>(N_global);
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const float p = __fdiv_rn(hist[k], nf);
+        ent += static_cast<double>(p * logf(p + 1e-10f));
+    }
+    ent = warp_sum_d(ent);
+    if (lane == 0) red[wib] = ent;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double e = 0.0;
+        for (int w = 0; w < 8; ++w) e += red[w];
+        *perplexity = expf(static_cast<float>(-e));
+        if (loss != nullptr && sse != nullptr) {
+            const float m =
+                static_cast<float>(static_cast<double>(*sse) / (static_cast<double>(N_global) * static_cast<double>(D)));
+            *loss = __fadd_rn(m, __fmul_rn(beta, m));
+        }
+    }
+}
+
+// dense one-hot from indices: one warp per row, write-only
+__global__ void __launch_bounds__(256) onehot_kernel(const int* __restrict__ idx, long long N, int K,
+                                                     float* __restrict__ onehot, int vec_ok) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    const long long nwarps = static_cast<long long>(gridDim.x) * 8;
+    for (long long r = warp0; r < N; r += nwarps) {
+        const int code = idx[r];
+        float* orow = onehot + r * K;
+        if (vec_ok) {
+            for (int c = lane; c < (K >> 2); c += 32) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c == (code >> 2)) {
+                    const int w = code & 3;
+                    v.x = w == 0 ? 1.f : 0.f; v.y = w == 1 ? 1.f : 0.f;
+                    v.z = w == 2 ? 1.f : 0.f; v.w = w == 3 ? 1.f : 0.f;
+                }
+                __stcs(reinterpret_cast<float4*>(orow) + c, v);
+            }
+        } else {
+            for (int k = lane; k < K; k += 32) orow[k] = (k == code) ? 1.0f : 0.0f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward: one warp per row.  dz = g_q - cz*(q - z);  dE[idx] += ce*(q - z)  (red.global.add)
+//   cz = g_loss*beta*2/(n_rows_dz*D), ce = g_loss*2/(n_rows_dE*D)   -- oracle/vq_oracle.c order
+// ---------------------------------------------------------------------------------------------
+template <bool TRAIN_VQ, bool HAS_GQ>
+__global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__ g_q, const float* __restrict__ g_loss,
+                                                       const float* __restrict__ z, const float* __restrict__ E,
+                                                       const int* __restrict__ idx, long long N, float denom_dz,
+                                                       float denom_dE, int D, float beta, float* __restrict__ dz,
+                                                       float* __restrict__ dE, int vec_ok) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    const long long nwarps = static_cast<long long>(gridDim.x) * 8;
+    const float gl = g_loss != nullptr ? __ldg(g_loss) : 1.0f;
+    const float cz = gl * beta * 2.0f / denom_dz;
+    const float ce = gl * 2.0f / denom_dE;
+    for (long long r = warp0; r < N; r += nwarps) {
+        const int code = idx[r];
+        const float* zr = z + r * D;
+        const float* er = E + static_cast<size_t>(code) * D;
+        float* dzr = dz + r * D;
+        float* der = TRAIN_VQ ? dE + static_cast<size_t>(code) * D : nullptr;
+        if (vec_ok) {
+            for (int c = lane; c < (D >> 2); c += 32) {
+                const float4 zv = __ldcs(reinterpret_cast<const float4*>(zr) + c);
+                const float4 ev = __ldg(reinterpret_cast<const float4*>(er) + c);
+                float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (HAS_GQ) gv = __ldcs(reinterpret_cast<const float4*>(g_q + r * D) + c);
+                float4 df, o;
+                df.x = ev.x - zv.x; df.y = ev.y - zv.y; df.z = ev.z - zv.z; df.w = ev.w - zv.w;
+                o.x = fmaf(-cz, df.x, gv.x); o.y = fmaf(-cz, df.y, gv.y);
+                o.z = fmaf(-cz, df.z, gv.z); o.w = fmaf(-cz, df.w, gv.w);
+                __stcs(reinterpret_cast<float4*>(dzr) + c, o);
+                if (TRAIN_VQ) {
+                    float4 a;
+                    a.x = ce * df.x; a.y = ce * df.y; a.z = ce * df.z; a.w = ce * df.w;
+                    atomicAdd(reinterpret_cast<float4*>(der) + c, a);
+                }
+            }
+        } else {
+            for (int d = lane; d < D; d += 32) {
+                const float zv = zr[d];
+                const float df = __ldg(er + d) - zv;
+                const float gv = HAS_GQ ? g_q[r * D + d] : 0.0f;
+                dzr[d] = fmaf(-cz, df, gv);
+                if (TRAIN_VQ) atomicAdd(der + d, ce * df);
+            }
+        }
+    }
+}
+
+}  // namespace b200vq

@@ -1,0 +1,276 @@
+"""VectorQuantizer: host-side mirror of the reference module, backed by libb200vq.so.
+
+Mirrors `/root/reference/src/acoustic_locating_vq_vae/vq_vae/vector_quantizer.py:8-58`:
+same constructor, same attributes (`_embedding`, `_embedding_dim`, `_num_embeddings`,
+`_commitment_cost`, `_train_vq`, `_flag_flatten`), same state-dict key (`_embedding.weight`),
+same `forward(inputs) -> (loss, quantized, perplexity, encodings)`, same error behaviour for
+inputs that `.view(-1, D)` rejects.  All arithmetic happens in hand-written sm_100a CUDA behind
+the C ABI in include/b200vq.h; PyTorch only owns the buffers and the stream.  There is no CPU
+path: a non-CUDA input raises.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import (FLAG_DEFER_STATS, FLAG_EXACT, FLAG_NO_QUANT, FLAG_ONEHOT, FLAG_TRAIN_VQ, check)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Buffers:
+    """Per-module device scratch, grown on demand and reused (stream-ordered, one stream per module)."""
+
+    def __init__(self):
+        self.ws = None
+        self.code = None     # (e_norm2, E_hi, E_lo)
+
+    def workspace(self, nbytes: int, device) -> torch.Tensor:
+        if self.ws is None or self.ws.numel() < nbytes or self.ws.device != device:
+            self.ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        return self.ws
+
+    def codebook(self, K: int, D: int, device):
+        c = self.code
+        if c is None or c[1].shape != (K, D) or c[1].device != device:
+            self.code = (torch.empty(K, dtype=torch.float32, device=device),
+                         torch.empty(K, D, dtype=torch.float32, device=device),
+                         torch.empty(K, D, dtype=torch.float32, device=device))
+        return self.code
+
+
+class _VQFunction(torch.autograd.Function):
+    """forward = vq_prepare_codebook + vq_forward; backward = vq_backward (+ optional all-reduce)."""
+
+    @staticmethod
+    def forward(ctx, inputs, weight, module, flags, want_onehot):
+        lib = _lib.load()
+        K, D = weight.shape
+        flat = inputs.view(-1, D)                     # vector_quantizer.py:32 (raises like the reference)
+        N = flat.shape[0]
+        dev = inputs.device
+        st = _stream()
+        w = weight.detach()
+        if not w.is_contiguous():
+            w = w.contiguous()
+        bufs: _Buffers = module._bufs
+        e_norm2, e_hi, e_lo = bufs.codebook(K, D, dev)
+        check(lib.vq_prepare_codebook(_ptr(w), K, D, _ptr(e_norm2), _ptr(e_hi), _ptr(e_lo), st))
+        q_out = torch.empty_like(inputs)
+        idx = torch.empty(N, dtype=torch.int32, device=dev)
+        stats = torch.empty(K + 1, dtype=torch.float32, device=dev)    # [hist(K) | sse]
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        perplexity = torch.empty((), dtype=torch.float32, device=dev)
+        onehot = torch.empty(N, K, dtype=torch.float32, device=dev) if want_onehot else None
+        fl = flags | (FLAG_ONEHOT if want_onehot else 0)
+        nbytes = lib.vq_workspace_bytes(N, K, D, fl)
+        ws = bufs.workspace(nbytes, dev)
+        sp = stats.data_ptr()
+        check(lib.vq_forward(_ptr(flat), _ptr(w), _ptr(e_norm2), _ptr(e_hi), _ptr(e_lo), N, K, D,
+                             float(module._commitment_cost), fl, _ptr(q_out), _ptr(idx), _ptr(onehot),
+                             sp, sp + 4 * K, _ptr(loss), _ptr(perplexity), _ptr(ws), ws.numel(), st))
+        if N == 0:   # mean over nothing: the reference yields NaN
+            loss.fill_(float("nan"))
+            perplexity.fill_(1.0)
+        ctx.save_for_backward(inputs, weight, idx)
+        ctx.module = module
+        ctx.stats = stats
+        ctx.train_vq = bool(module._train_vq)
+        if onehot is not None:
+            ctx.mark_non_differentiable(perplexity, idx, onehot)
+        else:
+            ctx.mark_non_differentiable(perplexity, idx)
+        module._last_stats = stats
+        return loss, q_out, perplexity, onehot, idx
+
+    @staticmethod
+    def backward(ctx, g_loss, g_q, _g_perp, _g_onehot, _g_idx):
+        lib = _lib.load()
+        inputs, weight, idx = ctx.saved_tensors
+        module = ctx.module
+        K, D = weight.shape
+        N = idx.shape[0]
+        dev = inputs.device
+        st = _stream()
+        need_dz = ctx.needs_input_grad[0]
+        need_dE = ctx.needs_input_grad[1] and ctx.train_vq
+        if g_loss is None:
+            g_loss = torch.zeros((), dtype=torch.float32, device=dev)
+        elif g_loss.dtype != torch.float32:
+            g_loss = g_loss.float()
+        if g_q is not None:
+            g_q = g_q.contiguous()
+            if g_q.dtype != torch.float32:
+                g_q = g_q.float()
+        pg = module.process_group
+        world = 1
+        if pg is not None or module.data_parallel:
+            import torch.distributed as dist
+            world = dist.get_world_size(pg)
+        packed = None
+        dE = None
+        if need_dE:
+            if world > 1:
+                # one all-reduce per step over [dE | hist | sse]  
+                packed = torch.zeros(K * D + K + 1, dtype=torch.float32, device=dev)
+                dE = packed[:K * D].view(K, D)
+            else:
+                dE = torch.zeros(K, D, dtype=torch.float32, device=dev)
+        dz = torch.empty_like(inputs)
+        w = weight.detach()
+        if not w.is_contiguous():
+            w = w.contiguous()
+        flags = FLAG_TRAIN_VQ if need_dE else 0
+        check(lib.vq_backward(_ptr(g_q), _ptr(g_loss), _ptr(inputs), _ptr(w), _ptr(idx), N, max(N, 1),
+                              max(N, 1) * world, K, D, float(module._commitment_cost), flags, _ptr(dz), _ptr(dE), st))
+        if packed is not None:
+            import torch.distributed as dist
+            packed[K * D:] = ctx.stats[:K + 1]
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=pg)
+            module._global_stats = (packed[K * D:], N * world)
+        return (dz if need_dz else None), dE, None, None, None
+
+
+class VectorQuantizer(nn.Module):
+    """Drop-in for the reference `VectorQuantizer` (vector_quantizer.py:8-58) on B200.
+
+    Extra keyword-only options (defaults reproduce the reference exactly):
+      return_encodings  False skips the dense (N, K) one-hot (4 K bytes per row of HBM traffic);
+                        the 4th return value is then None.  `last_indices` always holds the codes.
+      exact             True computes distances on CUDA cores in the oracle's fp32 FMA-chain order
+                        (bit-exact indices vs oracle/vq_oracle.c); False (default) uses the tcgen05
+                        3xTF32 tensor-core path whenever the shape allows (D in {32,64,96,128}, K % 128 == 0).
+      process_group     set (or `data_parallel=True` for the default group) to all-reduce the packed
+                        [dE | usage histogram | squared error] once per step across data-parallel ranks.
+    """
+
+    def __init__(self, num_embeddings, embedding_dim, commitment_cost, flag_flatten=True, *,
+                 return_encodings: bool = True, exact: bool = False, process_group=None,
+                 data_parallel: bool = False):
+        super().__init__()
+        self._embedding_dim = embedding_dim
+        self._num_embeddings = num_embeddings
+        # vector_quantizer.py:15-16: nn.Embedding then U(-1/K, 1/K)
+        self._embedding = nn.Embedding(self._num_embeddings, self._embedding_dim)
+        self._embedding.weight.data.uniform_(-1 / self._num_embeddings, 1 / self._num_embeddings)
+        self._commitment_cost = commitment_cost
+        self._train_vq = True
+        self._flag_flatten = flag_flatten
+        self.return_encodings = return_encodings
+        self.exact = exact
+        self.process_group = process_group
+        self.data_parallel = data_parallel
+        self._bufs = _Buffers()
+        self._last_stats = None
+        self._global_stats = None
+        self.last_indices = None
+
+    # -- reference accessors (vector_quantizer.py:23-27) ------------------------------------------
+    def get_embedding_dim(self):
+        return self._embedding_dim
+
+    def set_train_vq(self, train_vq):
+        self._train_vq = train_vq
+
+    # -- pickling: scratch buffers and process groups do not travel -------------------------------
+    def __getstate__(self):
+        s = dict(self.__dict__)
+        s["_bufs"] = None
+        s["_last_stats"] = None
+        s["_global_stats"] = None
+        s["last_indices"] = None
+        s["process_group"] = None
+        return s
+
+    def __setstate__(self, s):
+        self.__dict__.update(s)
+        self._bufs = _Buffers()
+
+    def forward(self, inputs):
+        if not isinstance(inputs, torch.Tensor):
+            raise TypeError("VectorQuantizer expects a tensor")
+        if not inputs.is_cuda:
+            raise RuntimeError("b200vq.VectorQuantizer runs on a B200 GPU only (no CPU fallback): "
+                               f"got a tensor on {inputs.device}")
+        if inputs.dtype != torch.float32:
+            raise RuntimeError(f"b200vq.VectorQuantizer expects float32 inputs, got {inputs.dtype}")
+        weight = self._embedding.weight
+        if weight.device != inputs.device:
+            raise RuntimeError(f"codebook on {weight.device} but inputs on {inputs.device}")
+        # vector_quantizer.py:32: `.view` raises RuntimeError for incompatible strides / sizes
+        flat = inputs.view(-1, self._embedding_dim)
+        if not flat.is_contiguous():
+            raise RuntimeError("view size is not compatible with input tensor's size and stride "
+                               "(b200vq needs a contiguous input, like the reference's .view)")
+        flags = FLAG_EXACT if self.exact else 0
+        loss, quantized, perplexity, encodings, idx = _VQFunction.apply(
+            inputs, weight, self, flags, bool(self.return_encodings))
+        self.last_indices = idx
+        return loss, quantized, perplexity, encodings
+
+    # -- extras ------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def usage_histogram(self) -> Optional[torch.Tensor]:
+        """Code usage counts (K,) of the last forward."""
+        return None if self._last_stats is None else self._last_stats[:self._num_embeddings]
+
+    @torch.no_grad()
+    def global_stats(self):
+        """(loss, perplexity) over all data-parallel ranks for the last backward; None otherwise."""
+        if self._global_stats is None:
+            return None
+        lib = _lib.load()
+        tail, n_global = self._global_stats
+        K, D = self._num_embeddings, self._embedding_dim
+        out = torch.empty(2, dtype=torch.float32, device=tail.device)
+        tail = tail.contiguous()
+        check(lib.vq_finalize_stats(tail.data_ptr(), tail.data_ptr() + 4 * K, n_global, K, D,
+                                    float(self._commitment_cost), out.data_ptr(), out.data_ptr() + 4, _stream()))
+        return out[0], out[1]
+
+    def encodings_from_indices(self, indices: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Dense (N, K) one-hot for callers that skipped it in forward (vector_quantizer.py:39-40)."""
+        lib = _lib.load()
+        idx = self.last_indices if indices is None else indices
+        idx = idx.to(torch.int32).contiguous()
+        out = torch.empty(idx.shape[0], self._num_embeddings, dtype=torch.float32, device=idx.device)
+        check(lib.vq_onehot(idx.data_ptr(), idx.shape[0], self._num_embeddings, out.data_ptr(), _stream()))
+        return out
+
+    @classmethod
+    def from_reference(cls, ref, **kw) -> "VectorQuantizer":
+        """Build from a reference `VectorQuantizer` instance (e.g. out of a torch.load'ed pickle)."""
+        new = cls(ref._num_embeddings, ref._embedding_dim, ref._commitment_cost,
+                  getattr(ref, "_flag_flatten", True), **kw)
+        new._embedding.weight.data = ref._embedding.weight.data.clone()
+        new._embedding.weight.requires_grad_(ref._embedding.weight.requires_grad)
+        new._train_vq = getattr(ref, "_train_vq", True)
+        new.train(ref.training)
+        return new.to(ref._embedding.weight.device)
+
+
+def swap_quantizers(model: nn.Module, **kw) -> int:
+    """Replace every reference-style quantizer inside `model` (`_vq` of ConvolutionalVQVAE,
+    `rir_model._vq` / `speech_model._vq` of EchoedSpeechReconModel) by the B200 one, in place.
+    Returns the number of modules swapped."""
+    n = 0
+    for name, child in list(model.named_children()):
+        if isinstance(child, VectorQuantizer):
+            continue
+        looks_like_vq = (type(child).__name__ == "VectorQuantizer" and hasattr(child, "_embedding")
+                         and hasattr(child, "_commitment_cost"))
+        if looks_like_vq:
+            setattr(model, name, VectorQuantizer.from_reference(child, **kw))
+            n += 1
+        else:
+            n += swap_quantizers(child, **kw)
+    return n

@@ -1,0 +1,125 @@
+/*
+ * b200vq.h -- C ABI of the B200-native VectorQuantizer hot path (libb200vq.so).
+ *
+ * The reference has no FFI: the hot path sits behind a Python nn.Module,
+ *   /root/reference/src/acoustic_locating_vq_vae/vq_vae/vector_quantizer.py:8-58
+ * called from convolutional_vq_vae.py:98,105.  This header is the boundary a binding for that
+ * module calls (the ctypes binding is acoustic_locating_vq-vae_b200/_lib.py; INTEGRATION.md shows
+ * the reference-side stub).  Plain pointers and sizes only; no torch types; no C++ exceptions
+ * cross the boundary.  Every function returns 0 on success or a VQ_ERR_* code, and
+ * vq_last_error() then holds a message for the calling thread.
+ *
+ * Conventions
+ *   - All matrices are fp32, row-major, contiguous.  z is (N, D): N rows of D consecutive floats,
+ *     i.e. the reference's `inputs.view(-1, D)` (vector_quantizer.py:32) -- no permute.
+ *   - E is the codebook (K, D) == `_embedding.weight` (vector_quantizer.py:15).
+ *   - Device pointers unless the name says host.  All work is enqueued on `stream`
+ *     (a cudaStream_t); nothing synchronises the host except the *_host entry points.
+ *   - The library never keeps caller memory and never allocates device memory, except inside a
+ *     vq_host_ctx (which owns its staging buffers).
+ */
+#ifndef B200VQ_H_
+#define B200VQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQ_ABI_VERSION 3
+
+/* error codes */
+#define VQ_OK            0
+#define VQ_ERR_ARG       1   /* bad shape / null pointer / misaligned pointer */
+#define VQ_ERR_CUDA      2   /* a CUDA runtime or driver call failed */
+#define VQ_ERR_NO_DEVICE 3   /* no sm_100 device: there is no CPU fallback */
+#define VQ_ERR_WORKSPACE 4   /* workspace too small */
+
+/* flags for vq_forward / vq_backward */
+#define VQ_FLAG_ONEHOT     (1 << 0)  /* forward: also write the dense (N,K) one-hot (vector_quantizer.py:39-40) */
+#define VQ_FLAG_TRAIN_VQ   (1 << 1)  /* backward: produce dE (vector_quantizer.py:47-50 `_train_vq`) */
+#define VQ_FLAG_EXACT      (1 << 2)  /* forward: CUDA-core distances in the oracle's fp32 FMA-chain order
+                                        (bit-exact vs oracle/vq_oracle.c) instead of the tcgen05 3xTF32 path */
+#define VQ_FLAG_DEFER_STATS (1 << 3) /* forward: leave loss/perplexity to vq_finalize_stats (data parallel) */
+#define VQ_FLAG_NO_QUANT   (1 << 4)  /* forward: indices/hist only; q_out, sse, loss are not produced */
+
+typedef void* vq_stream_t;   /* cudaStream_t */
+
+/* -- introspection ------------------------------------------------------------------------- */
+int         vq_abi_version(void);
+const char* vq_last_error(void);
+/* 0 when the current CUDA device is sm_100 (B200); VQ_ERR_NO_DEVICE otherwise. */
+int         vq_device_check(void);
+/* Which forward path vq_forward would take: 1 = tcgen05 tensor path, 0 = exact CUDA-core path. */
+int         vq_forward_uses_tensor_path(int64_t n_rows, int K, int D, int flags);
+/* Kernel launches issued by this library since load (all streams); bench.py's gpu_launches. */
+int64_t     vq_launch_count(void);
+
+/* -- codebook preparation (once per optimizer step: Adam changes E) ------------------------- */
+/* e_norm2[k] = |E_k|^2 (vector_quantizer.py:35) as an fp32 FMA chain over d;
+ * E_hi = tf32_rna(E), E_lo = tf32_rna(E - E_hi): the split operands of the 3xTF32 contraction.
+ * E_hi / E_lo may be NULL when only the exact path will be used. */
+int vq_prepare_codebook(const float* E, int K, int D,
+                        float* e_norm2, float* E_hi, float* E_lo, vq_stream_t stream);
+
+/* -- forward: vector_quantizer.py:29-58 ------------------------------------------------------ */
+size_t vq_workspace_bytes(int64_t n_rows, int K, int D, int flags);
+
+/* Outputs:
+ *   q_out  (N,D)  fl(z + fl(E[idx]-z))            vector_quantizer.py:43,54
+ *   idx    (N)    int32 code index, first minimum vector_quantizer.py:38
+ *   onehot (N,K)  fp32 one-hot or NULL            vector_quantizer.py:39-40   (VQ_FLAG_ONEHOT)
+ *   hist   (K)    fp32 usage counts               vector_quantizer.py:55 (mean(enc,0) * N)
+ *   sse    (1)    sum (E[idx]-z)^2                vector_quantizer.py:46-50 numerator
+ *   loss   (1)    (1+beta) * sse / (N*D)          vector_quantizer.py:52
+ *   perplexity(1) exp(-sum p log(p+1e-10))        vector_quantizer.py:56
+ * loss/perplexity are untouched under VQ_FLAG_DEFER_STATS. */
+int vq_forward(const float* z, const float* E, const float* e_norm2,
+               const float* E_hi, const float* E_lo,
+               int64_t n_rows, int K, int D, float beta, int flags,
+               float* q_out, int32_t* idx, float* onehot, float* hist, float* sse,
+               float* loss, float* perplexity,
+               void* workspace, size_t workspace_bytes, vq_stream_t stream);
+
+/* loss / perplexity from (all-reduced) usage counts and squared error over n_rows_global rows. */
+int vq_finalize_stats(const float* hist, const float* sse, int64_t n_rows_global, int K, int D,
+                      float beta, float* loss, float* perplexity, vq_stream_t stream);
+
+/* (N,K) one-hot from indices (vector_quantizer.py:39-40), for callers that ask for it late. */
+int vq_onehot(const int32_t* idx, int64_t n_rows, int K, float* onehot, vq_stream_t stream);
+
+/* -- backward: autograd of vector_quantizer.py:46-54 ----------------------------------------- */
+/*   dz[n,:]       = g_q[n,:] + g_loss*beta*2*(z - E[idx])/(n_rows_dz*D)     g_q may be NULL (zero)
+ *   dE[idx[n],:] += g_loss*2*(E[idx] - z)/(n_rows_dE*D)   when VQ_FLAG_TRAIN_VQ and dE != NULL
+ * dE must be zeroed by the caller (it is accumulated into; under data parallelism the caller
+ * all-reduces it).  g_loss is a device scalar (NULL means 1).  The straight-through output sends
+ * no gradient to E. */
+int vq_backward(const float* g_q, const float* g_loss, const float* z, const float* E,
+                const int32_t* idx, int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE,
+                int K, int D, float beta, int flags, float* dz, float* dE, vq_stream_t stream);
+
+/* -- host-buffer entry points (what a non-torch caller binds; used for the end-to-end figure) - */
+typedef struct vq_host_ctx vq_host_ctx;
+
+/* Owns device staging for up to max_rows rows, two copy/compute lanes and pinned result slots. */
+int  vq_host_ctx_create(int64_t max_rows, int K, int D, vq_host_ctx** out);
+void vq_host_ctx_destroy(vq_host_ctx* ctx);
+/* Upload the codebook (host pointer) and prepare it. */
+int  vq_host_set_codebook(vq_host_ctx* ctx, const float* E_host);
+/* One forward+backward step on host buffers: copies z (and g_q if not NULL; NULL means ones, the
+ * `(loss + quantized.sum()).backward()` workload) to the device, runs prepare/forward/backward,
+ * and copies back loss, perplexity and -- when the pointers are not NULL -- idx (N), q_out (N,D),
+ * dz (N,D), dE (K,D).  Host pointers should be pinned for full PCIe speed.  Asynchronous: the
+ * step is enqueued on lane (step_no % 2); results are valid after vq_host_wait(ctx, lane). */
+int  vq_host_step_async(vq_host_ctx* ctx, int lane, const float* z_host, const float* gq_host,
+                        int64_t n_rows, float beta, int flags,
+                        float* loss_host, float* perplexity_host, int32_t* idx_host,
+                        float* q_host, float* dz_host, float* dE_host);
+int  vq_host_wait(vq_host_ctx* ctx, int lane);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VQ_H_ */
