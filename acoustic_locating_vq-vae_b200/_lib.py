@@ -9,13 +9,14 @@ import os
 
 from .build import SO_PATH
 
-ABI_VERSION = 3
+ABI_VERSION = 5
 
 FLAG_ONEHOT = 1 << 0
 FLAG_TRAIN_VQ = 1 << 1
 FLAG_EXACT = 1 << 2
 FLAG_DEFER_STATS = 1 << 3
 FLAG_NO_QUANT = 1 << 4
+FLAG_ZERO_DE = 1 << 5
 
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -30,6 +31,8 @@ SIGNATURES = {
     "vq_device_check": (_int, []),
     "vq_forward_uses_tensor_path": (_int, [_i64, _int, _int, _int]),
     "vq_launch_count": (_i64, []),
+    "vq_profile_enable": (None, [_int]),
+    "vq_profile_read": (_int, [_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i64)]),
     "vq_prepare_codebook": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp]),
     "vq_workspace_bytes": (_sz, [_i64, _int, _int, _int]),
     "vq_forward": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _f32, _int,
@@ -40,8 +43,11 @@ SIGNATURES = {
     "vq_host_ctx_create": (_int, [_i64, _int, _int, ctypes.POINTER(_vp)]),
     "vq_host_ctx_destroy": (None, [_vp]),
     "vq_host_set_codebook": (_int, [_vp, _vp]),
-    "vq_host_step_async": (_int, [_vp, _int, _vp, _vp, _i64, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vq_host_step_async": (_int, [_vp, _int, _vp, _vp, _i64, _i64, _f32, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vq_host_timer_start": (_int, [_vp]),
+    "vq_host_timer_stop_ms": (_int, [_vp, ctypes.POINTER(_f32)]),
     "vq_host_wait": (_int, [_vp, _int]),
+    "vq_host_lane_buffers": (_int, [_vp, _int, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
 }
 
 _lib = None

@@ -10,7 +10,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
@@ -42,6 +44,34 @@ int fail(int code, const char* fmt, ...) {
         if (e__ != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
         g_launches.fetch_add(1, std::memory_order_relaxed);                                        \
     } while (0)
+
+// ---- optional per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream ------
+enum KernelId { KID_PREP = 0, KID_ARGMIN_TC, KID_ARGMIN_SIMT, KID_ROWS, KID_BACKWARD, KID_FINALIZE, KID_ONEHOT, KID_COUNT };
+struct ProfSlot { cudaEvent_t a, b; int kid; };
+bool g_prof_on = false;
+std::vector<ProfSlot> g_prof_slots;
+size_t g_prof_used = 0;
+std::mutex g_prof_mu;
+
+struct ProfScope {
+    cudaStream_t st;
+    ProfSlot* slot = nullptr;
+    ProfScope(int kid, cudaStream_t s) : st(s) {
+        if (!g_prof_on) return;
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        if (g_prof_used == g_prof_slots.size()) {
+            ProfSlot ns{};
+            if (cudaEventCreate(&ns.a) != cudaSuccess || cudaEventCreate(&ns.b) != cudaSuccess) return;
+            g_prof_slots.push_back(ns);
+        }
+        slot = &g_prof_slots[g_prof_used++];
+        slot->kid = kid;
+        cudaEventRecord(slot->a, st);
+    }
+    ~ProfScope() {
+        if (slot != nullptr) cudaEventRecord(slot->b, st);
+    }
+};
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -151,6 +181,7 @@ int launch_tc(const CUtensorMap& tz, const CUtensorMap& thi, const CUtensorMap& 
         configured = true;
     }
     dim3 grid(static_cast<unsigned>((N + TC_ROWS - 1) / TC_ROWS), static_cast<unsigned>(splits));
+    ProfScope prof(KID_ARGMIN_TC, st);
     argmin_tc_kernel<NSLAB, NSTAGE><<<grid, TC_THREADS, smem, st>>>(tz, thi, tlo, e_norm2, N, K, codes_per_split, idx,
                                                                     keys, hist, counter);
     LAUNCH_CHECK("argmin_tc_kernel");
@@ -169,6 +200,32 @@ const char* vq_last_error(void) { return g_err; }
 int vq_device_check(void) { return check_device(); }
 int64_t vq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+void vq_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+    if (on) g_prof_used = 0;
+}
+
+// total elapsed ms and launch count recorded for kernel `kid` since vq_profile_enable(1); call after a
+// device synchronise.  kid: 0 prep, 1 argmin_tc, 2 argmin_simt, 3 rows, 4 backward, 5 finalize, 6 onehot.
+int vq_profile_read(int kid, double* total_ms, int64_t* count) {
+    if (total_ms == nullptr || count == nullptr || kid < 0 || kid >= KID_COUNT) return fail(VQ_ERR_ARG, "vq_profile_read: bad argument");
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    double t = 0.0;
+    int64_t n = 0;
+    for (size_t i = 0; i < g_prof_used; ++i) {
+        if (g_prof_slots[i].kid != kid) continue;
+        float ms = 0.f;
+        cudaError_t e = cudaEventElapsedTime(&ms, g_prof_slots[i].a, g_prof_slots[i].b);
+        if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "vq_profile_read: %s (synchronise the device first)", cudaGetErrorString(e));
+        t += ms;
+        ++n;
+    }
+    *total_ms = t;
+    *count = n;
+    return VQ_OK;
+}
+
 int vq_forward_uses_tensor_path(int64_t n_rows, int K, int D, int flags) {
     return tensor_path_ok(n_rows, K, D, flags) ? 1 : 0;
 }
@@ -184,6 +241,7 @@ int vq_prepare_codebook(const float* E, int K, int D, float* e_norm2, float* E_h
     if (E == nullptr || e_norm2 == nullptr || K < 1 || D < 1) return fail(VQ_ERR_ARG, "vq_prepare_codebook: bad argument (K=%d D=%d)", K, D);
     if ((E_hi == nullptr) != (E_lo == nullptr)) return fail(VQ_ERR_ARG, "vq_prepare_codebook: E_hi and E_lo must both be given or both be NULL");
     const int blocks = (K + 7) / 8;
+    ProfScope prof(KID_PREP, static_cast<cudaStream_t>(stream));
     prep_codebook_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(E, K, D, e_norm2, E_hi, E_lo);
     LAUNCH_CHECK("prep_codebook_kernel");
     return VQ_OK;
@@ -255,6 +313,7 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
             CUDA_TRY(cudaMemsetAsync(keys, 0xFF, sizeof(unsigned long long) * N, st));
         }
         dim3 grid(static_cast<unsigned>(row_tiles), static_cast<unsigned>(splits));
+        ProfScope prof(KID_ARGMIN_SIMT, st);
         argmin_simt_kernel<<<grid, 256, 0, st>>>(z, E, e_norm2, N, K, D, cps, idx, keys, hist, counter);
         LAUNCH_CHECK("argmin_simt_kernel");
     }
@@ -263,6 +322,7 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
     const int vec_ok = (D % 4 == 0) && aligned16(z) && aligned16(E) && (!quant || aligned16(q_out));
     const int oh_vec_ok = want_onehot && (K % 4 == 0) && aligned16(onehot);
     const int fin = defer ? 0 : 1;
+    ProfScope prof_rows(KID_ROWS, st);
 #define ROWS_ARGS z, E, idx, keys, N, K, D, beta, q_out, idx, onehot, hist, partials, counter, sse, loss, perplexity, fin, vec_ok, oh_vec_ok
     if (want_onehot && quant) quantize_rows_kernel<true, true><<<w.rows_grid, 256, 0, st>>>(ROWS_ARGS);
     else if (want_onehot) quantize_rows_kernel<true, false><<<w.rows_grid, 256, 0, st>>>(ROWS_ARGS);
@@ -278,6 +338,7 @@ int vq_finalize_stats(const float* hist, const float* sse, int64_t n_rows_global
     if (int rc = check_device()) return rc;
     if (hist == nullptr || perplexity == nullptr || K < 1 || D < 1 || n_rows_global < 1)
         return fail(VQ_ERR_ARG, "vq_finalize_stats: bad argument");
+    ProfScope prof(KID_FINALIZE, static_cast<cudaStream_t>(stream));
     finalize_stats_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(hist, sse, n_rows_global, K, D, beta, loss, perplexity);
     LAUNCH_CHECK("finalize_stats_kernel");
     return VQ_OK;
@@ -288,6 +349,7 @@ int vq_onehot(const int32_t* idx, int64_t n_rows, int K, float* onehot, vq_strea
     if (idx == nullptr || onehot == nullptr || K < 1 || n_rows < 0) return fail(VQ_ERR_ARG, "vq_onehot: bad argument");
     if (n_rows == 0) return VQ_OK;
     const int vec_ok = (K % 4 == 0) && aligned16(onehot);
+    ProfScope prof(KID_ONEHOT, static_cast<cudaStream_t>(stream));
     onehot_kernel<<<rows_grid_for(n_rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(idx, n_rows, K, onehot, vec_ok);
     LAUNCH_CHECK("onehot_kernel");
     return VQ_OK;
@@ -302,13 +364,18 @@ int vq_backward(const float* g_q, const float* g_loss, const float* z, const flo
     if (z == nullptr || E == nullptr || idx == nullptr || dz == nullptr || K < 1 || D < 1 || N < 0 || n_rows_dz < 1 ||
         n_rows_dE < 1)
         return fail(VQ_ERR_ARG, "vq_backward: bad argument");
-    if (N == 0) return VQ_OK;
+    if (N == 0) {
+        if (train && (flags & VQ_FLAG_ZERO_DE)) CUDA_TRY(cudaMemsetAsync(dE, 0, sizeof(float) * static_cast<size_t>(K) * D, static_cast<cudaStream_t>(stream)));
+        return VQ_OK;
+    }
     const float denom_dz = static_cast<float>(static_cast<double>(n_rows_dz) * static_cast<double>(D));
     const float denom_dE = static_cast<float>(static_cast<double>(n_rows_dE) * static_cast<double>(D));
     const int vec_ok = (D % 4 == 0) && aligned16(z) && aligned16(E) && aligned16(dz) && (g_q == nullptr || aligned16(g_q)) &&
                        (!train || aligned16(dE));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (train && (flags & VQ_FLAG_ZERO_DE)) CUDA_TRY(cudaMemsetAsync(dE, 0, sizeof(float) * static_cast<size_t>(K) * D, st));
     const int grid = rows_grid_for(N);
+    ProfScope prof(KID_BACKWARD, st);
 #define BWD_ARGS g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, D, beta, dz, dE, vec_ok
     if (train && g_q) backward_kernel<true, true><<<grid, 256, 0, st>>>(BWD_ARGS);
     else if (train) backward_kernel<true, false><<<grid, 256, 0, st>>>(BWD_ARGS);
@@ -333,7 +400,9 @@ struct vq_host_ctx {
         void* ws;
         size_t ws_bytes;
         bool gq_is_ones;
+        cudaEvent_t ev_stop;
     } lane[2];
+    cudaEvent_t ev_start;
 };
 
 static void host_ctx_free(vq_host_ctx* c) {
@@ -342,8 +411,10 @@ static void host_ctx_free(vq_host_ctx* c) {
     for (auto& l : c->lane) {
         cudaFree(l.z); cudaFree(l.gq); cudaFree(l.q); cudaFree(l.dz); cudaFree(l.dE); cudaFree(l.hist);
         cudaFree(l.scal); cudaFree(l.idx); cudaFree(l.ws);
+        if (l.ev_stop) cudaEventDestroy(l.ev_stop);
         if (l.st) cudaStreamDestroy(l.st);
     }
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
     delete c;
 }
 
@@ -361,6 +432,7 @@ int vq_host_ctx_create(int64_t max_rows, int K, int D, vq_host_ctx** out) {
     A(reinterpret_cast<void**>(&c->E_hi), kd); A(reinterpret_cast<void**>(&c->E_lo), kd);
     for (auto& l : c->lane) {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreate(&l.ev_stop);
         A(reinterpret_cast<void**>(&l.z), nd); A(reinterpret_cast<void**>(&l.gq), nd);
         A(reinterpret_cast<void**>(&l.q), nd); A(reinterpret_cast<void**>(&l.dz), nd);
         A(reinterpret_cast<void**>(&l.dE), kd); A(reinterpret_cast<void**>(&l.hist), sizeof(float) * K);
@@ -369,6 +441,7 @@ int vq_host_ctx_create(int64_t max_rows, int K, int D, vq_host_ctx** out) {
         l.ws_bytes = vq_workspace_bytes(max_rows, K, D, 0);
         A(&l.ws, l.ws_bytes);
     }
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev_start);
     if (e != cudaSuccess) {
         host_ctx_free(c);
         return fail(VQ_ERR_CUDA, "vq_host_ctx_create: %s", cudaGetErrorString(e));
@@ -388,8 +461,8 @@ int vq_host_set_codebook(vq_host_ctx* c, const float* E_host) {
     return VQ_OK;
 }
 
-int vq_host_step_async(vq_host_ctx* c, int lane, const float* z_host, const float* gq_host, int64_t n_rows, float beta,
-                       int flags, float* loss_host, float* perplexity_host, int32_t* idx_host, float* q_host,
+int vq_host_step_async(vq_host_ctx* c, int lane, const float* z_host, const float* gq_host, int64_t n_rows,
+                       int64_t n_rows_dE, float beta, int flags, float* loss_host, float* perplexity_host, int32_t* idx_host, float* q_host,
                        float* dz_host, float* dE_host) {
     if (c == nullptr || z_host == nullptr || lane < 0 || lane > 1) return fail(VQ_ERR_ARG, "vq_host_step_async: bad argument");
     if (n_rows < 1 || n_rows > c->max_rows) return fail(VQ_ERR_ARG, "vq_host_step_async: n_rows=%lld outside [1, %lld]", (long long)n_rows, c->max_rows);
@@ -408,10 +481,9 @@ int vq_host_step_async(vq_host_ctx* c, int lane, const float* z_host, const floa
     if (int rc = vq_forward(l.z, c->E, c->e_norm2, c->E_hi, c->E_lo, n_rows, c->K, c->D, beta, flags & ~(VQ_FLAG_ONEHOT | VQ_FLAG_DEFER_STATS | VQ_FLAG_NO_QUANT),
                             l.q, l.idx, nullptr, l.hist, l.scal + 0, l.scal + 1, l.scal + 2, l.ws, l.ws_bytes, l.st))
         return rc;
-    if (train) CUDA_TRY(cudaMemsetAsync(l.dE, 0, kd, l.st));
     // gq_host == NULL: the lane's g_q buffer still holds the ones written at context creation, i.e. the
     // `(loss + quantized.sum()).backward()` workload; the kernel reads it like any upstream gradient.
-    if (int rc = vq_backward(l.gq, nullptr, l.z, c->E, l.idx, n_rows, n_rows, n_rows, c->K, c->D, beta, flags, l.dz,
+    if (int rc = vq_backward(l.gq, nullptr, l.z, c->E, l.idx, n_rows, n_rows, n_rows_dE > 0 ? n_rows_dE : n_rows, c->K, c->D, beta, flags | VQ_FLAG_ZERO_DE, l.dz,
                              train ? l.dE : nullptr, l.st))
         return rc;
     if (loss_host) CUDA_TRY(cudaMemcpyAsync(loss_host, l.scal + 1, sizeof(float), cudaMemcpyDeviceToHost, l.st));
@@ -420,6 +492,39 @@ int vq_host_step_async(vq_host_ctx* c, int lane, const float* z_host, const floa
     if (q_host) CUDA_TRY(cudaMemcpyAsync(q_host, l.q, nd, cudaMemcpyDeviceToHost, l.st));
     if (dz_host) CUDA_TRY(cudaMemcpyAsync(dz_host, l.dz, nd, cudaMemcpyDeviceToHost, l.st));
     if (dE_host && train) CUDA_TRY(cudaMemcpyAsync(dE_host, l.dE, kd, cudaMemcpyDeviceToHost, l.st));
+    return VQ_OK;
+}
+
+int vq_host_lane_buffers(vq_host_ctx* c, int lane, void** stream, float** dE, float** hist_sse) {
+    if (c == nullptr || lane < 0 || lane > 1) return fail(VQ_ERR_ARG, "vq_host_lane_buffers: bad argument");
+    if (stream) *stream = c->lane[lane].st;
+    if (dE) *dE = c->lane[lane].dE;
+    if (hist_sse) *hist_sse = c->lane[lane].hist;
+    return VQ_OK;
+}
+
+// Device-side stopwatch over both lanes: start = both lanes idle, then an event on lane 0 that lane 1 waits for;
+// stop = an event at the tail of each lane, elapsed = the later of the two.
+int vq_host_timer_start(vq_host_ctx* c) {
+    if (c == nullptr) return fail(VQ_ERR_ARG, "vq_host_timer_start: null");
+    CUDA_TRY(cudaStreamSynchronize(c->lane[0].st));
+    CUDA_TRY(cudaStreamSynchronize(c->lane[1].st));
+    CUDA_TRY(cudaEventRecord(c->ev_start, c->lane[0].st));
+    CUDA_TRY(cudaStreamWaitEvent(c->lane[1].st, c->ev_start, 0));
+    return VQ_OK;
+}
+
+int vq_host_timer_stop_ms(vq_host_ctx* c, float* ms) {
+    if (c == nullptr || ms == nullptr) return fail(VQ_ERR_ARG, "vq_host_timer_stop_ms: null");
+    float best = 0.f;
+    for (auto& l : c->lane) {
+        CUDA_TRY(cudaEventRecord(l.ev_stop, l.st));
+        CUDA_TRY(cudaEventSynchronize(l.ev_stop));
+        float t = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&t, c->ev_start, l.ev_stop));
+        if (t > best) best = t;
+    }
+    *ms = best;
     return VQ_OK;
 }
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VQ_ABI_VERSION 3
+#define VQ_ABI_VERSION 5
 
 /* error codes */
 #define VQ_OK            0
@@ -44,6 +44,7 @@ extern "C" {
                                         (bit-exact vs oracle/vq_oracle.c) instead of the tcgen05 3xTF32 path */
 #define VQ_FLAG_DEFER_STATS (1 << 3) /* forward: leave loss/perplexity to vq_finalize_stats (data parallel) */
 #define VQ_FLAG_NO_QUANT   (1 << 4)  /* forward: indices/hist only; q_out, sse, loss are not produced */
+#define VQ_FLAG_ZERO_DE    (1 << 5)  /* backward: zero dE (memset on `stream`) before accumulating into it */
 
 typedef void* vq_stream_t;   /* cudaStream_t */
 
@@ -56,6 +57,13 @@ int         vq_device_check(void);
 int         vq_forward_uses_tensor_path(int64_t n_rows, int K, int D, int flags);
 /* Kernel launches issued by this library since load (all streams); bench.py's gpu_launches. */
 int64_t     vq_launch_count(void);
+
+/* Per-kernel device timing for the roofline report: while enabled, every launch is bracketed by CUDA
+ * events on its own stream.  vq_profile_read (after a device synchronise) returns the summed elapsed
+ * time and launch count of kernel `kid`: 0 prepare, 1 tensor-core argmin, 2 exact argmin, 3 rows,
+ * 4 backward, 5 finalize, 6 one-hot. */
+void        vq_profile_enable(int on);
+int         vq_profile_read(int kid, double* total_ms, int64_t* count);
 
 /* -- codebook preparation (once per optimizer step: Adam changes E) ------------------------- */
 /* e_norm2[k] = |E_k|^2 (vector_quantizer.py:35) as an fp32 FMA chain over d;
@@ -93,8 +101,8 @@ int vq_onehot(const int32_t* idx, int64_t n_rows, int K, float* onehot, vq_strea
 /* -- backward: autograd of vector_quantizer.py:46-54 ----------------------------------------- */
 /*   dz[n,:]       = g_q[n,:] + g_loss*beta*2*(z - E[idx])/(n_rows_dz*D)     g_q may be NULL (zero)
  *   dE[idx[n],:] += g_loss*2*(E[idx] - z)/(n_rows_dE*D)   when VQ_FLAG_TRAIN_VQ and dE != NULL
- * dE must be zeroed by the caller (it is accumulated into; under data parallelism the caller
- * all-reduces it).  g_loss is a device scalar (NULL means 1).  The straight-through output sends
+ * dE is accumulated into: zero it first or pass VQ_FLAG_ZERO_DE (under data parallelism the caller
+ * all-reduces it afterwards).  g_loss is a device scalar (NULL means 1).  The straight-through output sends
  * no gradient to E. */
 int vq_backward(const float* g_q, const float* g_loss, const float* z, const float* E,
                 const int32_t* idx, int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE,
@@ -114,10 +122,17 @@ int  vq_host_set_codebook(vq_host_ctx* ctx, const float* E_host);
  * dz (N,D), dE (K,D).  Host pointers should be pinned for full PCIe speed.  Asynchronous: the
  * step is enqueued on lane (step_no % 2); results are valid after vq_host_wait(ctx, lane). */
 int  vq_host_step_async(vq_host_ctx* ctx, int lane, const float* z_host, const float* gq_host,
-                        int64_t n_rows, float beta, int flags,
+                        int64_t n_rows, int64_t n_rows_dE /* 0: n_rows; data parallel: global rows */,
+                        float beta, int flags,
                         float* loss_host, float* perplexity_host, int32_t* idx_host,
                         float* q_host, float* dz_host, float* dE_host);
 int  vq_host_wait(vq_host_ctx* ctx, int lane);
+/* Device-side stopwatch spanning both lanes (CUDA events on the lanes' own streams). */
+int  vq_host_timer_start(vq_host_ctx* ctx);
+int  vq_host_timer_stop_ms(vq_host_ctx* ctx, float* ms);
+/* Device-side handles of a lane, for callers that must all-reduce dE (K*D floats) across ranks on the
+ * lane's stream before reading it back: the stream, the dE buffer and the hist buffer (K floats). */
+int  vq_host_lane_buffers(vq_host_ctx* ctx, int lane, void** stream, float** dE, float** hist);
 
 #ifdef __cplusplus
 }
