@@ -9,7 +9,7 @@ import os
 
 from .build import SO_PATH
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 FLAG_ONEHOT = 1 << 0
 FLAG_TRAIN_VQ = 1 << 1
@@ -17,6 +17,7 @@ FLAG_EXACT = 1 << 2
 FLAG_DEFER_STATS = 1 << 3
 FLAG_NO_QUANT = 1 << 4
 FLAG_ZERO_DE = 1 << 5
+FLAG_TC_1CTA = 1 << 6
 
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64

@@ -131,14 +131,14 @@ bool tensor_path_ok(long long N, int K, int D, int flags, const float* z = nullp
 
 // number of codebook splits per row tile: fill the 148 SMs when there are few row tiles.
 // cost(s) ~ waves(s) * (code tiles per CTA + fixed per-CTA overhead of ~1 tile)
-int choose_splits(long long row_tiles, int code_tiles, int max_splits) {
+int choose_splits(long long row_tiles, int code_tiles, int max_splits, int slots = kNumSMs, double overhead = 1.0) {
     int best_s = 1;
     double best_cost = 1e30;
     for (int s = 1; s <= code_tiles && s <= max_splits; ++s) {
         if (code_tiles % s != 0) continue;
         const long long ctas = row_tiles * s;
-        const long long waves = (ctas + kNumSMs - 1) / kNumSMs;
-        const double cost = static_cast<double>(waves) * (static_cast<double>(code_tiles / s) + 1.0);
+        const long long waves = (ctas + slots - 1) / slots;
+        const double cost = static_cast<double>(waves) * (static_cast<double>(code_tiles / s) + overhead);
         if (cost < best_cost - 1e-9) {
             best_cost = cost;
             best_s = s;
@@ -152,19 +152,29 @@ struct WsLayout {
     int rows_grid;
 };
 
-int rows_grid_for(long long N) {
-    long long g = (N + 7) / 8;
-    const long long cap = static_cast<long long>(kNumSMs) * 8;   // 8 CTAs of 256 threads per SM
-    if (g > cap) g = cap;
+// rows per CTA group of the streaming kernels: 256 threads, one 16-byte (or 4-byte) element each
+int rows_per_group(int D, bool vec) {
+    const int dv = vec ? D / 4 : D;
+    int R = 256 / (dv < 1 ? 1 : dv);
+    if (R < 1) R = 1;
+    if (R > ROWS_MAX_R) R = ROWS_MAX_R;
+    return R;
+}
+
+constexpr int kMaxRowsGrid = kNumSMs * 16;   // persistent-ish: at most 16 CTAs of 256 threads per SM
+
+int rows_grid_for(long long N, int R) {
+    long long g = (N + R - 1) / R;
+    if (g > kMaxRowsGrid) g = kMaxRowsGrid;
     if (g < 1) g = 1;
     return static_cast<int>(g);
 }
 
 WsLayout ws_layout(long long N) {
     WsLayout w;
-    w.rows_grid = rows_grid_for(N);
+    w.rows_grid = 0;
     w.partials_off = 0;
-    w.counter_off = static_cast<size_t>(kNumSMs) * 8 * sizeof(double);
+    w.counter_off = static_cast<size_t>(kMaxRowsGrid) * sizeof(double);
     w.keys_off = w.counter_off + 256;
     w.total = w.keys_off + static_cast<size_t>(N) * sizeof(unsigned long long);
     return w;
@@ -185,6 +195,27 @@ int launch_tc(const CUtensorMap& tz, const CUtensorMap& thi, const CUtensorMap& 
     argmin_tc_kernel<NSLAB, NSTAGE><<<grid, TC_THREADS, smem, st>>>(tz, thi, tlo, e_norm2, N, K, codes_per_split, idx,
                                                                     keys, hist, counter);
     LAUNCH_CHECK("argmin_tc_kernel");
+    return VQ_OK;
+}
+
+template <int NSLAB, int NSTAGE, int ZBUF>
+int launch_tc2(const CUtensorMap& tz, const CUtensorMap& thi, const CUtensorMap& tlo, const float* e_norm2, long long N,
+               int K, int codes_per_split, int splits, int* idx, unsigned long long* keys, float* hist,
+               unsigned int* counter, cudaStream_t st) {
+    constexpr int smem = tc2_smem_bytes(NSLAB, NSTAGE, ZBUF);
+    static_assert(smem <= 232448, "CTA-pair kernel exceeds 227 KB of shared memory");
+    static bool configured = false;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(argmin_tc2_kernel<NSLAB, NSTAGE, ZBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const long long row_tiles = (N + TC_ROWS - 1) / TC_ROWS;
+    const long long n_items = ((row_tiles + 1) / 2) * splits;          // (row-tile pair, codebook split)
+    const int pairs = static_cast<int>(n_items < kNumSMs / 2 ? n_items : kNumSMs / 2);
+    ProfScope prof(KID_ARGMIN_TC, st);
+    argmin_tc2_kernel<NSLAB, NSTAGE, ZBUF><<<2 * pairs, TC2_THREADS, smem, st>>>(
+        tz, thi, tlo, e_norm2, N, K, codes_per_split, splits, static_cast<int>(n_items), idx, keys, hist, counter);
+    LAUNCH_CHECK("argmin_tc2_kernel");
     return VQ_OK;
 }
 
@@ -281,8 +312,11 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
     unsigned long long* keys = nullptr;
     if (tensor_path_ok(N, K, D, flags, z, E_hi, E_lo, true)) {
         const long long row_tiles = (N + TC_ROWS - 1) / TC_ROWS;
-        const int code_tiles = K / TC_CODES;
-        const int splits = choose_splits(row_tiles, code_tiles, 65535);
+        const bool pair = (K % TC2_CODES == 0) && !(flags & VQ_FLAG_TC_1CTA);
+        // CTA pairs: a wave is 74 pairs, each covering 256 rows x 256 codes per tile
+        const int code_tiles = pair ? K / TC2_CODES : K / TC_CODES;
+        const int splits = pair ? choose_splits((row_tiles + 1) / 2, code_tiles, 65535, kNumSMs / 2, 0.35)
+                                : choose_splits(row_tiles, code_tiles, 65535, kNumSMs);
         const int cps = K / splits;
         if (splits > 1) {
             keys = keys_buf;
@@ -293,12 +327,23 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
         if (int rc = make_tmap(&thi, E_hi, K, D)) return rc;
         if (int rc = make_tmap(&tlo, E_lo, K, D)) return rc;
         int rc = VQ_OK;
-        switch (D / TC_SLAB_FLOATS) {
-            case 1: rc = launch_tc<1, 8>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
-            case 2: rc = launch_tc<2, 8>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
-            case 3: rc = launch_tc<3, 6>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
-            case 4: rc = launch_tc<4, 6>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
-            default: return fail(VQ_ERR_ARG, "vq_forward: unsupported D=%d on the tensor path", D);
+        const int nslab = D / TC_SLAB_FLOATS;
+        if (pair) {
+            switch (nslab) {
+                case 1: rc = launch_tc2<1, 8, 2>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
+                case 2: rc = launch_tc2<2, 5, 2>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
+                case 3: rc = launch_tc2<3, 6, 1>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
+                case 4: rc = launch_tc2<4, 5, 1>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
+                default: return fail(VQ_ERR_ARG, "vq_forward: unsupported D=%d on the tensor path", D);
+            }
+        } else {
+            switch (nslab) {
+                case 1: rc = launch_tc<1, 8>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
+                case 2: rc = launch_tc<2, 8>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
+                case 3: rc = launch_tc<3, 6>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
+                case 4: rc = launch_tc<4, 6>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
+                default: return fail(VQ_ERR_ARG, "vq_forward: unsupported D=%d on the tensor path", D);
+            }
         }
         if (rc) return rc;
     } else {
@@ -319,15 +364,23 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
     }
 
     // ---- 2. rows: gather / straight-through value / SSE / histogram / one-hot / loss / perplexity ----------
-    const int vec_ok = (D % 4 == 0) && aligned16(z) && aligned16(E) && (!quant || aligned16(q_out));
+    const bool vec = (D % 4 == 0) && aligned16(z) && aligned16(E) && (!quant || aligned16(q_out));
     const int oh_vec_ok = want_onehot && (K % 4 == 0) && aligned16(onehot);
     const int fin = defer ? 0 : 1;
+    const int R = rows_per_group(D, vec);
+    const int rgrid = rows_grid_for(N, R);
     ProfScope prof_rows(KID_ROWS, st);
-#define ROWS_ARGS z, E, idx, keys, N, K, D, beta, q_out, idx, onehot, hist, partials, counter, sse, loss, perplexity, fin, vec_ok, oh_vec_ok
-    if (want_onehot && quant) quantize_rows_kernel<true, true><<<w.rows_grid, 256, 0, st>>>(ROWS_ARGS);
-    else if (want_onehot) quantize_rows_kernel<true, false><<<w.rows_grid, 256, 0, st>>>(ROWS_ARGS);
-    else if (quant) quantize_rows_kernel<false, true><<<w.rows_grid, 256, 0, st>>>(ROWS_ARGS);
-    else quantize_rows_kernel<false, false><<<w.rows_grid, 256, 0, st>>>(ROWS_ARGS);
+#define ROWS_ARGS z, E, idx, keys, N, K, D, beta, q_out, idx, onehot, hist, partials, counter, sse, loss, perplexity, fin, R, oh_vec_ok
+#define ROWS_LAUNCH(OH, QU)                                                                      \
+    do {                                                                                         \
+        if (vec) quantize_rows_kernel<OH, QU, 4><<<rgrid, 256, 0, st>>>(ROWS_ARGS);              \
+        else quantize_rows_kernel<OH, QU, 1><<<rgrid, 256, 0, st>>>(ROWS_ARGS);                  \
+    } while (0)
+    if (want_onehot && quant) ROWS_LAUNCH(true, true);
+    else if (want_onehot) ROWS_LAUNCH(true, false);
+    else if (quant) ROWS_LAUNCH(false, true);
+    else ROWS_LAUNCH(false, false);
+#undef ROWS_LAUNCH
 #undef ROWS_ARGS
     LAUNCH_CHECK("quantize_rows_kernel");
     return VQ_OK;
@@ -350,7 +403,7 @@ int vq_onehot(const int32_t* idx, int64_t n_rows, int K, float* onehot, vq_strea
     if (n_rows == 0) return VQ_OK;
     const int vec_ok = (K % 4 == 0) && aligned16(onehot);
     ProfScope prof(KID_ONEHOT, static_cast<cudaStream_t>(stream));
-    onehot_kernel<<<rows_grid_for(n_rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(idx, n_rows, K, onehot, vec_ok);
+    onehot_kernel<<<rows_grid_for(n_rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(idx, n_rows, K, onehot, vec_ok);
     LAUNCH_CHECK("onehot_kernel");
     return VQ_OK;
 }
@@ -370,17 +423,26 @@ int vq_backward(const float* g_q, const float* g_loss, const float* z, const flo
     }
     const float denom_dz = static_cast<float>(static_cast<double>(n_rows_dz) * static_cast<double>(D));
     const float denom_dE = static_cast<float>(static_cast<double>(n_rows_dE) * static_cast<double>(D));
-    const int vec_ok = (D % 4 == 0) && aligned16(z) && aligned16(E) && aligned16(dz) && (g_q == nullptr || aligned16(g_q)) &&
-                       (!train || aligned16(dE));
+    const bool vec = (D % 4 == 0) && aligned16(z) && aligned16(E) && aligned16(dz) && (g_q == nullptr || aligned16(g_q)) &&
+                     (!train || aligned16(dE));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (train && (flags & VQ_FLAG_ZERO_DE)) CUDA_TRY(cudaMemsetAsync(dE, 0, sizeof(float) * static_cast<size_t>(K) * D, st));
-    const int grid = rows_grid_for(N);
+    const long long n_el = N * (vec ? D / 4 : D);
+    long long g = (n_el + 255) / 256;
+    if (g > kNumSMs * 32) g = kNumSMs * 32;
+    const int grid = static_cast<int>(g);
     ProfScope prof(KID_BACKWARD, st);
-#define BWD_ARGS g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, D, beta, dz, dE, vec_ok
-    if (train && g_q) backward_kernel<true, true><<<grid, 256, 0, st>>>(BWD_ARGS);
-    else if (train) backward_kernel<true, false><<<grid, 256, 0, st>>>(BWD_ARGS);
-    else if (g_q) backward_kernel<false, true><<<grid, 256, 0, st>>>(BWD_ARGS);
-    else backward_kernel<false, false><<<grid, 256, 0, st>>>(BWD_ARGS);
+#define BWD_ARGS g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, D, beta, dz, dE
+#define BWD_LAUNCH(TR, GQ)                                                               \
+    do {                                                                                 \
+        if (vec) backward_kernel<TR, GQ, 4><<<grid, 256, 0, st>>>(BWD_ARGS);             \
+        else backward_kernel<TR, GQ, 1><<<grid, 256, 0, st>>>(BWD_ARGS);                 \
+    } while (0)
+    if (train && g_q) BWD_LAUNCH(true, true);
+    else if (train) BWD_LAUNCH(true, false);
+    else if (g_q) BWD_LAUNCH(false, true);
+    else BWD_LAUNCH(false, false);
+#undef BWD_LAUNCH
 #undef BWD_ARGS
     LAUNCH_CHECK("backward_kernel");
     return VQ_OK;

@@ -28,23 +28,24 @@ __global__ void __launch_bounds__(256) prep_codebook_kernel(const float* __restr
     const int lane = threadIdx.x & 31;
     if (warp >= K) return;
     const float* row = E + static_cast<size_t>(warp) * D;
-    if (E_hi != nullptr) {
-        for (int d = lane; d < D; d += 32) {
-            const float v = row[d];
+    // |E_k|^2 as ONE sequential FMA chain over d (the order oracle/vq_oracle.c:norm2_chain fixes): the row is
+    // loaded coalesced, each element is broadcast by shuffle, and every lane carries the same chain.
+    float acc = 0.0f;
+    for (int d0 = 0; d0 < D; d0 += 32) {
+        const int d = d0 + lane;
+        const float v = d < D ? row[d] : 0.0f;
+        if (E_hi != nullptr && d < D) {
             const float hi = tf32_rna(v);
             E_hi[static_cast<size_t>(warp) * D + d] = hi;
             E_lo[static_cast<size_t>(warp) * D + d] = tf32_rna(v - hi);
         }
-    }
-    if (lane == 0) {
-        // sequential FMA chain: the order oracle/vq_oracle.c:norm2_chain fixes
-        float acc = 0.0f;
-        for (int d = 0; d < D; ++d) {
-            const float v = row[d];
-            acc = fmaf(v, v, acc);
+        const int n = min(32, D - d0);
+        for (int l = 0; l < n; ++l) {
+            const float x = __shfl_sync(0xffffffffu, v, l);
+            acc = fmaf(x, x, acc);
         }
-        e_norm2[warp] = acc;
     }
+    if (lane == 0) e_norm2[warp] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -161,73 +162,93 @@ __global__ void __launch_bounds__(256) argmin_simt_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// rows: one warp per row, lanes along D.  HBM-bound streaming kernel.
-//   q_out = fl(z + fl(E[idx] - z)); sse += (E[idx]-z)^2; hist[idx] += 1; optional one-hot row.
+// rows: HBM-bound streaming kernel.  A CTA takes groups of R consecutive rows; every thread owns one
+// 16-byte (or 4-byte) element of the group, so all lanes are busy for any D and the loads of a whole
+// group are in flight together:
+//   phase 1  q_out = fl(z + fl(E[idx] - z)); sse += (E[idx]-z)^2; hist[idx] += 1
+//   phase 2  the R one-hot rows (K floats each), coalesced 16-byte streaming stores
 // The last CTA to finish reduces the per-CTA partial sums in a fixed order and (unless deferred)
 // writes loss and perplexity, so a single-GPU forward needs no further launch.
 // ---------------------------------------------------------------------------------------------
-template <bool ONEHOT, bool QUANT>
+constexpr int ROWS_MAX_R = 64;
+
+template <bool ONEHOT, bool QUANT, int VEC>
 __global__ void __launch_bounds__(256) quantize_rows_kernel(
     const float* __restrict__ z, const float* __restrict__ E, const int* __restrict__ idx_in,
     const unsigned long long* __restrict__ keys, long long N, int K, int D, float beta, float* __restrict__ q_out,
     int* __restrict__ idx_out, float* __restrict__ onehot, float* __restrict__ hist, double* __restrict__ partials,
     unsigned int* __restrict__ counter, float* __restrict__ sse_out, float* __restrict__ loss,
-    float* __restrict__ perplexity, int finalize, int vec_ok, int onehot_vec_ok) {
+    float* __restrict__ perplexity, int finalize, int R, int onehot_vec_ok) {
     __shared__ double red[8];
     __shared__ bool is_last;
+    __shared__ int s_idx[ROWS_MAX_R];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long long warp0 = static_cast<long long>(blockIdx.x) * 8 + wib;
-    const long long nwarps = static_cast<long long>(gridDim.x) * 8;
+    const int DV = D / VEC;                 // elements (of VEC floats) per row
+    const long long n_groups = (N + R - 1) / R;
     float sse = 0.0f;
-    for (long long r = warp0; r < N; r += nwarps) {
-        int code;
-        if (keys != nullptr) {
-            code = static_cast<int>(keys[r] & 0xffffffffu);
-            if (lane == 0) idx_out[r] = code;
-        } else {
-            code = idx_in[r];
+    for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const long long row0 = grp * R;
+        const int rows_here = static_cast<int>(min(static_cast<long long>(R), N - row0));
+        if (threadIdx.x < rows_here) {
+            const long long r = row0 + threadIdx.x;
+            int code;
+            if (keys != nullptr) {
+                code = static_cast<int>(keys[r] & 0xffffffffu);
+                idx_out[r] = code;
+            } else {
+                code = idx_in[r];
+            }
+            s_idx[threadIdx.x] = code;
+            atomicAdd(hist + code, 1.0f);
         }
-        if (lane == 0) atomicAdd(hist + code, 1.0f);
+        __syncthreads();
         if (QUANT) {
-            const float* zr = z + r * D;
-            const float* er = E + static_cast<size_t>(code) * D;
-            float* qr = q_out + r * D;
-            if (vec_ok) {
-                for (int c = lane; c < (D >> 2); c += 32) {
-                    const float4 zv = __ldcs(reinterpret_cast<const float4*>(zr) + c);
-                    const float4 ev = __ldg(reinterpret_cast<const float4*>(er) + c);
+            const int n_el = rows_here * DV;
+            for (int e = threadIdx.x; e < n_el; e += 256) {
+                const int rr = e / DV, c = e - rr * DV;
+                const int code = s_idx[rr];
+                if (VEC == 4) {
+                    const float4 zv = __ldcs(reinterpret_cast<const float4*>(z + (row0 + rr) * D) + c);
+                    const float4 ev = __ldg(reinterpret_cast<const float4*>(E + static_cast<size_t>(code) * D) + c);
                     float4 df, qv;
                     df.x = ev.x - zv.x; df.y = ev.y - zv.y; df.z = ev.z - zv.z; df.w = ev.w - zv.w;
                     qv.x = zv.x + df.x; qv.y = zv.y + df.y; qv.z = zv.z + df.z; qv.w = zv.w + df.w;
-                    __stcs(reinterpret_cast<float4*>(qr) + c, qv);
+                    __stcs(reinterpret_cast<float4*>(q_out + (row0 + rr) * D) + c, qv);
                     sse = fmaf(df.x, df.x, sse); sse = fmaf(df.y, df.y, sse);
                     sse = fmaf(df.z, df.z, sse); sse = fmaf(df.w, df.w, sse);
-                }
-            } else {
-                for (int d = lane; d < D; d += 32) {
-                    const float zv = zr[d];
-                    const float df = __ldg(er + d) - zv;
-                    qr[d] = zv + df;
+                } else {
+                    const float zv = z[(row0 + rr) * D + c];
+                    const float df = __ldg(E + static_cast<size_t>(code) * D + c) - zv;
+                    q_out[(row0 + rr) * D + c] = zv + df;
                     sse = fmaf(df, df, sse);
                 }
             }
         }
         if (ONEHOT) {
-            float* orow = onehot + r * K;
             if (onehot_vec_ok) {
-                for (int c = lane; c < (K >> 2); c += 32) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (c == (code >> 2)) {
-                        const int w = code & 3;
-                        v.x = w == 0 ? 1.f : 0.f; v.y = w == 1 ? 1.f : 0.f;
-                        v.z = w == 2 ? 1.f : 0.f; v.w = w == 3 ? 1.f : 0.f;
+                const int KV = K >> 2;
+                for (int rr = 0; rr < rows_here; ++rr) {
+                    const int code = s_idx[rr];
+                    float4* orow = reinterpret_cast<float4*>(onehot + (row0 + rr) * K);
+                    for (int c = threadIdx.x; c < KV; c += 256) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (c == (code >> 2)) {
+                            const int w = code & 3;
+                            v.x = w == 0 ? 1.f : 0.f; v.y = w == 1 ? 1.f : 0.f;
+                            v.z = w == 2 ? 1.f : 0.f; v.w = w == 3 ? 1.f : 0.f;
+                        }
+                        __stcs(orow + c, v);
                     }
-                    __stcs(reinterpret_cast<float4*>(orow) + c, v);
                 }
             } else {
-                for (int k = lane; k < K; k += 32) orow[k] = (k == code) ? 1.0f : 0.0f;
+                for (int rr = 0; rr < rows_here; ++rr) {
+                    const int code = s_idx[rr];
+                    float* orow = onehot + (row0 + rr) * K;
+                    for (int k = threadIdx.x; k < K; k += 256) orow[k] = (k == code) ? 1.0f : 0.0f;
+                }
             }
         }
+        __syncthreads();   // s_idx is reused by the next group
     }
     // block partial (double), then last-CTA-done reduction in a fixed order
     double s = warp_sum_d(static_cast<double>(sse));
@@ -333,52 +354,47 @@ __global__ void __launch_bounds__(256) onehot_kernel(const int* __restrict__ idx
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward: one warp per row.  dz = g_q - cz*(q - z);  dE[idx] += ce*(q - z)  (red.global.add)
+// backward: flat grid-stride over 16-byte elements (thread = one float4 of one row), HBM-bound.
+//   dz = g_q - cz*(q - z);  dE[idx] += ce*(q - z)  (red.global.add, 16 bytes per request)
 //   cz = g_loss*beta*2/(n_rows_dz*D), ce = g_loss*2/(n_rows_dE*D)   -- oracle/vq_oracle.c order
 // ---------------------------------------------------------------------------------------------
-template <bool TRAIN_VQ, bool HAS_GQ>
+template <bool TRAIN_VQ, bool HAS_GQ, int VEC>
 __global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__ g_q, const float* __restrict__ g_loss,
                                                        const float* __restrict__ z, const float* __restrict__ E,
                                                        const int* __restrict__ idx, long long N, float denom_dz,
                                                        float denom_dE, int D, float beta, float* __restrict__ dz,
-                                                       float* __restrict__ dE, int vec_ok) {
-    const int lane = threadIdx.x & 31;
-    const long long warp0 = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-    const long long nwarps = static_cast<long long>(gridDim.x) * 8;
+                                                       float* __restrict__ dE) {
     const float gl = g_loss != nullptr ? __ldg(g_loss) : 1.0f;
     const float cz = gl * beta * 2.0f / denom_dz;
     const float ce = gl * 2.0f / denom_dE;
-    for (long long r = warp0; r < N; r += nwarps) {
-        const int code = idx[r];
-        const float* zr = z + r * D;
-        const float* er = E + static_cast<size_t>(code) * D;
-        float* dzr = dz + r * D;
-        float* der = TRAIN_VQ ? dE + static_cast<size_t>(code) * D : nullptr;
-        if (vec_ok) {
-            for (int c = lane; c < (D >> 2); c += 32) {
-                const float4 zv = __ldcs(reinterpret_cast<const float4*>(zr) + c);
-                const float4 ev = __ldg(reinterpret_cast<const float4*>(er) + c);
-                float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (HAS_GQ) gv = __ldcs(reinterpret_cast<const float4*>(g_q + r * D) + c);
-                float4 df, o;
-                df.x = ev.x - zv.x; df.y = ev.y - zv.y; df.z = ev.z - zv.z; df.w = ev.w - zv.w;
-                o.x = fmaf(-cz, df.x, gv.x); o.y = fmaf(-cz, df.y, gv.y);
-                o.z = fmaf(-cz, df.z, gv.z); o.w = fmaf(-cz, df.w, gv.w);
-                __stcs(reinterpret_cast<float4*>(dzr) + c, o);
-                if (TRAIN_VQ) {
-                    float4 a;
-                    a.x = ce * df.x; a.y = ce * df.y; a.z = ce * df.z; a.w = ce * df.w;
-                    atomicAdd(reinterpret_cast<float4*>(der) + c, a);
-                }
+    const int DV = D / VEC;
+    const long long n_el = N * DV;
+    const long long stride = static_cast<long long>(gridDim.x) * 256;
+    for (long long e = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; e < n_el; e += stride) {
+        const long long r = e / DV;
+        const int c = static_cast<int>(e - r * DV);
+        const int code = __ldg(idx + r);
+        if (VEC == 4) {
+            const float4 zv = __ldcs(reinterpret_cast<const float4*>(z) + e);
+            const float4 ev = __ldg(reinterpret_cast<const float4*>(E + static_cast<size_t>(code) * D) + c);
+            float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (HAS_GQ) gv = __ldcs(reinterpret_cast<const float4*>(g_q) + e);
+            float4 df, o;
+            df.x = ev.x - zv.x; df.y = ev.y - zv.y; df.z = ev.z - zv.z; df.w = ev.w - zv.w;
+            o.x = fmaf(-cz, df.x, gv.x); o.y = fmaf(-cz, df.y, gv.y);
+            o.z = fmaf(-cz, df.z, gv.z); o.w = fmaf(-cz, df.w, gv.w);
+            __stcs(reinterpret_cast<float4*>(dz) + e, o);
+            if (TRAIN_VQ) {
+                float4 a;
+                a.x = ce * df.x; a.y = ce * df.y; a.z = ce * df.z; a.w = ce * df.w;
+                atomicAdd(reinterpret_cast<float4*>(dE + static_cast<size_t>(code) * D) + c, a);
             }
         } else {
-            for (int d = lane; d < D; d += 32) {
-                const float zv = zr[d];
-                const float df = __ldg(er + d) - zv;
-                const float gv = HAS_GQ ? g_q[r * D + d] : 0.0f;
-                dzr[d] = fmaf(-cz, df, gv);
-                if (TRAIN_VQ) atomicAdd(der + d, ce * df);
-            }
+            const float zv = z[e];
+            const float df = __ldg(E + static_cast<size_t>(code) * D + c) - zv;
+            const float gv = HAS_GQ ? g_q[e] : 0.0f;
+            dz[e] = fmaf(-cz, df, gv);
+            if (TRAIN_VQ) atomicAdd(dE + static_cast<size_t>(code) * D + c, ce * df);
         }
     }
 }

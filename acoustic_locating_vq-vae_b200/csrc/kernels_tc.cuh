@@ -242,4 +242,326 @@ argmin_tc_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
     }
 }
 
+
+// =========================================================================================================
+// Persistent CTA-pair kernel (cta_group::2): the production tensor path.
+//
+// Why a pair: with both operands in shared memory one M=128,N=128,K=8 TF32 MMA reads 8 KB in 64 cycles =
+// 128 B/clk, i.e. ALL of one SM's shared-memory bandwidth, before the TMA writes that refill the ring
+// (measured: tensor pipe 38 % active).  In a pair, one UMMA is M=256 (128 rows of z from each CTA) x N=256
+// (128 codes of E from each CTA): per SM 8 KB per 128 cycles, and every E tile leaves L2 once per 256 rows.
+// Why persistent: at K=1024, D=64 a row tile is only ~6 us of MMA work; launching a CTA per tile paid
+// ~9 us of prologue/epilogue around it.  Here 74 pairs loop over work items (row-tile pair x codebook split)
+// and every stage of the pipeline runs ahead across items.
+//
+//   cluster (2,1,1): CTA r of a pair owns rows [(2*rtp + r)*128, +128) of the item and, per code tile of
+//   256, stages the codes [k0 + r*128, +128).
+//   warp 0        E producer: TMA ring of NSTAGE 16 KB slabs (E_lo slabs, then E_hi slabs, per code tile)
+//   warp 1        MMA issuer (leader CTA only): tcgen05.mma.cta_group::2.kind::tf32, M=256 N=256 K=8
+//   warps 2-3     z pipeline: TMA the raw z tile, |z_n|^2 chain, in-place tf32 hi/lo split, publish
+//   warps 4-11    epilogue: warp w reads TMEM lanes 32*(w%4).. and columns [128*(w>=8), +128) with
+//                 double-buffered tcgen05.ld; distance in the reference's order; 4 running minima per thread
+//   barriers      z_full/z_free/a_ready (per CTA), z_ready (leader, both CTAs' converters arrive),
+//                 full (leader; both CTAs' TMA complete_tx), empty / acc_full (per CTA, multicast commit),
+//                 acc_empty (leader; one arrival per epilogue warp of both CTAs)
+//   TMEM          2 x 256 columns (double-buffered accumulator), cta_group::2 allocation by both CTAs
+// =========================================================================================================
+constexpr int TC2_CODES = 256;     // codes per accumulator tile (UMMA N); each CTA stages 128 of them
+constexpr int TC2_TMEM_COLS = 512;
+constexpr int TC2_THREADS = 384;
+constexpr int TC2_ARING = 4;       // ring of |z_n|^2 vectors (one per in-flight item)
+
+__host__ __device__ constexpr int tc2_smem_bytes(int nslab, int nstage, int zbuf) {
+    return zbuf * 2 * nslab * TC_SLAB_BYTES + nstage * TC_SLAB_BYTES + 2 * TC2_CODES * 4 /* b tile */ +
+           TC2_ARING * TC_ROWS * 4 /* a ring */ + 2 * TC_ROWS * 8 /* merge */ + 512 /* barriers */ + 1024 /* align */;
+}
+
+template <int NSLAB, int NSTAGE, int ZBUF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
+argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_ehi,
+                  const __grid_constant__ CUtensorMap tm_elo, const float* __restrict__ e_norm2, long long N, int K,
+                  int codes_per_split, int splits, int n_items, int* __restrict__ idx_out,
+                  unsigned long long* __restrict__ keys, float* __restrict__ hist_to_zero,
+                  unsigned int* __restrict__ counter_to_zero) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int ZBYTES = 2 * NSLAB * TC_SLAB_BYTES;          // one z buffer: hi then lo
+    uint8_t* zbufs = smem;
+    uint8_t* stages = zbufs + ZBUF * ZBYTES;
+    float* b_tile = reinterpret_cast<float*>(stages + NSTAGE * TC_SLAB_BYTES);   // [2][256]
+    float* a_ring = b_tile + 2 * TC2_CODES;                                      // [TC2_ARING][128]
+    unsigned long long* merge = reinterpret_cast<unsigned long long*>(a_ring + TC2_ARING * TC_ROWS);   // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(merge + 2 * TC_ROWS);
+    uint64_t* bar_z_full = bars;                        // [ZBUF]
+    uint64_t* bar_z_free = bar_z_full + ZBUF;           // [ZBUF]
+    uint64_t* bar_z_ready = bar_z_free + ZBUF;          // [ZBUF]  (leader side)
+    uint64_t* bar_a_ready = bar_z_ready + ZBUF;         // [TC2_ARING]
+    uint64_t* bar_full = bar_a_ready + TC2_ARING;       // [NSTAGE] (leader side)
+    uint64_t* bar_empty = bar_full + NSTAGE;            // [NSTAGE]
+    uint64_t* bar_acc_full = bar_empty + NSTAGE;        // [2]
+    uint64_t* bar_acc_empty = bar_acc_full + 2;         // [2]      (leader side)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int n_ctiles = codes_per_split / TC2_CODES;
+
+    if (blockIdx.x == 0) {
+        for (int k = threadIdx.x; k < K; k += TC2_THREADS) hist_to_zero[k] = 0.0f;
+        if (threadIdx.x == 0) *counter_to_zero = 0u;
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_z);
+        tma_prefetch_desc(&tm_ehi);
+        tma_prefetch_desc(&tm_elo);
+        for (int i = 0; i < ZBUF; ++i) {
+            mbar_init(bar_z_full + i, 1);
+            mbar_init(bar_z_free + i, 1);
+            mbar_init(bar_z_ready + i, 128);      // 64 converter threads of each CTA
+        }
+        for (int i = 0; i < TC2_ARING; ++i) mbar_init(bar_a_ready + i, 64);
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(bar_full + s, 1);
+            mbar_init(bar_empty + s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_acc_full + b, 1);
+            mbar_init(bar_acc_empty + b, 16);     // 8 epilogue warps of each CTA
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_2sm(tmem_slot, TC2_TMEM_COLS);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== E producer (both CTAs: each loads its 128-code half of every tile) =====
+        if (lane == 0) {
+            int L = 0;
+            for (int w = pair; w < n_items; w += n_pairs) {
+                const int k_begin = (w % splits) * codes_per_split;
+                for (int ct = 0; ct < n_ctiles; ++ct) {
+                    for (int i = 0; i < 2 * NSLAB; ++i, ++L) {
+                        const int stage = L % NSTAGE;
+                        mbar_wait(bar_empty + stage, ((L / NSTAGE) & 1) ^ 1);
+                        const bool lo = i < NSLAB;
+                        const int slab = lo ? i : i - NSLAB;
+                        if (leader) mbar_arrive_expect_tx(bar_full + stage, 2 * TC_SLAB_BYTES);
+                        tma_load_2d_2sm(stages + stage * TC_SLAB_BYTES, lo ? &tm_elo : &tm_ehi, bar_full + stage,
+                                        slab * TC_SLAB_FLOATS, k_begin + ct * TC2_CODES + static_cast<int>(cta_rank) * TC_ROWS);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(2 * TC_ROWS, TC2_CODES);
+            int L = 0, ctg = 0, it = 0;
+            for (int w = pair; w < n_items; w += n_pairs, ++it) {
+                const int zb = it % ZBUF;
+                mbar_wait(bar_z_ready + zb, (it / ZBUF) & 1);
+                tc_fence_after();
+                const uint32_t zhi_addr = smem_u32(zbufs + zb * ZBYTES);
+                const uint32_t zlo_addr = zhi_addr + NSLAB * TC_SLAB_BYTES;
+                for (int ct = 0; ct < n_ctiles; ++ct, ++ctg) {
+                    const int buf = ctg & 1;
+                    mbar_wait(bar_acc_empty + buf, ((ctg >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * TC2_CODES;
+                    uint32_t accumulate = 0;
+                    for (int i = 0; i < 2 * NSLAB; ++i, ++L) {
+                        const int stage = L % NSTAGE;
+                        mbar_wait(bar_full + stage, (L / NSTAGE) & 1);
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_u32(stages + stage * TC_SLAB_BYTES);
+                        if (i < NSLAB) {   // z_hi . E_lo
+                            const uint32_t a_addr = zhi_addr + i * TC_SLAB_BYTES;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                tc_mma_tf32_2sm(d_tmem, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32),
+                                                idesc, accumulate);
+                                accumulate = 1;
+                            }
+                        } else {           // z_lo . E_hi, then z_hi . E_hi
+                            const int s = i - NSLAB;
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                tc_mma_tf32_2sm(d_tmem, umma_desc_sw128(zlo_addr + s * TC_SLAB_BYTES + kk * 32),
+                                                umma_desc_sw128(b_addr + kk * 32), idesc, 1);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                tc_mma_tf32_2sm(d_tmem, umma_desc_sw128(zhi_addr + s * TC_SLAB_BYTES + kk * 32),
+                                                umma_desc_sw128(b_addr + kk * 32), idesc, 1);
+                        }
+                        tc_commit_2sm(bar_empty + stage);
+                    }
+                    tc_commit_2sm(bar_acc_full + buf);
+                }
+                tc_commit_2sm(bar_z_free + zb);    // every MMA that reads this z buffer has completed
+            }
+        }
+    } else if (warp < 4) {
+        // ===== z pipeline (64 threads per CTA): TMA, |z_n|^2, hi/lo split, publish =====
+        const int c = threadIdx.x - 64;            // 0..63
+        int it = 0;
+        for (int w = pair; w < n_items; w += n_pairs, ++it) {
+            const int zb = it % ZBUF;
+            const int row_tile = 2 * (w / splits) + static_cast<int>(cta_rank);
+            uint8_t* z_hi = zbufs + zb * ZBYTES;
+            uint8_t* z_lo = z_hi + NSLAB * TC_SLAB_BYTES;
+            if (c == 0) {
+                mbar_wait(bar_z_free + zb, ((it / ZBUF) & 1) ^ 1);
+                mbar_arrive_expect_tx(bar_z_full + zb, NSLAB * TC_SLAB_BYTES);
+                for (int s = 0; s < NSLAB; ++s)
+                    tma_load_2d(z_hi + s * TC_SLAB_BYTES, &tm_z, bar_z_full + zb, s * TC_SLAB_FLOATS, row_tile * TC_ROWS);
+            }
+            mbar_wait(bar_z_full + zb, (it / ZBUF) & 1);
+            // |z_n|^2: thread c owns rows c and c+64 (sequential FMA chains over d)
+            float* a_dst = a_ring + (it % TC2_ARING) * TC_ROWS;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = c + h * 64;
+                const uint8_t* rowp = z_hi + (r >> 3) * 1024 + (r & 7) * 128;
+                float a = 0.0f;
+#pragma unroll
+                for (int s = 0; s < NSLAB; ++s) {
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch) {   // logical 16-byte chunk ch lives at physical chunk ch ^ (r & 7)
+                        const float4 v = *reinterpret_cast<const float4*>(rowp + s * TC_SLAB_BYTES + ((ch ^ (r & 7)) << 4));
+                        a = fmaf(v.x, v.x, a);
+                        a = fmaf(v.y, v.y, a);
+                        a = fmaf(v.z, v.z, a);
+                        a = fmaf(v.w, v.w, a);
+                    }
+                }
+                a_dst[r] = a;
+            }
+            named_bar_sync(3, 64);                  // all |z|^2 reads of the raw tile are done before it is overwritten
+            float4* hi4 = reinterpret_cast<float4*>(z_hi);
+            float4* lo4 = reinterpret_cast<float4*>(z_lo);
+            constexpr int NV = NSLAB * TC_SLAB_BYTES / 16;
+#pragma unroll 4
+            for (int i = c; i < NV; i += 64) {
+                const float4 v = hi4[i];
+                float4 h, l;
+                h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+                l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+                hi4[i] = h;
+                lo4[i] = l;
+            }
+            fence_proxy_async_smem();               // generic-proxy writes -> visible to the MMA's async-proxy reads
+            mbar_arrive(bar_a_ready + (it % TC2_ARING));
+            mbar_arrive_cluster(bar_z_ready + zb, 0);
+        }
+        // drain: the leader's last multicast commits on z_free must have landed before this CTA may exit
+        if (c == 0) {
+            for (int j = it > ZBUF ? it - ZBUF : 0; j < it; ++j) mbar_wait(bar_z_free + (j % ZBUF), (j / ZBUF) & 1);
+        }
+    } else {
+        // ===== epilogue (8 warps per CTA): thread = (row, column half) =====
+        const int ew = warp - 4;                    // 0..7
+        const int half = ew >> 2;                   // columns [128*half, +128) of every code tile
+        const int row = (ew & 3) * 32 + lane;       // TMEM lane == row of the CTA's 128-row tile
+        const int et = threadIdx.x - 128;           // 0..255
+        const uint32_t lane_base = static_cast<uint32_t>((ew & 3) * 32) << 16;
+        int it = 0, ctg = 0;
+        for (int w = pair; w < n_items; w += n_pairs, ++it) {
+            const int k_begin = (w % splits) * codes_per_split;
+            const int row_tile = 2 * (w / splits) + static_cast<int>(cta_rank);
+            mbar_wait(bar_a_ready + (it % TC2_ARING), (it / TC2_ARING) & 1);
+            const float a_n = a_ring[(it % TC2_ARING) * TC_ROWS + row];
+            float best[4];
+            int best_k[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                best[q] = INFINITY;
+                best_k[q] = k_begin;
+            }
+            for (int ct = 0; ct < n_ctiles; ++ct, ++ctg) {
+                const int buf = ctg & 1;
+                const int k0 = k_begin + ct * TC2_CODES;
+                b_tile[buf * TC2_CODES + et] = __ldg(e_norm2 + k0 + et);
+                named_bar_sync(1, 256);
+                mbar_wait(bar_acc_full + buf, (ctg >> 1) & 1);
+                tc_fence_after();
+                const uint32_t t_addr = tmem_base + lane_base + buf * TC2_CODES + half * 128;
+                const float4* b4 = reinterpret_cast<const float4*>(b_tile + buf * TC2_CODES + half * 128);
+                uint32_t va[32], vb[32];
+                tmem_ld_32x32b_x32(t_addr, va);
+                auto consume = [&](const uint32_t (&v)[32], int cc) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 b = b4[cc * 8 + j4];
+                        const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float tsum = a_n + bb[q];                                    // fl(|z|^2 + |E|^2)
+                            const float dist = fmaf(-2.0f, __uint_as_float(v[j4 * 4 + q]), tsum);   // fl(tsum - 2c)
+                            if (dist < best[q]) {
+                                best[q] = dist;
+                                best_k[q] = k0 + half * 128 + cc * 32 + j4 * 4 + q;
+                            }
+                        }
+                    }
+                };
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(t_addr + 32, vb);
+                consume(va, 0);
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(t_addr + 64, va);
+                consume(vb, 1);
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(t_addr + 96, vb);
+                consume(va, 2);
+                tmem_ld_wait();
+                // this warp's share of the accumulator is in registers: hand the buffer back early
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(bar_acc_empty + buf, 0);
+                consume(vb, 3);
+            }
+            // merge the 4 chains (smallest distance, then smallest index), then the two column halves
+            float bd = best[0];
+            int bk = best_k[0];
+#pragma unroll
+            for (int q = 1; q < 4; ++q) {
+                if (best[q] < bd || (best[q] == bd && best_k[q] < bk)) {
+                    bd = best[q];
+                    bk = best_k[q];
+                }
+            }
+            unsigned long long key = pack_key(bd, bk);
+            unsigned long long* mslot = merge + (it & 1) * TC_ROWS;
+            if (half == 1) mslot[row] = key;
+            named_bar_sync(2, 256);
+            if (half == 0) {
+                const unsigned long long other = mslot[row];
+                key = other < key ? other : key;
+                const long long r = static_cast<long long>(row_tile) * TC_ROWS + row;
+                if (r < N) {
+                    if (keys != nullptr)
+                        atomicMin(keys + r, key);
+                    else
+                        idx_out[r] = static_cast<int>(key & 0xffffffffu);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();      // no CTA leaves (or frees TMEM) while its peer may still signal it
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, TC2_TMEM_COLS);
+    }
+}
+
 }  // namespace b200vq

@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, parallel
 from ._lib import (FLAG_DEFER_STATS, FLAG_EXACT, FLAG_NO_QUANT, FLAG_ONEHOT, FLAG_TRAIN_VQ, check)
 
 
@@ -121,8 +121,8 @@ class _VQFunction(torch.autograd.Function):
         if need_dE:
             if world > 1:
                 # one all-reduce per step over [dE | hist | sse]  
-                packed = torch.zeros(K * D + K + 1, dtype=torch.float32, device=dev)
-                dE = packed[:K * D].view(K, D)
+                packed = parallel.new_packed(K, D, dev)
+                dE = parallel.packed_views(packed, K, D)[0]
             else:
                 dE = torch.zeros(K, D, dtype=torch.float32, device=dev)
         dz = torch.empty_like(inputs)
@@ -133,9 +133,8 @@ class _VQFunction(torch.autograd.Function):
         check(lib.vq_backward(_ptr(g_q), _ptr(g_loss), _ptr(inputs), _ptr(w), _ptr(idx), N, max(N, 1),
                               max(N, 1) * world, K, D, float(module._commitment_cost), flags, _ptr(dz), _ptr(dE), st))
         if packed is not None:
-            import torch.distributed as dist
             packed[K * D:] = ctx.stats[:K + 1]
-            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=pg)
+            parallel.all_reduce_packed(packed, pg)
             module._global_stats = (packed[K * D:], N * world)
         return (dz if need_dz else None), dE, None, None, None
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VQ_ABI_VERSION 5
+#define VQ_ABI_VERSION 6
 
 /* error codes */
 #define VQ_OK            0
@@ -44,6 +44,7 @@ extern "C" {
                                         (bit-exact vs oracle/vq_oracle.c) instead of the tcgen05 3xTF32 path */
 #define VQ_FLAG_DEFER_STATS (1 << 3) /* forward: leave loss/perplexity to vq_finalize_stats (data parallel) */
 #define VQ_FLAG_NO_QUANT   (1 << 4)  /* forward: indices/hist only; q_out, sse, loss are not produced */
+#define VQ_FLAG_TC_1CTA    (1 << 6)  /* forward: single-CTA tensor kernel (M=128,N=128) even when the CTA-pair kernel applies */
 #define VQ_FLAG_ZERO_DE    (1 << 5)  /* backward: zero dE (memset on `stream`) before accumulating into it */
 
 typedef void* vq_stream_t;   /* cudaStream_t */

@@ -133,6 +133,17 @@ def test_exact_path_abi(lib, golden, name):
 TENSOR_CASES = [n for n, c in CASES.items() if c["D"] in (32, 64, 96, 128) and c["K"] % 128 == 0]
 
 
+@pytest.mark.parametrize("name", [n for n in TENSOR_CASES if CASES[n]["K"] % 256 == 0])
+def test_tensor_path_single_cta_kernel(lib, golden, name):
+    """The M=128/N=128 single-CTA tcgen05 kernel (used when K % 256 != 0), forced with VQ_FLAG_TC_1CTA."""
+    c = CASES[name]
+    E, z, g = make_inputs(c)
+    D = c["D"]
+    out = run_abi(lib, z.numpy().reshape(-1, D), E.numpy(), g.numpy().reshape(-1, D), c["g_loss"], c["beta"],
+                  c["train_vq"], flags_extra=1 << 6)
+    check_against_oracle_and_golden(out, name, golden, exact=False)
+
+
 @pytest.mark.parametrize("name", TENSOR_CASES)
 def test_tensor_path_abi(lib, golden, name):
     c = CASES[name]
