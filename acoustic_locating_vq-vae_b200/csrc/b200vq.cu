@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -22,6 +23,7 @@ using namespace b200vq;
 namespace {
 
 thread_local char g_err[512] = "";
+long long* g_trace_buf = nullptr;   // VQ_TRACE builds: device buffer handed to the fused kernel
 std::atomic<long long> g_launches{0};
 
 int fail(int code, const char* fmt, ...) {
@@ -201,21 +203,32 @@ int launch_tc(const CUtensorMap& tz, const CUtensorMap& thi, const CUtensorMap& 
 template <int NSLAB, int NSTAGE, int ZBUF>
 int launch_tc2(const CUtensorMap& tz, const CUtensorMap& thi, const CUtensorMap& tlo, const float* e_norm2, long long N,
                int K, int codes_per_split, int splits, int* idx, unsigned long long* keys, float* hist,
-               unsigned int* counter, cudaStream_t st) {
+               unsigned int* counter, const FusedRowArgs* fused, cudaStream_t st) {
     constexpr int smem = tc2_smem_bytes(NSLAB, NSTAGE, ZBUF);
     static_assert(smem <= 232448, "CTA-pair kernel exceeds 227 KB of shared memory");
     static bool configured = false;
     if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(argmin_tc2_kernel<NSLAB, NSTAGE, ZBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUDA_TRY(cudaFuncSetAttribute(argmin_tc2_kernel<NSLAB, NSTAGE, ZBUF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CUDA_TRY(cudaFuncSetAttribute(argmin_tc2_kernel<NSLAB, NSTAGE, ZBUF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     const long long row_tiles = (N + TC_ROWS - 1) / TC_ROWS;
     const long long n_items = ((row_tiles + 1) / 2) * splits;          // (row-tile pair, codebook split)
     const int pairs = static_cast<int>(n_items < kNumSMs / 2 ? n_items : kNumSMs / 2);
-    ProfScope prof(KID_ARGMIN_TC, st);
-    argmin_tc2_kernel<NSLAB, NSTAGE, ZBUF><<<2 * pairs, TC2_THREADS, smem, st>>>(
-        tz, thi, tlo, e_norm2, N, K, codes_per_split, splits, static_cast<int>(n_items), idx, keys, hist, counter);
-    LAUNCH_CHECK("argmin_tc2_kernel");
+    if (fused != nullptr) {
+        zero_state_kernel<<<1, 256, 0, st>>>(hist, K, counter);
+        LAUNCH_CHECK("zero_state_kernel");
+        ProfScope prof(KID_ARGMIN_TC, st);
+        argmin_tc2_kernel<NSLAB, NSTAGE, ZBUF, true><<<2 * pairs, TC2_THREADS_FUSED, smem, st>>>(
+            tz, thi, tlo, e_norm2, N, K, codes_per_split, splits, static_cast<int>(n_items), idx, keys, hist, counter, *fused);
+        LAUNCH_CHECK("argmin_tc2_kernel<fused>");
+    } else {
+        FusedRowArgs none{};
+        ProfScope prof(KID_ARGMIN_TC, st);
+        argmin_tc2_kernel<NSLAB, NSTAGE, ZBUF, false><<<2 * pairs, TC2_THREADS, smem, st>>>(
+            tz, thi, tlo, e_norm2, N, K, codes_per_split, splits, static_cast<int>(n_items), idx, keys, hist, counter, none);
+        LAUNCH_CHECK("argmin_tc2_kernel");
+    }
     return VQ_OK;
 }
 
@@ -256,6 +269,9 @@ int vq_profile_read(int kid, double* total_ms, int64_t* count) {
     *count = n;
     return VQ_OK;
 }
+
+// Debug builds (-DVQ_TRACE) only: device buffer of 148*8*64 int64 that receives per-role clock64 stamps.
+void vq_debug_set_trace(long long* device_buffer) { g_trace_buf = device_buffer; }
 
 int vq_forward_uses_tensor_path(int64_t n_rows, int K, int D, int flags) {
     return tensor_path_ok(n_rows, K, D, flags) ? 1 : 0;
@@ -315,8 +331,19 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
         const bool pair = (K % TC2_CODES == 0) && !(flags & VQ_FLAG_TC_1CTA);
         // CTA pairs: a wave is 74 pairs, each covering 256 rows x 256 codes per tile
         const int code_tiles = pair ? K / TC2_CODES : K / TC_CODES;
-        const int splits = pair ? choose_splits((row_tiles + 1) / 2, code_tiles, 65535, kNumSMs / 2, 0.35)
-                                : choose_splits(row_tiles, code_tiles, 65535, kNumSMs);
+        int splits = pair ? choose_splits((row_tiles + 1) / 2, code_tiles, 65535, kNumSMs / 2, 0.35)
+                          : choose_splits(row_tiles, code_tiles, 65535, kNumSMs);
+        const bool can_fuse = pair && quant && !(flags & VQ_FLAG_NO_FUSE) && aligned16(q_out) && aligned16(E) &&
+                              (!want_onehot || aligned16(onehot));
+        if (can_fuse && splits > 1) {
+            // One fused launch (no key merge, no separate rows kernel) is worth about two code tiles of time:
+            // split the codebook only when that still wins, i.e. when very few row tiles would leave SMs idle.
+            const long long rtp = (row_tiles + 1) / 2;
+            const int slots = kNumSMs / 2;
+            const double fused_cost = static_cast<double>((rtp + slots - 1) / slots) * (code_tiles + 0.35);
+            const double split_cost = static_cast<double>((rtp * splits + slots - 1) / slots) * (code_tiles / splits + 0.35);
+            if (fused_cost <= split_cost + 2.0) splits = 1;
+        }
         const int cps = K / splits;
         if (splits > 1) {
             keys = keys_buf;
@@ -329,13 +356,27 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
         int rc = VQ_OK;
         const int nslab = D / TC_SLAB_FLOATS;
         if (pair) {
+            // fused forward: the persistent kernel's writer warps also do vector_quantizer.py:39-56 (one launch)
+            FusedRowArgs fr{};
+            const bool fuse = can_fuse && splits == 1;
+            if (fuse) {
+                fr.z = z; fr.E = E; fr.q_out = q_out; fr.onehot = want_onehot ? onehot : nullptr; fr.hist = hist;
+                fr.partials = partials; fr.counter = counter; fr.sse_out = sse; fr.loss = loss; fr.perplexity = perplexity;
+                fr.beta = beta; fr.finalize = defer ? 0 : 1;
+                fr.trace = g_trace_buf;
+                static const int evict_first = [] { const char* e = getenv("B200VQ_ONEHOT_EVICT_FIRST"); return e != nullptr && e[0] == '0' ? 0 : 1; }();   // default on
+                fr.onehot_evict_first = evict_first;
+            }
+            const FusedRowArgs* frp = fuse ? &fr : nullptr;
             switch (nslab) {
-                case 1: rc = launch_tc2<1, 8, 2>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
-                case 2: rc = launch_tc2<2, 5, 2>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
-                case 3: rc = launch_tc2<3, 6, 1>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
-                case 4: rc = launch_tc2<4, 5, 1>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;
+                case 1: rc = launch_tc2<1, 8, 2>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, frp, st); break;
+                case 2: rc = launch_tc2<2, 5, 2>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, frp, st); break;
+                case 3: rc = launch_tc2<3, 6, 1>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, frp, st); break;
+                case 4: rc = launch_tc2<4, 5, 1>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, frp, st); break;
                 default: return fail(VQ_ERR_ARG, "vq_forward: unsupported D=%d on the tensor path", D);
             }
+            if (rc) return rc;
+            if (fuse) return VQ_OK;     // rows work already done inside the kernel
         } else {
             switch (nslab) {
                 case 1: rc = launch_tc<1, 8>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, st); break;

@@ -18,6 +18,12 @@ __global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ p, float 
         p[i] = v;
 }
 
+// zeroes the usage histogram and the last-CTA counter ahead of the fused forward kernel
+__global__ void __launch_bounds__(256) zero_state_kernel(float* __restrict__ hist, int K, unsigned int* __restrict__ counter) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) hist[k] = 0.0f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;
+}
+
 // ---------------------------------------------------------------------------------------------
 // prep: one warp per codeword
 // ---------------------------------------------------------------------------------------------

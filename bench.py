@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--no-onehot", action="store_true", help="indices-only mode (encodings not materialised)")
     ap.add_argument("--exact", action="store_true", help="CUDA-core exact path instead of tcgen05")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-fuse", action="store_true", help="argmin and row epilogue as two kernels (VQ_FLAG_NO_FUSE)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()
@@ -233,7 +234,7 @@ def main():
     scal = torch.empty(2, device=dev)                                 # loss, perplexity
     dz = torch.empty(N, D, device=dev)
     g_loss = torch.ones((), device=dev)
-    fwd_flags = (L.FLAG_ONEHOT if emit_onehot else 0) | (L.FLAG_EXACT if args.exact else 0)
+    fwd_flags = (L.FLAG_ONEHOT if emit_onehot else 0) | (L.FLAG_EXACT if args.exact else 0) | (L.FLAG_NO_FUSE if args.no_fuse else 0)
     bwd_flags = L.FLAG_TRAIN_VQ | L.FLAG_ZERO_DE
     wsb = lib.vq_workspace_bytes(N, K, D, fwd_flags)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
@@ -296,27 +297,33 @@ def main():
         k["avg_us"] = round(k["avg_us"], 3)
     dom = max(kern, key=lambda n: kern[n]["avg_us"] * kern[n]["launches"])
     traffic = load_traffic()
+    fused = "rows" not in kern and "argmin_tc" in kern          # row epilogue ran inside the tensor kernel
+    rows_bytes = 4.0 * (2 * N * D + N + K * D + K + (N * K if emit_onehot else 0))
+    # algorithmic work per launch: SURVEY.md section 8(d) per-row figures x rows per launch
     alg = {
-        "argmin_tc": ("tensor", 2.0 * N * K * D),
-        "argmin_exact": ("tensor", 2.0 * N * K * D),
-        "rows": ("hbm", 4.0 * (2 * N * D + N + K * D + K + (N * K if emit_onehot else 0))),
-        "backward": ("hbm", 4.0 * (3 * N * D + N + 2 * K * D)),
-        "prepare_codebook": ("hbm", 4.0 * (3 * K * D + K)),
+        "argmin_tc": {"flops": 2.0 * N * K * D, "bytes": rows_bytes if fused else 4.0 * (N * D + N + 2 * K * D)},
+        "argmin_exact": {"flops": 2.0 * N * K * D, "bytes": 4.0 * (N * D + N + K * D)},
+        "rows": {"flops": 0.0, "bytes": rows_bytes},
+        "backward": {"flops": 0.0, "bytes": 4.0 * (3 * N * D + N + 2 * K * D)},
+        "prepare_codebook": {"flops": 0.0, "bytes": 4.0 * (3 * K * D + K)},
     }
-    bound, work = alg.get(dom, ("hbm", 0.0))
+    work = alg.get(dom, {"flops": 0.0, "bytes": 0.0})
     dur_s = kern[dom]["avg_us"] * 1e-6
-    if bound == "tensor":
-        peak = peaks["bf16_tflops"] / 2.0     # TF32 pipe = half the measured dense bf16 rate
-        achieved = work / dur_s / 1e12
-        unit = "TFLOP/s"
+    tf32_peak = peaks["bf16_tflops"] / 2.0                        # TF32 pipe = half the measured dense bf16 rate
+    t_tensor = work["flops"] / (tf32_peak * 1e12)
+    t_hbm = work["bytes"] / (peaks["hbm_gbs"] * 1e9)
+    if t_tensor >= t_hbm:                                          # whichever roofline binds this launch
+        bound, peak, achieved, unit = "tensor", tf32_peak, work["flops"] / dur_s / 1e12, "TFLOP/s"
+        per_launch = work["flops"]
     else:
-        peak = peaks["hbm_gbs"]
-        achieved = work / dur_s / 1e9
-        unit = "GB/s"
-    roofline = {"kernel": dom, "bound": bound, "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": unit,
-                "frac": round(achieved / peak, 4), "traffic": traffic.get(args.workload, {}).get(dom),
+        bound, peak, achieved, unit = "hbm", peaks["hbm_gbs"], work["bytes"] / dur_s / 1e9, "GB/s"
+        per_launch = work["bytes"]
+    roofline = {"kernel": ("fused forward (argmin_tc2 + row epilogue)" if fused and dom == "argmin_tc" else dom), "bound": bound,
+                "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": unit, "frac": round(achieved / peak, 4),
+                "traffic": traffic.get(args.workload, {}).get(dom),
                 "peak_source": peaks["source"] + (" bf16/2 (tf32 pipe)" if bound == "tensor" else " copy bandwidth"),
-                "per_launch": work, "avg_us": kern[dom]["avg_us"]}
+                "per_launch": per_launch, "avg_us": kern[dom]["avg_us"],
+                "other_roof": {"tensor_tflops": round(work["flops"] / dur_s / 1e12, 2), "hbm_gbs": round(work["bytes"] / dur_s / 1e9, 1)}}
 
     # ---- end to end through the host-buffer C ABI: pinned host z in, loss/perplexity/indices out ------
     e2e = None

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VQ_ABI_VERSION 6
+#define VQ_ABI_VERSION 7
 
 /* error codes */
 #define VQ_OK            0
@@ -45,6 +45,7 @@ extern "C" {
 #define VQ_FLAG_DEFER_STATS (1 << 3) /* forward: leave loss/perplexity to vq_finalize_stats (data parallel) */
 #define VQ_FLAG_NO_QUANT   (1 << 4)  /* forward: indices/hist only; q_out, sse, loss are not produced */
 #define VQ_FLAG_TC_1CTA    (1 << 6)  /* forward: single-CTA tensor kernel (M=128,N=128) even when the CTA-pair kernel applies */
+#define VQ_FLAG_NO_FUSE    (1 << 7)  /* forward: keep argmin and the row epilogue as two kernels (default: fused into one) */
 #define VQ_FLAG_ZERO_DE    (1 << 5)  /* backward: zero dE (memset on `stream`) before accumulating into it */
 
 typedef void* vq_stream_t;   /* cudaStream_t */
@@ -65,6 +66,10 @@ int64_t     vq_launch_count(void);
  * 4 backward, 5 finalize, 6 one-hot. */
 void        vq_profile_enable(int on);
 int         vq_profile_read(int kid, double* total_ms, int64_t* count);
+
+/* Debug hook: in -DVQ_TRACE builds the fused forward kernel writes clock64 stamps (148 CTAs x 8 roles x 64
+ * int64) into this device buffer; a no-op in production builds.  See tools/trace_fused.py. */
+void        vq_debug_set_trace(long long* device_buffer);
 
 /* -- codebook preparation (once per optimizer step: Adam changes E) ------------------------- */
 /* e_norm2[k] = |E_k|^2 (vector_quantizer.py:35) as an fp32 FMA chain over d;

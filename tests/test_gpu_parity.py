@@ -144,6 +144,17 @@ def test_tensor_path_single_cta_kernel(lib, golden, name):
     check_against_oracle_and_golden(out, name, golden, exact=False)
 
 
+@pytest.mark.parametrize("name", [n for n in TENSOR_CASES if CASES[n]["K"] % 256 == 0])
+def test_tensor_path_unfused(lib, golden, name):
+    """CTA-pair argmin kernel + separate rows kernel (VQ_FLAG_NO_FUSE): the path taken when the codebook is split."""
+    c = CASES[name]
+    E, z, g = make_inputs(c)
+    D = c["D"]
+    out = run_abi(lib, z.numpy().reshape(-1, D), E.numpy(), g.numpy().reshape(-1, D), c["g_loss"], c["beta"],
+                  c["train_vq"], flags_extra=1 << 7)
+    check_against_oracle_and_golden(out, name, golden, exact=False)
+
+
 @pytest.mark.parametrize("name", TENSOR_CASES)
 def test_tensor_path_abi(lib, golden, name):
     c = CASES[name]

@@ -1,0 +1,53 @@
+"""Timeline of the fused forward kernel (debug): builds libb200vq_trace.so with -DVQ_TRACE, runs one
+forward on the bench workload and prints per-role clock64 stamps (in us at the nominal 1.9 GHz) for a few CTAs."""
+import ctypes, os, subprocess, sys
+import numpy as np
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from importlib import import_module
+B = import_module("acoustic_locating_vq-vae_b200.build")
+L = import_module("acoustic_locating_vq-vae_b200._lib")
+so = os.path.join(B.CSRC, "libb200vq_trace.so")
+subprocess.run([B._nvcc(), *B.NVCC_FLAGS, "-DVQ_TRACE", "-o", so, os.path.join(B.CSRC, "b200vq.cu")], check=True)
+lib = ctypes.CDLL(so)
+for name, (res, args) in L.SIGNATURES.items():
+    fn = getattr(lib, name); fn.restype = res; fn.argtypes = args
+onehot_on = "--no-onehot" not in sys.argv
+Bn, D, T, K = 256, 64, 201, 1024
+N = Bn * T
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+E = torch.randn(K, D, device=dev); z = torch.randn(N, D, device=dev)
+e2 = torch.empty(K, device=dev); ehi = torch.empty_like(E); elo = torch.empty_like(E)
+q = torch.empty_like(z); idx = torch.empty(N, dtype=torch.int32, device=dev)
+oh = torch.empty(N, K, device=dev) if onehot_on else None
+stats = torch.empty(K + 3, device=dev)
+wsb = lib.vq_workspace_bytes(N, K, D, 1); ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+trace = torch.zeros(148 * 8 * 64, dtype=torch.int64, device=dev)
+st = torch.cuda.current_stream().cuda_stream
+lib.vq_debug_set_trace(trace.data_ptr())
+for rep in range(3):
+    trace.zero_()
+    assert lib.vq_prepare_codebook(E.data_ptr(), K, D, e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(), st) == 0
+    rc = lib.vq_forward(z.data_ptr(), E.data_ptr(), e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(), N, K, D, 0.25, 1 if onehot_on else 0,
+                        q.data_ptr(), idx.data_ptr(), None if oh is None else oh.data_ptr(), stats.data_ptr(), stats.data_ptr() + 4 * K,
+                        stats.data_ptr() + 4 * (K + 1), stats.data_ptr() + 4 * (K + 2), ws.data_ptr(), wsb, st)
+    assert rc == 0, lib.vq_last_error()
+    torch.cuda.synchronize()
+t = trace.cpu().numpy().reshape(148, 8, 64)
+roles = {0: "epi tiles (wait start | acc full | scanned) x12", 1: "mma  (wait z_ready | got | item issued)", 2: "zpipe(tma issue | z landed | converted)", 3: "epi  (a_ready | first acc | last acc | idx out)",
+         4: "fill (issue start | issued)", 5: "work (idx got | q done | ones done)", 6: "zeros_done published (per item)", 7: "cta  (start | roles done | after cluster sync)"}
+for cta in (0, 1, 73, 147):
+    t0 = t[cta, 7, 0]
+    print(f"--- CTA {cta} (us since role dispatch, 1.9 GHz nominal) ---")
+    for r, name in roles.items():
+        vals = [(s, (v - t0) / 1900.0) for s, v in enumerate(t[cta, r]) if v != 0 and not (r == 7 and s >= 3)]
+        print(f"  {name:50s}", " ".join(f"{s}:{u:.1f}" for s, u in vals[:40]))
+cyc = (t[:, 7, 2] - t[:, 7, 0]).astype(np.float64); ns = (t[:, 7, 4] - t[:, 7, 3]).astype(np.float64)
+print("effective SM clock during the kernel: %.0f MHz (median over CTAs)" % np.median(cyc / np.maximum(ns, 1) * 1e3))
+ld = t[0::2, 6, :]
+print("leader MMA thread: cycles waiting on acc_empty: median %.0f ; on full (E TMA): median %.0f ; residency cycles median %.0f" % (
+    np.median(ld[:, 32]), np.median(ld[:, 33]), np.median(cyc)))
+ends = (t[:, 7, 2] - t[:, 7, 0]) / 1900.0
+print("kernel residency per CTA (us): min %.1f  median %.1f  max %.1f" % (ends.min(), np.median(ends), ends.max()))
