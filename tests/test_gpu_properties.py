@@ -1,0 +1,151 @@
+"""GPU property tests at BASELINE.json's full sizes (configs[1] and the N = 1M sweep), where the CPU
+oracle would take minutes: size-independent properties the domain offers.
+
+  * the tensor path (tcgen05 3xTF32, fused forward) agrees with the exact CUDA-core path (bit-exact vs
+    oracle/vq_oracle.c at oracle-sized cases) except on fp32 near-ties;
+  * histogram / one-hot / index consistency (checksum of checksums);
+  * idempotence: quantizing the codewords themselves returns their own indices and a zero loss;
+  * the loss identity loss == (1+beta) * mean((q_out - z)^2) and the gradient sum rules
+        sum_k dE_k == ce * sum_n (E[idx_n] - z_n),   dz - g == -beta * ce' * (E[idx] - z);
+  * linearity of backward in (g_loss, g_q);
+  * a slice of the big problem checked against the CPU oracle.
+"""
+import numpy as np
+import pytest
+import torch
+
+from util import NEAR_TIE_TENSOR
+
+pytestmark = pytest.mark.gpu
+BETA = 0.25
+
+
+def _dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _forward(lib, z, E, flags, want_onehot=False):
+    dev = z.device
+    N, D = z.shape
+    K = E.shape[0]
+    st = torch.cuda.current_stream().cuda_stream
+    e2 = torch.empty(K, device=dev); ehi = torch.empty_like(E); elo = torch.empty_like(E)
+    assert lib.vq_prepare_codebook(E.data_ptr(), K, D, e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(), st) == 0
+    q = torch.empty_like(z); idx = torch.empty(N, dtype=torch.int32, device=dev)
+    oh = torch.empty(N, K, device=dev) if want_onehot else None
+    stats = torch.empty(K + 3, device=dev)
+    fl = flags | (1 if want_onehot else 0)
+    wsb = lib.vq_workspace_bytes(N, K, D, fl); ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    sp = stats.data_ptr()
+    rc = lib.vq_forward(z.data_ptr(), E.data_ptr(), e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(), N, K, D, BETA, fl,
+                        q.data_ptr(), idx.data_ptr(), None if oh is None else oh.data_ptr(), sp, sp + 4 * K, sp + 4 * (K + 1),
+                        sp + 4 * (K + 2), ws.data_ptr(), wsb, st)
+    assert rc == 0, lib.vq_last_error()
+    torch.cuda.synchronize()
+    return dict(q=q, idx=idx, onehot=oh, hist=stats[:K], sse=stats[K], loss=stats[K + 1], perplexity=stats[K + 2])
+
+
+def _near_tie_gap(z, E, idx_a, idx_b):
+    mis = torch.nonzero(idx_a != idx_b).flatten()
+    if mis.numel() == 0:
+        return 0, 0.0
+    zr = z[mis].double()
+    ea, eb = E[idx_a[mis].long()].double(), E[idx_b[mis].long()].double()
+    da, db = ((zr - ea) ** 2).sum(1), ((zr - eb) ** 2).sum(1)
+    scale = (zr ** 2).sum(1) + torch.maximum((ea ** 2).sum(1), (eb ** 2).sum(1))
+    return int(mis.numel()), float(((da - db).abs() / scale).max())
+
+
+FULL = [
+    ("rir256", 256 * 201, 64, 1024, True),        # BASELINE configs[1], dense one-hot on
+    ("sweep_k1024_d64", 1 << 20, 64, 1024, False),  # configs[3]
+    ("sweep_k512_d64", 1 << 20, 64, 512, False),
+    ("sweep_k2048_d128", 1 << 19, 128, 2048, False),
+]
+
+
+@pytest.mark.parametrize("name,N,D,K,onehot", FULL)
+def test_full_size_properties(lib, name, N, D, K, onehot):
+    from oracle import c_oracle
+    dev = _dev()
+    torch.manual_seed(0)
+    E = torch.randn(K, D, device=dev)
+    z = torch.randn(N, D, device=dev)
+    t = _forward(lib, z, E, 0, want_onehot=onehot)           # tensor path, fused
+    assert lib.vq_forward_uses_tensor_path(N, K, D, 0) == 1
+    x = _forward(lib, z, E, 4)                                # exact CUDA-core path
+    n_mis, gap = _near_tie_gap(z, E, t["idx"], x["idx"])
+    assert gap <= NEAR_TIE_TENSOR and n_mis <= max(1, N // 2000), f"{name}: {n_mis} rows differ, worst gap {gap:.2e}"
+    # histogram / indices / one-hot: a checksum of checksums
+    hist = torch.bincount(t["idx"].long(), minlength=K).float()
+    assert torch.equal(hist, t["hist"]) and float(t["hist"].sum()) == N
+    assert int(t["idx"].min()) >= 0 and int(t["idx"].max()) < K
+    if onehot:
+        oh = t["onehot"]
+        assert torch.equal(oh.sum(0), t["hist"]) and torch.equal(oh.argmax(1).int(), t["idx"])
+        assert float(oh.sum()) == N and float(oh.max()) == 1.0 and float(oh.min()) == 0.0
+    # straight-through value, loss and perplexity identities (fp64 on the GPU as the yardstick)
+    qe = E[t["idx"].long()]
+    assert torch.equal(t["q"], z + (qe - z))
+    m = ((qe.double() - z.double()) ** 2).mean()
+    assert abs(float(t["loss"]) - float(m * (1 + BETA))) <= 1e-5 * float(m * (1 + BETA))
+    assert abs(float(t["sse"]) - float(m * N * D)) <= 1e-5 * float(m * N * D)
+    p = (hist / N).double()
+    perp = torch.exp(-(p * torch.log(p + 1e-10)).sum())
+    assert abs(float(t["perplexity"]) - float(perp)) <= 1e-5 * float(perp)
+    # a slice against the CPU oracle (bit-exact indices on the exact path)
+    rows = z[:4096].cpu().numpy()
+    o_idx = c_oracle.argmin(rows, E.cpu().numpy())
+    assert np.array_equal(x["idx"][:4096].cpu().numpy(), o_idx)
+    # idempotence: the codewords quantize to themselves with zero error
+    s = _forward(lib, E.clone(), E, 0)
+    dup = torch.equal(s["idx"], torch.arange(K, dtype=torch.int32, device=dev))
+    assert dup and float(s["sse"]) == 0.0 and torch.equal(s["q"], E)
+
+
+def test_backward_sum_rules_and_linearity(lib):
+    dev = _dev()
+    N, D, K = 256 * 201, 64, 1024
+    torch.manual_seed(1)
+    E = torch.randn(K, D, device=dev); z = torch.randn(N, D, device=dev); g = torch.randn(N, D, device=dev)
+    idx = _forward(lib, z, E, 0)["idx"]
+    st = torch.cuda.current_stream().cuda_stream
+
+    def bwd(g_q, g_loss):
+        dz = torch.empty_like(z); dE = torch.zeros_like(E)
+        gl = torch.tensor(g_loss, device=dev)
+        rc = lib.vq_backward(None if g_q is None else g_q.data_ptr(), gl.data_ptr(), z.data_ptr(), E.data_ptr(), idx.data_ptr(),
+                             N, N, N, K, D, BETA, 2, dz.data_ptr(), dE.data_ptr(), st)
+        assert rc == 0
+        torch.cuda.synchronize()
+        return dz, dE
+
+    dz1, dE1 = bwd(g, 1.0)
+    diff = (E[idx.long()] - z).double()
+    ce = 2.0 / (N * D)
+    assert torch.allclose(dE1.double().sum(0), ce * diff.sum(0), rtol=1e-4, atol=1e-9)
+    ref_dE = torch.zeros(K, D, dtype=torch.float64, device=dev).index_add_(0, idx.long(), ce * diff)
+    assert float((dE1.double() - ref_dE).abs().max()) <= 1e-5 * float(ref_dE.abs().max())
+    assert float((dz1.double() - (g.double() - BETA * ce * diff)).abs().max()) <= 1e-6
+    # linearity: backward(a*g, b*g_loss) == a*backward(g, 0) + b*backward(0, g_loss)
+    dz_g, dE_g = bwd(g, 0.0)
+    dz_l, dE_l = bwd(None, 1.0)
+    dz2, dE2 = bwd(2.0 * g, 3.0)
+    assert torch.allclose(dz2, 2.0 * dz_g + 3.0 * dz_l, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(dE2, 3.0 * dE_l, rtol=1e-5, atol=1e-9) and float(dE_g.abs().max()) == 0.0
+    assert torch.equal(dz_g, g)        # straight-through: the upstream gradient passes unchanged
+
+
+def test_uniform_init_ties_at_full_size(lib):
+    """At the reference's own init (U(-1/K, 1/K), vector_quantizer.py:16) |z|^2 dwarfs |E|^2 and fp32 ties are
+    common: the tensor path must still agree with the exact path up to near-ties."""
+    dev = _dev()
+    N, D, K = 256 * 201, 64, 1024
+    torch.manual_seed(2)
+    E = (torch.rand(K, D, device=dev) * 2 - 1) / K
+    z = torch.randn(N, D, device=dev)
+    t = _forward(lib, z, E, 0)
+    x = _forward(lib, z, E, 4)
+    n_mis, gap = _near_tie_gap(z, E, t["idx"], x["idx"])
+    assert gap <= NEAR_TIE_TENSOR and n_mis <= N // 200, (n_mis, gap)
