@@ -9,7 +9,7 @@ import os
 
 from .build import SO_PATH
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 FLAG_ONEHOT = 1 << 0
 FLAG_TRAIN_VQ = 1 << 1
@@ -19,6 +19,7 @@ FLAG_NO_QUANT = 1 << 4
 FLAG_ZERO_DE = 1 << 5
 FLAG_TC_1CTA = 1 << 6
 FLAG_NO_FUSE = 1 << 7
+FLAG_STATE_READY = 1 << 8
 
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -37,6 +38,7 @@ SIGNATURES = {
     "vq_profile_read": (_int, [_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i64)]),
     "vq_debug_set_trace": (None, [_vp]),
     "vq_prepare_codebook": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp]),
+    "vq_prepare_step": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "vq_workspace_bytes": (_sz, [_i64, _int, _int, _int]),
     "vq_forward": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _f32, _int,
                           _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -75,6 +75,23 @@ struct ProfScope {
     }
 };
 
+// launch with the programmatic-stream-serialization attribute (PDL): the kernel may start while its predecessor in
+// the stream is finishing; it orders itself with griddepcontrol.wait
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- device gate: this library only runs on sm_100 ------------------------------------------------
@@ -203,7 +220,7 @@ int launch_tc(const CUtensorMap& tz, const CUtensorMap& thi, const CUtensorMap& 
 template <int NSLAB, int NSTAGE, int ZBUF>
 int launch_tc2(const CUtensorMap& tz, const CUtensorMap& thi, const CUtensorMap& tlo, const float* e_norm2, long long N,
                int K, int codes_per_split, int splits, int* idx, unsigned long long* keys, float* hist,
-               unsigned int* counter, const FusedRowArgs* fused, cudaStream_t st) {
+               unsigned int* counter, const FusedRowArgs* fused, bool state_ready, cudaStream_t st) {
     constexpr int smem = tc2_smem_bytes(NSLAB, NSTAGE, ZBUF);
     static_assert(smem <= 232448, "CTA-pair kernel exceeds 227 KB of shared memory");
     static bool configured = false;
@@ -216,11 +233,15 @@ int launch_tc2(const CUtensorMap& tz, const CUtensorMap& thi, const CUtensorMap&
     const long long n_items = ((row_tiles + 1) / 2) * splits;          // (row-tile pair, codebook split)
     const int pairs = static_cast<int>(n_items < kNumSMs / 2 ? n_items : kNumSMs / 2);
     if (fused != nullptr) {
-        zero_state_kernel<<<1, 256, 0, st>>>(hist, K, counter);
-        LAUNCH_CHECK("zero_state_kernel");
+        if (!state_ready) {
+            zero_state_kernel<<<1, 256, 0, st>>>(hist, K, counter);
+            LAUNCH_CHECK("zero_state_kernel");
+        }
         ProfScope prof(KID_ARGMIN_TC, st);
-        argmin_tc2_kernel<NSLAB, NSTAGE, ZBUF, true><<<2 * pairs, TC2_THREADS_FUSED, smem, st>>>(
-            tz, thi, tlo, e_norm2, N, K, codes_per_split, splits, static_cast<int>(n_items), idx, keys, hist, counter, *fused);
+        cudaError_t e = launch_pdl(argmin_tc2_kernel<NSLAB, NSTAGE, ZBUF, true>, dim3(2 * pairs), dim3(TC2_THREADS_FUSED), smem, st,
+                                   tz, thi, tlo, e_norm2, N, K, codes_per_split, splits, static_cast<int>(n_items), idx, keys, hist,
+                                   counter, *fused);
+        if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of argmin_tc2_kernel<fused> failed: %s", cudaGetErrorString(e));
         LAUNCH_CHECK("argmin_tc2_kernel<fused>");
     } else {
         FusedRowArgs none{};
@@ -283,15 +304,30 @@ size_t vq_workspace_bytes(int64_t n_rows, int K, int D, int flags) {
     return ws_layout(n_rows).total;
 }
 
-int vq_prepare_codebook(const float* E, int K, int D, float* e_norm2, float* E_hi, float* E_lo, vq_stream_t stream) {
+static int prepare_impl(const float* E, int K, int D, float* e_norm2, float* E_hi, float* E_lo, float* hist,
+                        unsigned int* counter, float* dE, cudaStream_t st) {
     if (int rc = check_device()) return rc;
-    if (E == nullptr || e_norm2 == nullptr || K < 1 || D < 1) return fail(VQ_ERR_ARG, "vq_prepare_codebook: bad argument (K=%d D=%d)", K, D);
-    if ((E_hi == nullptr) != (E_lo == nullptr)) return fail(VQ_ERR_ARG, "vq_prepare_codebook: E_hi and E_lo must both be given or both be NULL");
+    if (E == nullptr || e_norm2 == nullptr || K < 1 || D < 1) return fail(VQ_ERR_ARG, "vq_prepare: bad argument (K=%d D=%d)", K, D);
+    if ((E_hi == nullptr) != (E_lo == nullptr)) return fail(VQ_ERR_ARG, "vq_prepare: E_hi and E_lo must both be given or both be NULL");
     const int blocks = (K + 7) / 8;
-    ProfScope prof(KID_PREP, static_cast<cudaStream_t>(stream));
-    prep_codebook_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(E, K, D, e_norm2, E_hi, E_lo);
+    ProfScope prof(KID_PREP, st);
+    cudaError_t e = launch_pdl(prep_codebook_kernel, dim3(blocks), dim3(256), 0, st, E, K, D, e_norm2, E_hi, E_lo, hist, counter, dE);
+    if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of prep_codebook_kernel failed: %s", cudaGetErrorString(e));
     LAUNCH_CHECK("prep_codebook_kernel");
     return VQ_OK;
+}
+
+int vq_prepare_codebook(const float* E, int K, int D, float* e_norm2, float* E_hi, float* E_lo, vq_stream_t stream) {
+    return prepare_impl(E, K, D, e_norm2, E_hi, E_lo, nullptr, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int vq_prepare_step(const float* E, int K, int D, float* e_norm2, float* E_hi, float* E_lo, float* hist, void* workspace,
+                    size_t workspace_bytes, float* dE, vq_stream_t stream) {
+    if (hist == nullptr || workspace == nullptr) return fail(VQ_ERR_ARG, "vq_prepare_step: hist / workspace is NULL");
+    const WsLayout w = ws_layout(0);
+    if (workspace_bytes < w.total) return fail(VQ_ERR_WORKSPACE, "vq_prepare_step: workspace %zu B < %zu B", workspace_bytes, w.total);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(workspace) + w.counter_off);
+    return prepare_impl(E, K, D, e_norm2, E_hi, E_lo, hist, counter, dE, static_cast<cudaStream_t>(stream));
 }
 
 int vq_forward(const float* z, const float* E, const float* e_norm2, const float* E_hi, const float* E_lo,
@@ -369,10 +405,10 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
             }
             const FusedRowArgs* frp = fuse ? &fr : nullptr;
             switch (nslab) {
-                case 1: rc = launch_tc2<1, 8, 2>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, frp, st); break;
-                case 2: rc = launch_tc2<2, 5, 2>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, frp, st); break;
-                case 3: rc = launch_tc2<3, 6, 1>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, frp, st); break;
-                case 4: rc = launch_tc2<4, 5, 1>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, frp, st); break;
+                case 1: rc = launch_tc2<1, 8, 2>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, frp, (flags & VQ_FLAG_STATE_READY) != 0, st); break;
+                case 2: rc = launch_tc2<2, 5, 2>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, frp, (flags & VQ_FLAG_STATE_READY) != 0, st); break;
+                case 3: rc = launch_tc2<3, 6, 1>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, frp, (flags & VQ_FLAG_STATE_READY) != 0, st); break;
+                case 4: rc = launch_tc2<4, 5, 1>(tz, thi, tlo, e_norm2, N, K, cps, splits, idx, keys, hist, counter, frp, (flags & VQ_FLAG_STATE_READY) != 0, st); break;
                 default: return fail(VQ_ERR_ARG, "vq_forward: unsupported D=%d on the tensor path", D);
             }
             if (rc) return rc;
@@ -474,10 +510,12 @@ int vq_backward(const float* g_q, const float* g_loss, const float* z, const flo
     const int grid = static_cast<int>(g);
     ProfScope prof(KID_BACKWARD, st);
 #define BWD_ARGS g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, D, beta, dz, dE
-#define BWD_LAUNCH(TR, GQ)                                                               \
-    do {                                                                                 \
-        if (vec) backward_kernel<TR, GQ, 4><<<grid, 256, 0, st>>>(BWD_ARGS);             \
-        else backward_kernel<TR, GQ, 1><<<grid, 256, 0, st>>>(BWD_ARGS);                 \
+#define BWD_LAUNCH(TR, GQ)                                                                                        \
+    do {                                                                                                          \
+        cudaError_t e__;                                                                                          \
+        if (vec) e__ = launch_pdl(backward_kernel<TR, GQ, 4>, dim3(grid), dim3(256), 0, st, BWD_ARGS);            \
+        else e__ = launch_pdl(backward_kernel<TR, GQ, 1>, dim3(grid), dim3(256), 0, st, BWD_ARGS);                \
+        if (e__ != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of backward_kernel failed: %s", cudaGetErrorString(e__)); \
     } while (0)
     if (train && g_q) BWD_LAUNCH(true, true);
     else if (train) BWD_LAUNCH(true, false);

@@ -29,7 +29,19 @@ __global__ void __launch_bounds__(256) zero_state_kernel(float* __restrict__ his
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) prep_codebook_kernel(const float* __restrict__ E, int K, int D,
                                                             float* __restrict__ e_norm2, float* __restrict__ E_hi,
-                                                            float* __restrict__ E_lo) {
+                                                            float* __restrict__ E_lo, float* __restrict__ hist_zero,
+                                                            unsigned int* __restrict__ counter_zero,
+                                                            float* __restrict__ dE_zero) {
+    pdl_launch_dependents();     // the forward kernel may set itself up while this one runs
+    pdl_wait_prior_grids();      // ... but the buffers reset below may still be in use by the previous step
+    {   // optional step-state reset riding along: usage histogram, last-CTA counter, dE accumulator
+        const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+        if (hist_zero != nullptr)
+            for (int k = tid; k < K; k += nth) hist_zero[k] = 0.0f;
+        if (counter_zero != nullptr && tid == 0) *counter_zero = 0u;
+        if (dE_zero != nullptr)
+            for (int i = tid; i < K * D; i += nth) dE_zero[i] = 0.0f;
+    }
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= K) return;
@@ -370,6 +382,8 @@ __global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__
                                                        const int* __restrict__ idx, long long N, float denom_dz,
                                                        float denom_dE, int D, float beta, float* __restrict__ dz,
                                                        float* __restrict__ dE) {
+    pdl_launch_dependents();
+    pdl_wait_prior_grids();
     const float gl = g_loss != nullptr ? __ldg(g_loss) : 1.0f;
     const float cz = gl * beta * 2.0f / denom_dz;
     const float ce = gl * 2.0f / denom_dE;

@@ -402,6 +402,7 @@ argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait_prior_grids();      // everything above overlapped the previous kernel (PDL); its outputs are visible from here
     if (threadIdx.x == 0) {
         VQ_TR(7, 0);
 #ifdef VQ_TRACE
@@ -813,6 +814,7 @@ argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
     }
 
     if (threadIdx.x == 0) VQ_TR(7, 1);
+    pdl_launch_dependents();
     tc_fence_before();
     cluster_sync_all();      // no CTA leaves (or frees TMEM) while its peer may still signal it
     if (threadIdx.x == 0) {

@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, parallel
-from ._lib import (FLAG_DEFER_STATS, FLAG_EXACT, FLAG_NO_QUANT, FLAG_ONEHOT, FLAG_TRAIN_VQ, check)
+from ._lib import (FLAG_DEFER_STATS, FLAG_EXACT, FLAG_NO_QUANT, FLAG_ONEHOT, FLAG_STATE_READY, FLAG_TRAIN_VQ, check)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -64,7 +64,6 @@ class _VQFunction(torch.autograd.Function):
             w = w.contiguous()
         bufs: _Buffers = module._bufs
         e_norm2, e_hi, e_lo = bufs.codebook(K, D, dev)
-        check(lib.vq_prepare_codebook(_ptr(w), K, D, _ptr(e_norm2), _ptr(e_hi), _ptr(e_lo), st))
         q_out = torch.empty_like(inputs)
         idx = torch.empty(N, dtype=torch.int32, device=dev)
         stats = torch.empty(K + 1, dtype=torch.float32, device=dev)    # [hist(K) | sse]
@@ -75,6 +74,9 @@ class _VQFunction(torch.autograd.Function):
         nbytes = lib.vq_workspace_bytes(N, K, D, fl)
         ws = bufs.workspace(nbytes, dev)
         sp = stats.data_ptr()
+        # codebook norms, tf32 hi/lo split and the reset of hist / completion counter in ONE launch
+        check(lib.vq_prepare_step(_ptr(w), K, D, _ptr(e_norm2), _ptr(e_hi), _ptr(e_lo), sp, _ptr(ws), ws.numel(), None, st))
+        fl |= FLAG_STATE_READY
         check(lib.vq_forward(_ptr(flat), _ptr(w), _ptr(e_norm2), _ptr(e_hi), _ptr(e_lo), N, K, D,
                              float(module._commitment_cost), fl, _ptr(q_out), _ptr(idx), _ptr(onehot),
                              sp, sp + 4 * K, _ptr(loss), _ptr(perplexity), _ptr(ws), ws.numel(), st))

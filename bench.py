@@ -234,8 +234,9 @@ def main():
     scal = torch.empty(2, device=dev)                                 # loss, perplexity
     dz = torch.empty(N, D, device=dev)
     g_loss = torch.ones((), device=dev)
-    fwd_flags = (L.FLAG_ONEHOT if emit_onehot else 0) | (L.FLAG_EXACT if args.exact else 0) | (L.FLAG_NO_FUSE if args.no_fuse else 0)
-    bwd_flags = L.FLAG_TRAIN_VQ | L.FLAG_ZERO_DE
+    fwd_flags = ((L.FLAG_ONEHOT if emit_onehot else 0) | (L.FLAG_EXACT if args.exact else 0) |
+                 (L.FLAG_NO_FUSE if args.no_fuse else 0) | L.FLAG_STATE_READY)
+    bwd_flags = L.FLAG_TRAIN_VQ
     wsb = lib.vq_workspace_bytes(N, K, D, fwd_flags)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
@@ -244,7 +245,8 @@ def main():
 
     def step(i):
         z = zs[i % nbuf]
-        L.check(lib.vq_prepare_codebook(P(E), K, D, P(e2), P(ehi), P(elo), st))
+        # one launch: codebook norms + tf32 split + reset of hist / completion counter / dE accumulator
+        L.check(lib.vq_prepare_step(P(E), K, D, P(e2), P(ehi), P(elo), P(hist), P(ws), wsb, P(dE), st))
         L.check(lib.vq_forward(P(z), P(E), P(e2), P(ehi), P(elo), N, K, D, BETA, fwd_flags, P(q), P(idx), P(onehot),
                                P(hist), P(sse), scal.data_ptr(), scal.data_ptr() + 4, P(ws), wsb, st))
         L.check(lib.vq_backward(P(gs[i % nbuf]), P(g_loss), P(z), P(E), P(idx), N, N, n_dE, K, D, BETA, bwd_flags,

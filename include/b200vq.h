@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VQ_ABI_VERSION 7
+#define VQ_ABI_VERSION 8
 
 /* error codes */
 #define VQ_OK            0
@@ -46,6 +46,7 @@ extern "C" {
 #define VQ_FLAG_NO_QUANT   (1 << 4)  /* forward: indices/hist only; q_out, sse, loss are not produced */
 #define VQ_FLAG_TC_1CTA    (1 << 6)  /* forward: single-CTA tensor kernel (M=128,N=128) even when the CTA-pair kernel applies */
 #define VQ_FLAG_NO_FUSE    (1 << 7)  /* forward: keep argmin and the row epilogue as two kernels (default: fused into one) */
+#define VQ_FLAG_STATE_READY (1 << 8) /* forward: vq_prepare_step already reset hist and the workspace counter for this call */
 #define VQ_FLAG_ZERO_DE    (1 << 5)  /* backward: zero dE (memset on `stream`) before accumulating into it */
 
 typedef void* vq_stream_t;   /* cudaStream_t */
@@ -77,6 +78,12 @@ void        vq_debug_set_trace(long long* device_buffer);
  * E_hi / E_lo may be NULL when only the exact path will be used. */
 int vq_prepare_codebook(const float* E, int K, int D,
                         float* e_norm2, float* E_hi, float* E_lo, vq_stream_t stream);
+
+/* vq_prepare_codebook plus the per-step state reset in the same launch: zeroes hist (K), the completion
+ * counter inside `workspace`, and -- when not NULL -- the dE accumulator (K*D).  Pass VQ_FLAG_STATE_READY to the
+ * vq_forward that follows (and no VQ_FLAG_ZERO_DE to vq_backward) to skip their own resets. */
+int vq_prepare_step(const float* E, int K, int D, float* e_norm2, float* E_hi, float* E_lo,
+                    float* hist, void* workspace, size_t workspace_bytes, float* dE, vq_stream_t stream);
 
 /* -- forward: vector_quantizer.py:29-58 ------------------------------------------------------ */
 size_t vq_workspace_bytes(int64_t n_rows, int K, int D, int flags);
