@@ -48,7 +48,7 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 // ---- optional per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream ------
-enum KernelId { KID_PREP = 0, KID_ARGMIN_TC, KID_ARGMIN_SIMT, KID_ROWS, KID_BACKWARD, KID_FINALIZE, KID_ONEHOT, KID_COUNT };
+enum KernelId { KID_PREP = 0, KID_ARGMIN_TC, KID_ARGMIN_SIMT, KID_ROWS, KID_BACKWARD, KID_FINALIZE, KID_ONEHOT, KID_ALLREDUCE, KID_COUNT };
 struct ProfSlot { cudaEvent_t a, b; int kid; };
 bool g_prof_on = false;
 std::vector<ProfSlot> g_prof_slots;
@@ -524,6 +524,57 @@ int vq_backward(const float* g_q, const float* g_loss, const float* z, const flo
 #undef BWD_LAUNCH
 #undef BWD_ARGS
     LAUNCH_CHECK("backward_kernel");
+    return VQ_OK;
+}
+
+// One-shot all-reduce over NVLink peer memory (see allreduce_oneshot_kernel).  peer_buffers: host array of `world`
+// device pointers, entry p = rank p's symmetric buffer as mapped into THIS process (entry `rank` = our own).
+int vq_allreduce_sum(const void* const* peer_buffers, int world, int rank, int64_t flag_offset_floats, int64_t n_floats,
+                     uint32_t seq, float* out, vq_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    if (peer_buffers == nullptr || out == nullptr || world < 1 || world > AR_MAX_RANKS || rank < 0 || rank >= world ||
+        n_floats < 0 || flag_offset_floats < n_floats)
+        return fail(VQ_ERR_ARG, "vq_allreduce_sum: bad argument (world=%d rank=%d)", world, rank);
+    PeerBuffers pb{};
+    for (int p = 0; p < world; ++p) {
+        if (peer_buffers[p] == nullptr || !aligned16(peer_buffers[p])) return fail(VQ_ERR_ARG, "vq_allreduce_sum: peer buffer %d is NULL or misaligned", p);
+        pb.buf[p] = static_cast<float*>(const_cast<void*>(peer_buffers[p]));
+    }
+    if (!aligned16(out)) return fail(VQ_ERR_ARG, "vq_allreduce_sum: out is misaligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    long long blocks = (n_floats / 4 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 64) blocks = 64;
+    ProfScope prof(KID_ALLREDUCE, st);
+    cudaError_t e = launch_pdl(allreduce_oneshot_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, pb, world, rank,
+                               static_cast<long long>(flag_offset_floats), static_cast<long long>(n_floats), seq, out);
+    if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of allreduce_oneshot_kernel failed: %s", cudaGetErrorString(e));
+    LAUNCH_CHECK("allreduce_oneshot_kernel");
+    return VQ_OK;
+}
+
+// Push ("low-latency") all-reduce: see allreduce_push_kernel.  recv_buffers[p] = rank p's symmetric RECEIVE buffer
+// (world slots of lines_per_slot 16-byte lines, zero-initialised) as mapped into this process.
+int vq_allreduce_push(const void* const* recv_buffers, int world, int rank, const float* payload, int64_t n_floats,
+                      uint32_t seq, float* out, vq_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    if (recv_buffers == nullptr || payload == nullptr || out == nullptr || world < 1 || world > AR_MAX_RANKS || rank < 0 ||
+        rank >= world || n_floats < 1 || seq == 0)
+        return fail(VQ_ERR_ARG, "vq_allreduce_push: bad argument (world=%d rank=%d seq=%u)", world, rank, seq);
+    PeerBuffers pb{};
+    for (int p = 0; p < world; ++p) {
+        if (recv_buffers[p] == nullptr || !aligned16(recv_buffers[p])) return fail(VQ_ERR_ARG, "vq_allreduce_push: receive buffer %d is NULL or misaligned", p);
+        pb.buf[p] = static_cast<float*>(const_cast<void*>(recv_buffers[p]));
+    }
+    const long long lines = (n_floats + 1) / 2;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    long long blocks = (lines + 255) / 256;
+    if (blocks > kNumSMs) blocks = kNumSMs;
+    ProfScope prof(KID_ALLREDUCE, st);
+    cudaError_t e = launch_pdl(allreduce_push_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, pb, world, rank, lines,
+                               payload, static_cast<long long>(n_floats), seq, out);
+    if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of allreduce_push_kernel failed: %s", cudaGetErrorString(e));
+    LAUNCH_CHECK("allreduce_push_kernel");
     return VQ_OK;
 }
 

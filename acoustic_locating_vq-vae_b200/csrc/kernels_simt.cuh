@@ -419,4 +419,128 @@ __global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// one-shot all-reduce over NVLink peer memory (data parallel: the packed [dE | hist | sse] buffer).
+// Every rank owns a symmetric buffer [payload | flags]; `peers.buf[p]` is rank p's buffer mapped into this
+// process (torch symmetric memory / CUDA IPC).  Protocol per call (sequence number `seq`, strictly increasing):
+//   1. block 0 publishes "my payload for `seq` is complete" into every peer's flag slot [rank];
+//   2. every block waits until all peers have published `seq` into OUR flags;
+//   3. out[i] = sum over ranks p = 0..W-1 (fixed order => bit-identical on every rank) of peer p's payload[i],
+//      read with system-scope loads that bypass the local L1 (peer lines are never cached in local L2).
+// The caller alternates between two symmetric buffers, so a buffer is rewritten only after every peer has
+// passed the barrier of the following call, i.e. finished reading it: no second barrier is needed.
+// ---------------------------------------------------------------------------------------------
+constexpr int AR_MAX_RANKS = 16;
+struct PeerBuffers {
+    float* buf[AR_MAX_RANKS];
+};
+
+__device__ __forceinline__ float4 ld_sys_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_sys_f1(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) allreduce_oneshot_kernel(PeerBuffers peers, int world, int rank,
+                                                                long long flag_off_floats, long long n, unsigned int seq,
+                                                                float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait_prior_grids();            // our own payload (written by the backward kernel) is complete
+    if (blockIdx.x == 0 && threadIdx.x < world) {
+        __threadfence_system();
+        unsigned int* peer_flags = reinterpret_cast<unsigned int*>(peers.buf[threadIdx.x] + flag_off_floats);
+        st_release_sys_u32(peer_flags + rank, seq);
+    }
+    if (threadIdx.x < world) {
+        const unsigned int* my_flags = reinterpret_cast<const unsigned int*>(peers.buf[rank] + flag_off_floats);
+        // sequence numbers only grow; "seq - flag" wraps negative (as int) once the peer has caught up
+        while (static_cast<int>(seq - ld_acquire_sys_u32(my_flags + threadIdx.x)) > 0) {
+        }
+    }
+    __syncthreads();
+    const long long n4 = n >> 2;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p < world; ++p) {
+            const float4 v = ld_sys_f4(reinterpret_cast<const float4*>(peers.buf[p]) + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(out)[i] = acc;
+    }
+    for (long long i = (n4 << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float acc = 0.f;
+        for (int p = 0; p < world; ++p) acc += ld_sys_f1(peers.buf[p] + i);
+        out[i] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// push ("low-latency") all-reduce: ONE NVLink one-way latency, no barrier.
+// Every rank owns a symmetric RECEIVE buffer of `world` slots; slot s holds rank s's contribution as 16-byte
+// lines {d0, seq, d1, seq}: the data and the sequence number of the call travel in the same store, so a line
+// whose two flag words equal `seq` is complete (16-byte stores may tear only at 8-byte granularity).
+//   1. every thread reads its part of the LOCAL payload and stores the lines into slot [rank] of every rank's
+//      receive buffer (remote stores over NVLink; the local one included);
+//   2. the same thread then polls ITS lines in all `world` local slots and sums them in rank order
+//      (bit-identical on every rank), writing `out`.
+// Two receive buffers alternate between calls: a peer can overwrite a slot for call c+2 only after it has
+// finished call c+1, which needed OUR contribution to c+1, which we send after having finished reading call c.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_volatile_v4(uint4* p, uint4 v) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) allreduce_push_kernel(PeerBuffers recv, int world, int rank, long long lines_per_slot,
+                                                             const float* __restrict__ payload, long long n,
+                                                             unsigned int seq, float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait_prior_grids();            // the local payload (written by the backward kernel) is complete
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long first = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    // 1. push: line i carries payload[2i], payload[2i+1]
+    for (long long i = first; i < lines_per_slot; i += stride) {
+        const float d0 = payload[2 * i];
+        const float d1 = (2 * i + 1 < n) ? payload[2 * i + 1] : 0.0f;
+        const uint4 line = make_uint4(__float_as_uint(d0), seq, __float_as_uint(d1), seq);
+        for (int p = 0; p < world; ++p) {
+            const int dst = (rank + p) % world;        // spread the ranks' first targets over the links
+            st_volatile_v4(reinterpret_cast<uint4*>(recv.buf[dst]) + static_cast<long long>(rank) * lines_per_slot + i, line);
+        }
+    }
+    // 2. poll our own receive slots and reduce in rank order
+    const uint4* mine = reinterpret_cast<const uint4*>(recv.buf[rank]);
+    for (long long i = first; i < lines_per_slot; i += stride) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int p = 0; p < world; ++p) {
+            uint4 v;
+            do {
+                v = ld_volatile_v4(mine + static_cast<long long>(p) * lines_per_slot + i);
+            } while (v.y != seq || v.w != seq);
+            a0 += __uint_as_float(v.x);
+            a1 += __uint_as_float(v.z);
+        }
+        out[2 * i] = a0;
+        if (2 * i + 1 < n) out[2 * i + 1] = a1;
+    }
+}
+
 }  // namespace b200vq

@@ -65,3 +65,99 @@ def global_row_count(n_rows_local: int, group=None, equal_shards: bool = True) -
         t = t.cuda()
     dist.all_reduce(t, group=group)
     return int(t.item())
+
+
+class SymmetricAllReduce:
+    """One-shot sum all-reduce of the packed step buffer over NVLink peer memory (vq_allreduce_sum).
+
+    Two symmetric buffers ([payload | flags], torch symmetric memory) alternate between calls; the kernel does a
+    flag barrier and sums the peers' payloads in rank order, so every rank gets bit-identical results.  The
+    backward kernel accumulates dE straight into `payload()`; `reduce()` returns the reduced packed buffer.
+    Falls back to NCCL (`all_reduce_packed`) when symmetric memory cannot be set up.
+    """
+
+    def __init__(self, n_floats: int, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.lib = _lib.load()
+        self.check = _lib.check
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.n = n_floats
+        self.flag_off = (n_floats + 63) // 64 * 64                   # flags start on a 256-byte boundary
+        total = self.flag_off + 64
+        self.bufs, self.ptr_arrays = [], []
+        for _ in range(2):
+            t = symm_mem.empty(total, dtype=torch.float32, device=device)
+            t.zero_()
+            hdl = symm_mem.rendezvous(t, self.group)
+            ptrs = list(hdl.buffer_ptrs)
+            import ctypes
+            arr = (ctypes.c_void_p * self.world)(*ptrs)
+            self.bufs.append(t)
+            self.ptr_arrays.append(arr)
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)                                     # zero-initialised flags are in place everywhere
+        self.out = torch.zeros(n_floats, dtype=torch.float32, device=device)
+        self.seq = 0
+
+    def payload(self) -> torch.Tensor:
+        """The buffer the NEXT reduce() will contribute (write the local partial result here)."""
+        return self.bufs[self.seq & 1][:self.n]
+
+    def reduce(self, stream_ptr: int) -> torch.Tensor:
+        which = self.seq & 1
+        self.seq += 1
+        seq_no = (self.seq + 1) // 2                                 # 1, 1, 2, 2, ...: per-buffer sequence number
+        self.check(self.lib.vq_allreduce_sum(self.ptr_arrays[which], self.world, self.rank, self.flag_off, self.n,
+                                             seq_no, self.out.data_ptr(), stream_ptr))
+        return self.out
+
+
+class PushAllReduce:
+    """Low-latency push all-reduce of the packed step buffer over NVLink peer memory (vq_allreduce_push).
+
+    Each rank owns two symmetric RECEIVE buffers (alternating between calls) of `world` slots; a call stores the
+    local payload -- data and sequence number in the same 16-byte line -- into slot [rank] of every rank's
+    receive buffer and then sums its own slots in rank order as the lines arrive: one NVLink one-way latency,
+    no barrier, bit-identical results on every rank.  `payload` is ordinary device memory (the backward kernel
+    accumulates dE straight into it).
+    """
+
+    def __init__(self, n_floats: int, device, group=None):
+        import ctypes
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.lib = _lib.load()
+        self.check = _lib.check
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.n = n_floats
+        lines = (n_floats + 1) // 2
+        self.bufs, self.ptr_arrays = [], []
+        for _ in range(2):
+            t = symm_mem.empty(self.world * lines * 4, dtype=torch.float32, device=device)
+            t.zero_()
+            hdl = symm_mem.rendezvous(t, self.group)
+            self.bufs.append(t)
+            self.ptr_arrays.append((ctypes.c_void_p * self.world)(*list(hdl.buffer_ptrs)))
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)                      # zero-initialised receive buffers are in place everywhere
+        self.payload_buf = torch.zeros(n_floats, dtype=torch.float32, device=device)
+        self.out = torch.zeros(n_floats, dtype=torch.float32, device=device)
+        self.seq = 0
+
+    def payload(self) -> torch.Tensor:
+        return self.payload_buf
+
+    def reduce(self, stream_ptr: int) -> torch.Tensor:
+        which = self.seq & 1
+        self.seq += 1
+        seq_no = (self.seq + 1) // 2                  # 1, 1, 2, 2, ...: per-buffer sequence number (never 0)
+        self.check(self.lib.vq_allreduce_push(self.ptr_arrays[which], self.world, self.rank, self.payload_buf.data_ptr(),
+                                              self.n, seq_no, self.out.data_ptr(), stream_ptr))
+        return self.out

@@ -120,10 +120,15 @@ class _VQFunction(torch.autograd.Function):
             world = dist.get_world_size(pg)
         packed = None
         dE = None
+        push = None
         if need_dE:
             if world > 1:
-                # one all-reduce per step over [dE | hist | sse]  
-                packed = parallel.new_packed(K, D, dev)
+                # one all-reduce per step over [dE | hist | sse]  (SURVEY.md section 8e): our own low-latency push
+                # kernel over NVLink peer memory when symmetric memory is available, NCCL otherwise
+                push = module._push_allreduce(K, D, dev, pg)
+                packed = push.payload() if push is not None else parallel.new_packed(K, D, dev)
+                if push is not None:
+                    packed.zero_()
                 dE = parallel.packed_views(packed, K, D)[0]
             else:
                 dE = torch.zeros(K, D, dtype=torch.float32, device=dev)
@@ -136,8 +141,13 @@ class _VQFunction(torch.autograd.Function):
                               max(N, 1) * world, K, D, float(module._commitment_cost), flags, _ptr(dz), _ptr(dE), st))
         if packed is not None:
             packed[K * D:] = ctx.stats[:K + 1]
-            parallel.all_reduce_packed(packed, pg)
-            module._global_stats = (packed[K * D:], N * world)
+            if push is not None:
+                reduced = push.reduce(st)
+                dE = reduced[:K * D].view(K, D).clone()       # `reduced` is reused by the next step
+                module._global_stats = (reduced[K * D:].clone(), N * world)
+            else:
+                parallel.all_reduce_packed(packed, pg)
+                module._global_stats = (packed[K * D:], N * world)
         return (dz if need_dz else None), dE, None, None, None
 
 
@@ -173,6 +183,7 @@ class VectorQuantizer(nn.Module):
         self._bufs = _Buffers()
         self._last_stats = None
         self._global_stats = None
+        self._push_ar = None
         self.last_indices = None
 
     # -- reference accessors (vector_quantizer.py:23-27) ------------------------------------------
@@ -190,6 +201,7 @@ class VectorQuantizer(nn.Module):
         s["_global_stats"] = None
         s["last_indices"] = None
         s["process_group"] = None
+        s["_push_ar"] = None
         return s
 
     def __setstate__(self, s):
@@ -217,6 +229,21 @@ class VectorQuantizer(nn.Module):
             inputs, weight, self, flags, bool(self.return_encodings))
         self.last_indices = idx
         return loss, quantized, perplexity, encodings
+
+    def _push_allreduce(self, K, D, dev, pg):
+        """Lazily set up the NVLink push all-reduce (parallel.PushAllReduce); None -> use NCCL."""
+        if self._push_ar is False:
+            return None
+        if self._push_ar is None:
+            try:
+                import torch.distributed as dist
+                if dist.get_backend(pg) != "nccl":
+                    raise RuntimeError("not an NCCL group")
+                self._push_ar = parallel.PushAllReduce(parallel.packed_size(K, D), dev, pg)
+            except Exception:
+                self._push_ar = False
+                return None
+        return self._push_ar
 
     # -- extras ------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -15,7 +15,7 @@ Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   e2e           same metric through the host-buffer C ABI (pinned host z in, loss/perplexity/indices out)
   kernels       per-kernel share of the step (CUDA events on the launching stream)
 Under torchrun (N > 1) every rank runs the same per-rank workload on its own rows (weak scaling) and
-all-reduces the packed [dE | hist | sse] buffer once per step with NCCL.
+all-reduces the packed [dE | hist | sse] buffer once per step (own one-shot NVLink kernel; --nccl for NCCL).
 """
 from __future__ import annotations
 
@@ -44,7 +44,7 @@ WORKLOADS = {
 }
 BETA = 0.25
 L2_BYTES = 126 * 1024 * 1024
-KERNEL_NAMES = ["prepare_codebook", "argmin_tc", "argmin_exact", "rows", "backward", "finalize", "onehot"]
+KERNEL_NAMES = ["prepare_codebook", "argmin_tc", "argmin_exact", "rows", "backward", "finalize", "onehot", "allreduce"]
 
 
 def load_peaks():
@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--exact", action="store_true", help="CUDA-core exact path instead of tcgen05")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-fuse", action="store_true", help="argmin and row epilogue as two kernels (VQ_FLAG_NO_FUSE)")
+    ap.add_argument("--nccl", action="store_true", help="N > 1: use NCCL for the per-step all-reduce instead of vq_allreduce_sum")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()
@@ -229,8 +230,23 @@ def main():
     e2 = torch.empty(K, device=dev); ehi = torch.empty(K, D, device=dev); elo = torch.empty(K, D, device=dev)
     q = torch.empty(N, D, device=dev); idx = torch.empty(N, dtype=torch.int32, device=dev)
     onehot = torch.empty(N, K, device=dev) if emit_onehot else None
-    packed = torch.zeros(K * D + K + 1, device=dev)                   # [dE | hist | sse] -> one all-reduce
-    dE = packed[:K * D]; hist = packed[K * D:K * D + K]; sse = packed[K * D + K:]
+    # [dE | hist | sse] -> one all-reduce per step.  With N > 1 the buffer lives in symmetric (peer-mapped) memory and
+    # is reduced by our own one-shot NVLink kernel (vq_allreduce_sum); NCCL is the fallback.
+    n_packed = K * D + K + 1
+    sym = None
+    collective = "none"
+    if world > 1 and not args.nccl:
+        try:
+            par = import_module("acoustic_locating_vq-vae_b200.parallel")
+            sym = par.PushAllReduce(n_packed, dev)
+            collective = "low-latency push all-reduce over NVLink peer memory (vq_allreduce_push)"
+        except Exception as e:      # symmetric memory unavailable: keep going with NCCL
+            sym = None
+            collective = f"NCCL all_reduce (symmetric memory unavailable: {type(e).__name__})"
+    elif world > 1:
+        collective = "NCCL all_reduce"
+    packs = [sym.payload()] if sym is not None else [torch.zeros(n_packed, device=dev)]
+    views = [(pk[:K * D], pk[K * D:K * D + K], pk[K * D + K:]) for pk in packs]
     scal = torch.empty(2, device=dev)                                 # loss, perplexity
     dz = torch.empty(N, D, device=dev)
     g_loss = torch.ones((), device=dev)
@@ -245,14 +261,17 @@ def main():
 
     def step(i):
         z = zs[i % nbuf]
+        dE, hist, sse = views[0]
         # one launch: codebook norms + tf32 split + reset of hist / completion counter / dE accumulator
         L.check(lib.vq_prepare_step(P(E), K, D, P(e2), P(ehi), P(elo), P(hist), P(ws), wsb, P(dE), st))
         L.check(lib.vq_forward(P(z), P(E), P(e2), P(ehi), P(elo), N, K, D, BETA, fwd_flags, P(q), P(idx), P(onehot),
                                P(hist), P(sse), scal.data_ptr(), scal.data_ptr() + 4, P(ws), wsb, st))
         L.check(lib.vq_backward(P(gs[i % nbuf]), P(g_loss), P(z), P(E), P(idx), N, N, n_dE, K, D, BETA, bwd_flags,
                                 P(dz), P(dE), st))
-        if world > 1:
-            dist.all_reduce(packed)
+        if sym is not None:
+            sym.reduce(st)                       # reduced [dE | hist | sse] lands in sym.out
+        elif world > 1:
+            dist.all_reduce(packs[0])
 
     def barrier():
         if world > 1:
@@ -403,7 +422,7 @@ def main():
                        "encodings": "dense one-hot emitted" if emit_onehot else "indices only",
                        "path": "exact CUDA-core" if args.exact else ("tcgen05" if lib.vq_forward_uses_tensor_path(N, K, D, fwd_flags) else "exact CUDA-core"),
                        "l2": f"inputs rotate over {nbuf} z + {nbuf} g buffers ({2 * nbuf * N * D * 4 >> 20} MiB > 126 MiB L2)",
-                       "parallelism": f"dp{world}: rows sharded, one NCCL all-reduce of [dE|hist|sse] per step" if world > 1 else "single GPU"},
+                       "parallelism": f"dp{world}: rows sharded, one all-reduce of [dE|hist|sse] per step: {collective}" if world > 1 else "single GPU"},
             "clocks": sampler.summary(),
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "kernels": kern,
             "loss": loss_val, "perplexity": perp_val,

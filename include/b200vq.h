@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VQ_ABI_VERSION 8
+#define VQ_ABI_VERSION 10
 
 /* error codes */
 #define VQ_OK            0
@@ -120,6 +120,23 @@ int vq_onehot(const int32_t* idx, int64_t n_rows, int K, float* onehot, vq_strea
 int vq_backward(const float* g_q, const float* g_loss, const float* z, const float* E,
                 const int32_t* idx, int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE,
                 int K, int D, float beta, int flags, float* dz, float* dE, vq_stream_t stream);
+
+/* -- data parallel: one-shot all-reduce over NVLink peer memory ------------------------------------------ */
+/* out[i] = sum over ranks (in rank order: bit-identical everywhere) of rank p's payload[i], i < n_floats.
+ * peer_buffers[p] = rank p's symmetric buffer as mapped into this process (torch symmetric memory / CUDA IPC),
+ * laid out [payload (n_floats) ... | flags at flag_offset_floats: `world` uint32, zero-initialised].
+ * `seq` must increase by one per call on a given buffer pair; callers alternate between TWO buffers so that a
+ * buffer is only rewritten after every peer has passed the next call's barrier.  4 <= kid 7 in vq_profile_read. */
+int vq_allreduce_sum(const void* const* peer_buffers, int world, int rank, int64_t flag_offset_floats,
+                     int64_t n_floats, uint32_t seq, float* out, vq_stream_t stream);
+
+/* Push ("low-latency") variant: one NVLink one-way latency, no barrier.  recv_buffers[p] = rank p's symmetric
+ * RECEIVE buffer as mapped into this process: `world` slots of ceil(n_floats/2) 16-byte lines {d0, seq, d1, seq},
+ * zero-initialised.  Every rank stores its payload into slot [rank] of every receive buffer, then polls its own
+ * slots until all lines carry `seq` and sums them in rank order.  `seq` >= 1 and increases by one per call on a
+ * given buffer; callers alternate between TWO receive buffers. */
+int vq_allreduce_push(const void* const* recv_buffers, int world, int rank, const float* payload,
+                      int64_t n_floats, uint32_t seq, float* out, vq_stream_t stream);
 
 /* -- host-buffer entry points (what a non-torch caller binds; used for the end-to-end figure) - */
 typedef struct vq_host_ctx vq_host_ctx;
