@@ -555,8 +555,8 @@ int vq_allreduce_sum(const void* const* peer_buffers, int world, int rank, int64
 
 // Push ("low-latency") all-reduce: see allreduce_push_kernel.  recv_buffers[p] = rank p's symmetric RECEIVE buffer
 // (world slots of lines_per_slot 16-byte lines, zero-initialised) as mapped into this process.
-int vq_allreduce_push(const void* const* recv_buffers, int world, int rank, const float* payload, int64_t n_floats,
-                      uint32_t seq, float* out, vq_stream_t stream) {
+int vq_allreduce_push(const void* const* recv_buffers, void* multicast_or_null, int world, int rank, const float* payload,
+                      int64_t n_floats, uint32_t seq, float* out, vq_stream_t stream) {
     if (int rc = check_device()) return rc;
     if (recv_buffers == nullptr || payload == nullptr || out == nullptr || world < 1 || world > AR_MAX_RANKS || rank < 0 ||
         rank >= world || n_floats < 1 || seq == 0)
@@ -571,8 +571,8 @@ int vq_allreduce_push(const void* const* recv_buffers, int world, int rank, cons
     long long blocks = (lines + 255) / 256;
     if (blocks > kNumSMs) blocks = kNumSMs;
     ProfScope prof(KID_ALLREDUCE, st);
-    cudaError_t e = launch_pdl(allreduce_push_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, pb, world, rank, lines,
-                               payload, static_cast<long long>(n_floats), seq, out);
+    cudaError_t e = launch_pdl(allreduce_push_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, pb,
+                               static_cast<float*>(multicast_or_null), world, rank, lines, payload, static_cast<long long>(n_floats), seq, out);
     if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of allreduce_push_kernel failed: %s", cudaGetErrorString(e));
     LAUNCH_CHECK("allreduce_push_kernel");
     return VQ_OK;

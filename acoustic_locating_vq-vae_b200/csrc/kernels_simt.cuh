@@ -509,9 +509,16 @@ __device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
     return v;
 }
 
-__global__ void __launch_bounds__(256) allreduce_push_kernel(PeerBuffers recv, int world, int rank, long long lines_per_slot,
-                                                             const float* __restrict__ payload, long long n,
-                                                             unsigned int seq, float* __restrict__ out) {
+// one store, delivered by the NVSwitch to the same offset of EVERY rank's buffer (NVLS multicast mapping)
+__device__ __forceinline__ void multimem_st_v4(void* mc_addr, uint4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(256) allreduce_push_kernel(PeerBuffers recv, float* multicast, int world, int rank,
+                                                             long long lines_per_slot, const float* __restrict__ payload,
+                                                             long long n, unsigned int seq, float* __restrict__ out) {
     pdl_launch_dependents();
     pdl_wait_prior_grids();            // the local payload (written by the backward kernel) is complete
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -521,22 +528,32 @@ __global__ void __launch_bounds__(256) allreduce_push_kernel(PeerBuffers recv, i
         const float d0 = payload[2 * i];
         const float d1 = (2 * i + 1 < n) ? payload[2 * i + 1] : 0.0f;
         const uint4 line = make_uint4(__float_as_uint(d0), seq, __float_as_uint(d1), seq);
-        for (int p = 0; p < world; ++p) {
-            const int dst = (rank + p) % world;        // spread the ranks' first targets over the links
-            st_volatile_v4(reinterpret_cast<uint4*>(recv.buf[dst]) + static_cast<long long>(rank) * lines_per_slot + i, line);
+        if (multicast != nullptr) {
+            // NVLS: the switch replicates this single store into slot [rank] of every rank's receive buffer
+            multimem_st_v4(reinterpret_cast<uint4*>(multicast) + static_cast<long long>(rank) * lines_per_slot + i, line);
+        } else {
+            for (int p = 0; p < world; ++p) {
+                const int dst = (rank + p) % world;    // spread the ranks' first targets over the links
+                st_volatile_v4(reinterpret_cast<uint4*>(recv.buf[dst]) + static_cast<long long>(rank) * lines_per_slot + i, line);
+            }
         }
     }
-    // 2. poll our own receive slots and reduce in rank order
+    // 2. poll our own receive slots and reduce in rank order.  All slots of a line are requested together
+    //    (independent loads in flight), then only the ones that have not arrived yet are re-polled.
     const uint4* mine = reinterpret_cast<const uint4*>(recv.buf[rank]);
     for (long long i = first; i < lines_per_slot; i += stride) {
+        uint4 v[AR_MAX_RANKS];
+#pragma unroll
+        for (int p = 0; p < AR_MAX_RANKS; ++p)
+            if (p < world) v[p] = ld_volatile_v4(mine + static_cast<long long>(p) * lines_per_slot + i);
         float a0 = 0.f, a1 = 0.f;
-        for (int p = 0; p < world; ++p) {
-            uint4 v;
-            do {
-                v = ld_volatile_v4(mine + static_cast<long long>(p) * lines_per_slot + i);
-            } while (v.y != seq || v.w != seq);
-            a0 += __uint_as_float(v.x);
-            a1 += __uint_as_float(v.z);
+#pragma unroll
+        for (int p = 0; p < AR_MAX_RANKS; ++p) {
+            if (p < world) {
+                while (v[p].y != seq || v[p].w != seq) v[p] = ld_volatile_v4(mine + static_cast<long long>(p) * lines_per_slot + i);
+                a0 += __uint_as_float(v[p].x);
+                a1 += __uint_as_float(v[p].z);
+            }
         }
         out[2 * i] = a0;
         if (2 * i + 1 < n) out[2 * i + 1] = a1;

@@ -13,6 +13,7 @@ the same value DDP's gradient averaging of per-rank mean losses yields for equal
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -138,13 +139,19 @@ class PushAllReduce:
         self.rank = dist.get_rank(self.group)
         self.n = n_floats
         lines = (n_floats + 1) // 2
-        self.bufs, self.ptr_arrays = [], []
+        self.bufs, self.ptr_arrays, self.mc_ptrs = [], [], []
+        use_mc = os.environ.get("B200VQ_NVLS", "1") != "0"
         for _ in range(2):
             t = symm_mem.empty(self.world * lines * 4, dtype=torch.float32, device=device)
             t.zero_()
             hdl = symm_mem.rendezvous(t, self.group)
             self.bufs.append(t)
             self.ptr_arrays.append((ctypes.c_void_p * self.world)(*list(hdl.buffer_ptrs)))
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if use_mc else 0
+            self.mc_ptrs.append(mc if mc != 0 else None)
+        self.nvls = all(m is not None for m in self.mc_ptrs)
+        if not self.nvls:
+            self.mc_ptrs = [None, None]
         torch.cuda.synchronize(device)
         dist.barrier(self.group)                      # zero-initialised receive buffers are in place everywhere
         self.payload_buf = torch.zeros(n_floats, dtype=torch.float32, device=device)
@@ -158,6 +165,6 @@ class PushAllReduce:
         which = self.seq & 1
         self.seq += 1
         seq_no = (self.seq + 1) // 2                  # 1, 1, 2, 2, ...: per-buffer sequence number (never 0)
-        self.check(self.lib.vq_allreduce_push(self.ptr_arrays[which], self.world, self.rank, self.payload_buf.data_ptr(),
-                                              self.n, seq_no, self.out.data_ptr(), stream_ptr))
+        self.check(self.lib.vq_allreduce_push(self.ptr_arrays[which], self.mc_ptrs[which], self.world, self.rank,
+                                              self.payload_buf.data_ptr(), self.n, seq_no, self.out.data_ptr(), stream_ptr))
         return self.out

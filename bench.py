@@ -239,7 +239,7 @@ def main():
         try:
             par = import_module("acoustic_locating_vq-vae_b200.parallel")
             sym = par.PushAllReduce(n_packed, dev)
-            collective = "low-latency push all-reduce over NVLink peer memory (vq_allreduce_push)"
+            collective = "low-latency push all-reduce over NVLink peer memory (vq_allreduce_push, " + ("NVLS multimem.st" if sym.nvls else "P2P stores") + ")"
         except Exception as e:      # symmetric memory unavailable: keep going with NCCL
             sym = None
             collective = f"NCCL all_reduce (symmetric memory unavailable: {type(e).__name__})"

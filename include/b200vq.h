@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VQ_ABI_VERSION 10
+#define VQ_ABI_VERSION 11
 
 /* error codes */
 #define VQ_OK            0
@@ -135,8 +135,10 @@ int vq_allreduce_sum(const void* const* peer_buffers, int world, int rank, int64
  * zero-initialised.  Every rank stores its payload into slot [rank] of every receive buffer, then polls its own
  * slots until all lines carry `seq` and sums them in rank order.  `seq` >= 1 and increases by one per call on a
  * given buffer; callers alternate between TWO receive buffers. */
-int vq_allreduce_push(const void* const* recv_buffers, int world, int rank, const float* payload,
-                      int64_t n_floats, uint32_t seq, float* out, vq_stream_t stream);
+int vq_allreduce_push(const void* const* recv_buffers, void* multicast_or_null, int world, int rank,
+                      const float* payload, int64_t n_floats, uint32_t seq, float* out, vq_stream_t stream);
+/* multicast_or_null: the NVLS multicast mapping of the same receive buffer (torch symmetric memory's
+ * `multicast_ptr`); when given, each line is sent with ONE multimem.st that the NVSwitch replicates to all ranks. */
 
 /* -- host-buffer entry points (what a non-torch caller binds; used for the end-to-end figure) - */
 typedef struct vq_host_ctx vq_host_ctx;

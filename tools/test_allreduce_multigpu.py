@@ -36,5 +36,5 @@ for name, fn in (("vq_allreduce_sum", lambda: ar.reduce(st)), ("nccl all_reduce"
     for _ in range(200): fn()
     b.record(); torch.cuda.synchronize()
     if rank == 0: print(f"{name}: {a.elapsed_time(b) / 200 * 1e3:.1f} us per call ({n * 4 / 1024:.0f} KiB, {world} ranks)")
-if rank == 0: print("ALLREDUCE TEST", "PASSED" if ok else "FAILED")
+if rank == 0: print("ALLREDUCE TEST", "PASSED" if ok else "FAILED", "| nvls:", getattr(ar, "nvls", None))
 dist.destroy_process_group()
