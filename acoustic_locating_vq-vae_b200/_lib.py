@@ -9,7 +9,7 @@ import os
 
 from .build import SO_PATH
 
-ABI_VERSION = 11
+ABI_VERSION = 13
 
 FLAG_ONEHOT = 1 << 0
 FLAG_TRAIN_VQ = 1 << 1
@@ -20,6 +20,8 @@ FLAG_ZERO_DE = 1 << 5
 FLAG_TC_1CTA = 1 << 6
 FLAG_NO_FUSE = 1 << 7
 FLAG_STATE_READY = 1 << 8
+FLAG_NO_SCREEN = 1 << 9
+FLAG_SCREEN = 1 << 10
 
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64

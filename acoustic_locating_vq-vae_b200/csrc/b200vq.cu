@@ -17,6 +17,7 @@
 
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_screen.cuh"
 
 using namespace b200vq;
 
@@ -142,8 +143,12 @@ bool tensor_path_ok(long long N, int K, int D, int flags, const float* z = nullp
                     const float* elo = nullptr, bool check_ptrs = false) {
     if (flags & VQ_FLAG_EXACT) return false;
     if (N < 1 || N >= (1ll << 31) - TC_ROWS) return false;
-    if (D % TC_SLAB_FLOATS != 0 || D < 32 || D > 128) return false;
+    if (D % TC_SLAB_FLOATS != 0 || D < 32 || D > 256) return false;
     if (K % TC_CODES != 0 || K < TC_CODES) return false;
+    // D in (128, 256] (and D = 160, 224) only fits the screen+refine kernel (tf32(z) alone in shared memory)
+    const bool screen_shape = (K % TC2_CODES == 0) && (D <= 128 || D == 192 || D == 256) && !(flags & VQ_FLAG_NO_SCREEN) &&
+                              !(flags & VQ_FLAG_NO_FUSE) && !(flags & VQ_FLAG_TC_1CTA);
+    if (D > 128 && !screen_shape) return false;
     if (check_ptrs && (ehi == nullptr || elo == nullptr || !aligned16(z) || !aligned16(ehi) || !aligned16(elo))) return false;
     return true;
 }
@@ -251,6 +256,36 @@ int launch_tc2(const CUtensorMap& tz, const CUtensorMap& thi, const CUtensorMap&
         LAUNCH_CHECK("argmin_tc2_kernel");
     }
     return VQ_OK;
+}
+
+template <int NSLAB, int NSTAGE, int ZBUF>
+int launch_screen(const CUtensorMap& tz, const CUtensorMap& thi, const float* e_norm2, long long N, int K, int* idx,
+                  float* hist, unsigned int* counter, const FusedRowArgs& fused, bool state_ready, cudaStream_t st) {
+    constexpr int smem = sc_smem_bytes(NSLAB, NSTAGE, ZBUF);
+    static_assert(smem <= 232448, "screen kernel exceeds 227 KB of shared memory");
+    static bool configured = false;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(vq_screen_kernel<NSLAB, NSTAGE, ZBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const long long row_tiles = (N + TC_ROWS - 1) / TC_ROWS;
+    const long long n_items = (row_tiles + 1) / 2;
+    const int pairs = static_cast<int>(n_items < kNumSMs / 2 ? n_items : kNumSMs / 2);
+    if (!state_ready) {
+        zero_state_kernel<<<1, 256, 0, st>>>(hist, K, counter);
+        LAUNCH_CHECK("zero_state_kernel");
+    }
+    ProfScope prof(KID_ARGMIN_TC, st);
+    cudaError_t e = launch_pdl(vq_screen_kernel<NSLAB, NSTAGE, ZBUF>, dim3(2 * pairs), dim3(SC_THREADS), smem, st, tz, thi, e_norm2, N,
+                               K, static_cast<int>(n_items), idx, fused);
+    if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of vq_screen_kernel failed: %s", cudaGetErrorString(e));
+    LAUNCH_CHECK("vq_screen_kernel");
+    return VQ_OK;
+}
+
+bool screen_enabled() {
+    static const bool on = [] { const char* e = getenv("B200VQ_SCREEN"); return !(e != nullptr && e[0] == '0'); }();
+    return on;
 }
 
 }  // namespace
@@ -364,6 +399,35 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
     unsigned long long* keys = nullptr;
     if (tensor_path_ok(N, K, D, flags, z, E_hi, E_lo, true)) {
         const long long row_tiles = (N + TC_ROWS - 1) / TC_ROWS;
+        // ---- screen + refine (one TF32 pass, exact fp32 refine of the candidates): the default fused forward ----
+        // Measured on B200: with D <= 64 AND the dense one-hot emitted the forward is HBM-bound and the 3xTF32 kernel's
+        // lighter row workers win (61 vs 65 us on the RIR-256 workload); everywhere else screen + refine is faster
+        // (1.4x at D = 64, 2x at D = 128) -- and D > 128 only fits this kernel.  VQ_FLAG_SCREEN forces it.
+        const bool screen_shape = (K % TC2_CODES == 0) && (D <= 128 || D == 192 || D == 256) && aligned16(E) &&
+                                  (!quant || aligned16(q_out)) && (!want_onehot || aligned16(onehot)) &&
+                                  !(flags & (VQ_FLAG_NO_SCREEN | VQ_FLAG_NO_FUSE | VQ_FLAG_TC_1CTA));
+        const bool screen = screen_shape && ((flags & VQ_FLAG_SCREEN) || (screen_enabled() && (D > 64 || !want_onehot)));
+        if (screen) {
+            FusedRowArgs fr{};
+            fr.z = z; fr.E = E; fr.q_out = quant ? q_out : nullptr; fr.onehot = want_onehot ? onehot : nullptr; fr.hist = hist;
+            fr.partials = partials; fr.counter = counter; fr.sse_out = sse; fr.loss = loss; fr.perplexity = perplexity;
+            fr.beta = beta; fr.finalize = defer ? 0 : 1; fr.trace = g_trace_buf;
+            static const int evict_first = [] { const char* e = getenv("B200VQ_ONEHOT_EVICT_FIRST"); return e != nullptr && e[0] == '0' ? 0 : 1; }();
+            fr.onehot_evict_first = evict_first;
+            CUtensorMap tz, thi;
+            if (int rc = make_tmap(&tz, z, N, D)) return rc;
+            if (int rc = make_tmap(&thi, E_hi, K, D)) return rc;
+            const bool ready = (flags & VQ_FLAG_STATE_READY) != 0;
+            switch (D / TC_SLAB_FLOATS) {
+                case 1: return launch_screen<1, 8, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
+                case 2: return launch_screen<2, 8, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
+                case 3: return launch_screen<3, 6, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
+                case 4: return launch_screen<4, 4, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
+                case 6: return launch_screen<6, 6, 1>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
+                case 8: return launch_screen<8, 4, 1>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
+                default: break;
+            }
+        }
         const bool pair = (K % TC2_CODES == 0) && !(flags & VQ_FLAG_TC_1CTA);
         // CTA pairs: a wave is 74 pairs, each covering 256 rows x 256 codes per tile
         const int code_tiles = pair ? K / TC2_CODES : K / TC_CODES;

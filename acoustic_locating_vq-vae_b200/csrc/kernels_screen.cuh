@@ -1,0 +1,773 @@
+// kernels_screen.cuh -- fused forward, "screen + refine" variant (sm_100a: TMA + tcgen05 + TMEM).
+//
+// The 3xTF32 kernel (kernels_tc.cuh) rebuilds an fp32-grade product from three tensor-core passes.  This kernel
+// spends ONE pass and restores exactness where it matters:
+//
+//   screen   s(n,k) = |E_k|^2 - 2 * <tf32(z_n), tf32(E_k)>          one tcgen05 TF32 pass, fp32 accumulate
+//            |s(n,k) + |z_n|^2 - dist(n,k)| <= eta_n                 eta_n = 2*eps_n + rounding,
+//                                                                    eps_n = 1.02 * 2^-10 * |z_n| * max_k|E_k|
+//            (each operand carries <= 2^-11 relative rounding error; Cauchy-Schwarz over the D products)
+//   collect  every code with s(n,k) <= min_k s(n,k) + 2*eta_n is a CANDIDATE; the oracle's argmin -- including all
+//            of its exact ties -- is provably among them.  ~93 % of rows have exactly one candidate.
+//   refine   the row workers evaluate the candidates of the remaining rows in EXACT fp32 in the oracle's order,
+//            dist = fmaf(-2, fma-chain <z_n, E_k>, fl(|z_n|^2 + |E_k|^2)), first index on ties
+//            (vector_quantizer.py:34-38; oracle/vq_oracle.c).  Indices are therefore bit-identical to the C oracle
+//            for any input, not merely equal up to fp32 near-ties.
+//
+// Candidate bookkeeping in the epilogue (thread = (row, column half)): per 256-code tile four running chains
+// (columns j mod 4) keep (best, index, second-best value); at the end of the tile a chain's best enters a sorted
+// 4-entry candidate list if it is within the margin of the running minimum, and anything that is within the margin
+// but cannot be kept (a chain's second best, an evicted entry) lowers `lost`.  If `lost` ends up within the margin
+// of the final minimum (~0.2 % of rows) the row is rescanned exactly over the whole codebook.
+//
+// Structure (persistent CTA pairs, cta_group::2, M=256 N=256 K=8) and the fused row epilogue are those of
+// argmin_tc2_kernel<..., FUSE=true>; only E_hi is streamed and only tf32(z) is kept in shared memory, which is
+// what makes D = 256 fit.
+#pragma once
+#include "common.cuh"
+#include "kernels_tc.cuh"
+
+namespace b200vq {
+
+constexpr int SC_THREADS = 512;
+constexpr int SC_NC_OVERFLOW = 255;   // status: candidate set could not be bounded -> exact scan of the whole codebook
+constexpr int SC_PMAX = 384;          // (row, code) pairs evaluated exactly per 128-row item
+
+__host__ __device__ constexpr int sc_smem_bytes(int nslab, int nstage, int zbuf) {
+    return zbuf * nslab * TC_SLAB_BYTES + nstage * TC_SLAB_BYTES + 2 * TC2_CODES * 4 /* b tile */ +
+           TC2_ARING * TC_ROWS * 4 /* a ring */ + 2 * TC_ROWS * 10 * 4 /* half merge */ +
+           2 * TC_ROWS * 8 * 4 /* handoff: 4 candidates, status, a_n, 2 rescan locations */ + TC_ROWS * 4 /* final idx */ +
+           TC_ROWS * 4 /* full-rescan list */ + TC_ROWS * 4 /* pair ranges */ + SC_PMAX * 8 /* pair list */ +
+           TC2_ZERO_BYTES + 512 /* barriers + scratch */ + 1024 /* align */;
+}
+
+// in-place tf32 rounding of `nv` float4, strided over `nthreads`
+__device__ __forceinline__ void round_tf32_inplace(float4* p4, int nv, int first, int nthreads) {
+#pragma unroll 4
+    for (int i = first; i < nv; i += nthreads) {
+        float4 v = p4[i];
+        v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w);
+        p4[i] = v;
+    }
+}
+
+// exact fp32 dot product in the oracle's order: one fmaf chain over d = 0..D-1
+template <int D>
+__device__ __forceinline__ float dot_chain_exact(const float* __restrict__ zr, const float* __restrict__ er) {
+    float acc = 0.0f;
+    const float4* z4 = reinterpret_cast<const float4*>(zr);
+    const float4* e4 = reinterpret_cast<const float4*>(er);
+    constexpr int B = 8;                                   // 8 + 8 independent 16-byte loads in flight per batch
+#pragma unroll 1
+    for (int i0 = 0; i0 < D / 4; i0 += B) {
+        float4 a[B], b[B];
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            a[u] = __ldg(z4 + i0 + u);
+            b[u] = __ldg(e4 + i0 + u);
+        }
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            acc = fmaf(a[u].x, b[u].x, acc);
+            acc = fmaf(a[u].y, b[u].y, acc);
+            acc = fmaf(a[u].z, b[u].z, acc);
+            acc = fmaf(a[u].w, b[u].w, acc);
+        }
+    }
+    return acc;
+}
+
+template <int NSLAB, int NSTAGE, int ZBUF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SC_THREADS, 1)
+vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_ehi,
+                 const float* __restrict__ e_norm2, long long N, int K, int n_items, int* __restrict__ idx_out,
+                 const FusedRowArgs fr) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int D = NSLAB * TC_SLAB_FLOATS;
+    constexpr int ZBYTES = NSLAB * TC_SLAB_BYTES;              // one z buffer: tf32(z) only
+    uint8_t* zbufs = smem;
+    uint8_t* stages = zbufs + ZBUF * ZBYTES;
+    float* b_tile = reinterpret_cast<float*>(stages + NSTAGE * TC_SLAB_BYTES);   // [2][256]
+    float* a_ring = b_tile + 2 * TC2_CODES;                                      // [TC2_ARING][128]
+    float* mrg = a_ring + TC2_ARING * TC_ROWS;                                   // [2][128][10]: half-1 list -> half 0
+    int* h_cand = reinterpret_cast<int*>(mrg + 2 * TC_ROWS * 10);                // [2][128][4]
+    int* h_nc = h_cand + 2 * TC_ROWS * 4;                                        // [2][128] status: nc | nloc << 8, or 255
+    float* h_an = reinterpret_cast<float*>(h_nc + 2 * TC_ROWS);                  // [2][128]
+    int* h_loc = reinterpret_cast<int*>(h_an + 2 * TC_ROWS);                     // [2][128][2] chain-instances to rescan
+    int* s_idx = h_loc + 2 * TC_ROWS * 2;                                        // [128] final codes of the workers' item
+    int* s_ovf = s_idx + TC_ROWS;                                                // [128] rows that need the full rescan
+    int* s_rng = s_ovf + TC_ROWS;                                                // [128] pair range of a row: base | count << 16
+    int* pair_rc = s_rng + TC_ROWS;                                              // [SC_PMAX] row << 20 | code
+    float* pair_dist = reinterpret_cast<float*>(pair_rc + SC_PMAX);              // [SC_PMAX]
+    float* zero_row = reinterpret_cast<float*>(pair_dist + SC_PMAX);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(zero_row + TC2_ZERO_BYTES / 4);
+    uint64_t* bar_z_full = bars;                        // [ZBUF]
+    uint64_t* bar_z_free = bar_z_full + ZBUF;           // [ZBUF]
+    uint64_t* bar_z_ready = bar_z_free + ZBUF;          // [ZBUF]  (leader side)
+    uint64_t* bar_a_ready = bar_z_ready + ZBUF;         // [TC2_ARING]
+    uint64_t* bar_full = bar_a_ready + TC2_ARING;       // [NSTAGE] (leader side)
+    uint64_t* bar_empty = bar_full + NSTAGE;            // [NSTAGE]
+    uint64_t* bar_acc_full = bar_empty + NSTAGE;        // [2]
+    uint64_t* bar_acc_empty = bar_acc_full + 2;         // [2]      (leader side)
+    uint64_t* bar_idx_ready = bar_acc_empty + 2;        // [2]
+    uint64_t* bar_idx_free = bar_idx_ready + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_idx_free + 2);
+    double* red = reinterpret_cast<double*>(tmem_slot + 2);   // [4] + flag
+    int* zeros_done = reinterpret_cast<int*>(red + 5);
+    int* ovf_count = zeros_done + 1;
+    unsigned long long* ovf_key = reinterpret_cast<unsigned long long*>(zeros_done + 2);
+    float* s_bmax = reinterpret_cast<float*>(ovf_key + 1);    // [8] warp maxima, then [0] = max_k |E_k|^2
+    int* pair_count = reinterpret_cast<int*>(s_bmax + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int n_ctiles = K / TC2_CODES;
+    const bool have_oh = fr.onehot != nullptr;
+    const bool quant = fr.q_out != nullptr;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_z);
+        tma_prefetch_desc(&tm_ehi);
+        for (int i = 0; i < ZBUF; ++i) {
+            mbar_init(bar_z_full + i, 1);
+            mbar_init(bar_z_free + i, 1);
+            mbar_init(bar_z_ready + i, 128);
+        }
+        for (int i = 0; i < TC2_ARING; ++i) mbar_init(bar_a_ready + i, 64);
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(bar_full + s, 1);
+            mbar_init(bar_empty + s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_acc_full + b, 1);
+            mbar_init(bar_acc_empty + b, 16);
+            mbar_init(bar_idx_ready + b, 4);
+            mbar_init(bar_idx_free + b, have_oh ? 3 : 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_2sm(tmem_slot, TC2_TMEM_COLS);
+        tmem_relinquish_2sm();
+    }
+    if (warp >= 12) {
+        for (int i = threadIdx.x - 384; i < TC2_ZERO_BYTES / 16; i += 128)
+            reinterpret_cast<float4*>(zero_row)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (threadIdx.x == 384) {
+            *zeros_done = 0;
+            *ovf_count = 0;
+            *pair_count = 0;
+        }
+        fence_proxy_async_smem();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait_prior_grids();
+    if (threadIdx.x == 0) {
+        VQ_TR(7, 0);
+#ifdef VQ_TRACE
+        if (fr.trace != nullptr) fr.trace[(blockIdx.x * 8 + 7) * 64 + 3] = static_cast<long long>(global_timer_ns());
+#endif
+    }
+
+    if (warp == 0) {
+        // ===== E producer: tf32(E) slabs only =====
+        if (lane == 0) {
+            int L = 0;
+            for (int w = pair; w < n_items; w += n_pairs) {
+                for (int ct = 0; ct < n_ctiles; ++ct) {
+                    for (int i = 0; i < NSLAB; ++i, ++L) {
+                        const int stage = L % NSTAGE;
+                        mbar_wait(bar_empty + stage, ((L / NSTAGE) & 1) ^ 1);
+                        if (leader) mbar_arrive_expect_tx(bar_full + stage, 2 * TC_SLAB_BYTES);
+                        tma_load_2d_2sm(stages + stage * TC_SLAB_BYTES, &tm_ehi, bar_full + stage, i * TC_SLAB_FLOATS,
+                                        ct * TC2_CODES + static_cast<int>(cta_rank) * TC_ROWS);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only): one TF32 pass =====
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(2 * TC_ROWS, TC2_CODES);
+            int L = 0, ctg = 0, it = 0;
+            for (int w = pair; w < n_items; w += n_pairs, ++it) {
+                const int zb = it % ZBUF;
+                VQ_TR(1, 3 * it);
+                mbar_wait(bar_z_ready + zb, (it / ZBUF) & 1);
+                VQ_TR(1, 3 * it + 1);
+                tc_fence_after();
+                const uint32_t z_addr = smem_u32(zbufs + zb * ZBYTES);
+                for (int ct = 0; ct < n_ctiles; ++ct, ++ctg) {
+                    const int buf = ctg & 1;
+#ifdef VQ_TRACE
+                    long long tw0 = clock64();
+#endif
+                    mbar_wait(bar_acc_empty + buf, ((ctg >> 1) & 1) ^ 1);
+#ifdef VQ_TRACE
+                    if (fr.trace != nullptr) fr.trace[(blockIdx.x * 8 + 6) * 64 + 32] += clock64() - tw0;
+#endif
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * TC2_CODES;
+                    uint32_t accumulate = 0;
+                    for (int i = 0; i < NSLAB; ++i, ++L) {
+                        const int stage = L % NSTAGE;
+#ifdef VQ_TRACE
+                        tw0 = clock64();
+#endif
+                        mbar_wait(bar_full + stage, (L / NSTAGE) & 1);
+#ifdef VQ_TRACE
+                        if (fr.trace != nullptr) fr.trace[(blockIdx.x * 8 + 6) * 64 + 33] += clock64() - tw0;
+#endif
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_u32(stages + stage * TC_SLAB_BYTES);
+                        const uint32_t a_addr = z_addr + i * TC_SLAB_BYTES;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            tc_mma_tf32_2sm(d_tmem, umma_desc_sw128(a_addr + kk * 32), umma_desc_sw128(b_addr + kk * 32), idesc,
+                                            accumulate);
+                            accumulate = 1;
+                        }
+                        tc_commit_2sm(bar_empty + stage);
+                    }
+                    tc_commit_2sm(bar_acc_full + buf);
+                }
+                tc_commit_2sm(bar_z_free + zb);
+                VQ_TR(1, 3 * it + 2);
+            }
+        }
+    } else if (warp < 4) {
+        // ===== z pipeline (64 threads per CTA): TMA, |z_n|^2 chain, in-place tf32 rounding, publish =====
+        const int c = threadIdx.x - 64;
+        int it = 0;
+        for (int w = pair; w < n_items; w += n_pairs, ++it) {
+            const int zb = it % ZBUF;
+            const int row_tile = 2 * w + static_cast<int>(cta_rank);
+            uint8_t* zt = zbufs + zb * ZBYTES;
+            if (c == 0) {
+                mbar_wait(bar_z_free + zb, ((it / ZBUF) & 1) ^ 1);
+                mbar_arrive_expect_tx(bar_z_full + zb, NSLAB * TC_SLAB_BYTES);
+                for (int s = 0; s < NSLAB; ++s)
+                    tma_load_2d(zt + s * TC_SLAB_BYTES, &tm_z, bar_z_full + zb, s * TC_SLAB_FLOATS, row_tile * TC_ROWS);
+            }
+            mbar_wait(bar_z_full + zb, (it / ZBUF) & 1);
+            float* a_dst = a_ring + (it % TC2_ARING) * TC_ROWS;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = c + h * 64;
+                const uint8_t* rowp = zt + (r >> 3) * 1024 + (r & 7) * 128;
+                float a = 0.0f;
+#pragma unroll
+                for (int s = 0; s < NSLAB; ++s) {
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch) {
+                        const float4 v = *reinterpret_cast<const float4*>(rowp + s * TC_SLAB_BYTES + ((ch ^ (r & 7)) << 4));
+                        a = fmaf(v.x, v.x, a);
+                        a = fmaf(v.y, v.y, a);
+                        a = fmaf(v.z, v.z, a);
+                        a = fmaf(v.w, v.w, a);
+                    }
+                }
+                a_dst[r] = a;
+            }
+            float4* z4 = reinterpret_cast<float4*>(zt);
+            constexpr int NV = NSLAB * TC_SLAB_BYTES / 16;
+            if (it == 0) {
+                named_bar_sync(5, 320);
+                round_tf32_inplace(z4, NV, c, 320);
+                fence_proxy_async_smem();
+                named_bar_sync(5, 320);
+            } else {
+                named_bar_sync(3, 64);
+                round_tf32_inplace(z4, NV, c, 64);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(bar_a_ready + (it % TC2_ARING));
+            mbar_arrive_cluster(bar_z_ready + zb, 0);
+        }
+        if (c == 0) {
+            for (int j = it > ZBUF ? it - ZBUF : 0; j < it; ++j) mbar_wait(bar_z_free + (j % ZBUF), (j / ZBUF) & 1);
+        }
+    } else if (warp < 12) {
+        // ===== epilogue (8 warps): screening scores -> candidates =====
+        const int ew = warp - 4;
+        const int half = ew >> 2;
+        const int row = (ew & 3) * 32 + lane;
+        const int et = threadIdx.x - 128;
+        const uint32_t lane_base = static_cast<uint32_t>((ew & 3) * 32) << 16;
+        // max_k |E_k|^2 (for the margin): 256 threads scan e_norm2 once
+        {
+            float bm = 0.0f;
+            for (int k = et; k < K; k += 256) bm = fmaxf(bm, __ldg(e_norm2 + k));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+            if (lane == 0) s_bmax[ew] = bm;
+            named_bar_sync(1, 256);
+            bm = s_bmax[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) bm = fmaxf(bm, s_bmax[i]);
+            named_bar_sync(1, 256);
+            if (et == 0) s_bmax[0] = bm;
+            named_bar_sync(1, 256);
+        }
+        const float b_max = s_bmax[0];
+        {   // help the z pipeline with the first tile
+            mbar_wait(bar_z_full + 0, 0);
+            named_bar_sync(5, 320);
+            round_tf32_inplace(reinterpret_cast<float4*>(zbufs), NSLAB * TC_SLAB_BYTES / 16, 64 + et, 320);
+            fence_proxy_async_smem();
+            named_bar_sync(5, 320);
+        }
+        int it = 0, ctg = 0;
+        for (int w = pair; w < n_items; w += n_pairs, ++it) {
+            mbar_wait(bar_a_ready + (it % TC2_ARING), (it / TC2_ARING) & 1);
+            const float a_n = a_ring[(it % TC2_ARING) * TC_ROWS + row];
+            // margin on the score scale: 2*eta = 4*eps + rounding slack (see the header)
+            const float margin = 1.0001f * (0.00398438f * sqrtf(a_n * b_max) + 1.9073486e-6f * (a_n + b_max));
+            float lv[4];     // candidate list, ascending
+            int lk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                lv[q] = INFINITY;
+                lk[q] = 0;
+            }
+            float lost = INFINITY;   // smallest score that is within the margin but could not be kept in the list ...
+            int lost_loc = -1;       // ... and where it hides: chain-instance ct*8 + half*4 + q, or -2 = anywhere
+            for (int ct = 0; ct < n_ctiles; ++ct, ++ctg) {
+                const int buf = ctg & 1;
+                const int k0 = ct * TC2_CODES;
+                b_tile[buf * TC2_CODES + et] = __ldg(e_norm2 + k0 + et);
+                named_bar_sync(1, 256);
+                if (et == 0) VQ_TR(0, 3 * ctg);
+                mbar_wait(bar_acc_full + buf, (ctg >> 1) & 1);
+                if (et == 0) VQ_TR(0, 3 * ctg + 1);
+                tc_fence_after();
+                const uint32_t t_addr = tmem_base + lane_base + buf * TC2_CODES + half * 128;
+                const float4* b4 = reinterpret_cast<const float4*>(b_tile + buf * TC2_CODES + half * 128);
+                float m1[4], m2[4], i1f[4];     // per chain: best, runner-up (value only), column of the best (as a float)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    m1[q] = INFINITY;
+                    m2[q] = INFINITY;
+                    i1f[q] = 0.0f;
+                }
+                uint32_t va[16], vb[16];
+                // The scan is bound by the ALU pipe (compare / select / min-max issue every 2 cycles per warp), so the
+                // two conditional updates are done as predicated FMA-pipe moves (d = s*1 + 0) and the column index is
+                // carried as a float: per element 3 FMA-pipe ops (score, 2 moves) and 3 ALU-pipe ops (setp, max, min).
+                auto consume = [&](const uint32_t (&v)[16], int cc) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 b = b4[cc * 4 + j4];
+                        const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float s = fmaf(-2.0f, __uint_as_float(v[j4 * 4 + q]), bb[q]);
+                            m2[q] = fminf(m2[q], fmaxf(s, m1[q]));                 // runner-up of the chain
+                            const float colf = static_cast<float>(cc * 16 + j4 * 4 + q);
+                            asm("{\n"
+                                ".reg .pred p;\n"
+                                "setp.lt.f32 p, %2, %0;\n"
+                                "@p fma.rn.f32 %0, %2, 0f3F800000, 0f00000000;\n"
+                                "@p fma.rn.f32 %1, %3, 0f3F800000, 0f00000000;\n"
+                                "}\n"
+                                : "+f"(m1[q]), "+f"(i1f[q])
+                                : "f"(s), "f"(colf));
+                        }
+                    }
+                };
+                tmem_ld_32x32b_x16(t_addr, va);
+#pragma unroll
+                for (int cc = 0; cc < 8; cc += 2) {
+                    tmem_ld_wait();
+                    tmem_ld_32x32b_x16(t_addr + (cc + 1) * 16, vb);
+                    consume(va, cc);
+                    tmem_ld_wait();
+                    if (cc + 2 < 8) {
+                        tmem_ld_32x32b_x16(t_addr + (cc + 2) * 16, va);
+                    } else {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster_relaxed(bar_acc_empty + buf, 0);
+                    }
+                    consume(vb, cc + 1);
+                }
+                // fold the tile's four chains into the candidate list
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float v = m1[q];
+                    if (v <= lv[0] + margin) {     // cannot be ruled out yet (the running minimum only decreases)
+                        const int kk = k0 + half * 128 + static_cast<int>(i1f[q]);
+                        float ev;                  // what falls off the list
+                        if (v < lv[3]) {
+                            ev = lv[3];
+                            if (v < lv[2]) {
+                                lv[3] = lv[2]; lk[3] = lk[2];
+                                if (v < lv[1]) {
+                                    lv[2] = lv[1]; lk[2] = lk[1];
+                                    if (v < lv[0]) {
+                                        lv[1] = lv[0]; lk[1] = lk[0];
+                                        lv[0] = v; lk[0] = kk;
+                                    } else {
+                                        lv[1] = v; lk[1] = kk;
+                                    }
+                                } else {
+                                    lv[2] = v; lk[2] = kk;
+                                }
+                            } else {
+                                lv[3] = v; lk[3] = kk;
+                            }
+                        } else {
+                            ev = v;
+                        }
+                        if (ev <= lv[0] + margin) {                 // a listed candidate fell off: no cheap way to find it again
+                            lost = fminf(lost, ev);
+                            lost_loc = -2;
+                        }
+                        if (m2[q] <= lv[0] + margin) {              // hidden behind the chain's best: remember the 32 columns
+                            const int loc = ct * 8 + half * 4 + q;
+                            if (lost_loc == -1 || !(lost <= lv[0] + margin)) {   // nothing (still relevant) recorded yet
+                                lost = m2[q];
+                                lost_loc = loc;
+                            } else {
+                                lost = fminf(lost, m2[q]);
+                                if (lost_loc != loc) lost_loc = -2;
+                            }
+                        }
+                    }
+                }
+                if (et == 0) VQ_TR(0, 3 * ctg + 2);
+            }
+            // merge the two column halves and publish the row's candidates
+            float* ms = mrg + ((it & 1) * TC_ROWS + row) * 10;
+            if (half == 1) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    ms[q] = lv[q];
+                    ms[4 + q] = __int_as_float(lk[q]);
+                }
+                ms[8] = lost;
+                ms[9] = __int_as_float(lost_loc);
+            } else {
+                mbar_wait(bar_idx_free + (it & 1), ((it >> 1) & 1) ^ 1);   // the workers are done with this handoff slot
+            }
+            named_bar_sync(2, 256);
+            if (half == 0) {
+                const float smin = fminf(lv[0], ms[0]);
+                const float thr = smin + margin;
+                int* cand = h_cand + ((it & 1) * TC_ROWS + row) * 4;
+                int* locs = h_loc + ((it & 1) * TC_ROWS + row) * 2;
+                int nc = 0, nloc = 0;
+                bool full = false;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (lv[q] <= thr) {
+                        if (nc < 4) cand[nc] = lk[q];
+                        ++nc;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (ms[q] <= thr) {
+                        if (nc < 4) cand[nc] = __float_as_int(ms[4 + q]);
+                        ++nc;
+                    }
+                }
+                if (lost <= thr) {
+                    if (lost_loc >= 0) locs[nloc++] = lost_loc; else full = true;
+                }
+                if (ms[8] <= thr) {
+                    const int l1 = __float_as_int(ms[9]);
+                    if (l1 >= 0) locs[nloc++] = l1; else full = true;
+                }
+                if (nc > 4 || nc == 0) full = true;
+                h_nc[(it & 1) * TC_ROWS + row] = full ? SC_NC_OVERFLOW : (nc | (nloc << 8));
+                h_an[(it & 1) * TC_ROWS + row] = a_n;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_idx_ready + (it & 1));
+                if (et == 0) VQ_TR(3, 4 * it + 3);
+            }
+        }
+    } else if (warp == 12 && have_oh) {
+        // ===== one-hot zero filler (1 thread): TMA bulk copies from one shared zero row, from kernel start =====
+        if (lane == 0) {
+            const uint32_t row_bytes = static_cast<uint32_t>(K) * 4u;
+            const uint32_t chunk = row_bytes < TC2_ZERO_BYTES ? row_bytes : TC2_ZERO_BYTES;
+            const uint64_t pol = l2_policy_evict_first();
+            for (int w = pair; w < n_items; w += n_pairs) {
+                const long long row0 = static_cast<long long>(2 * w + static_cast<int>(cta_rank)) * TC_ROWS;
+                const long long left = N - row0;
+                const int rows_here = left <= 0 ? 0 : (left < TC_ROWS ? static_cast<int>(left) : TC_ROWS);
+                uint8_t* obase = reinterpret_cast<uint8_t*>(fr.onehot + row0 * K);
+                const size_t total = static_cast<size_t>(rows_here) * row_bytes;
+                if (fr.onehot_evict_first) {
+                    for (size_t off = 0; off < total; off += chunk) bulk_store_s2g_hint(obase + off, zero_row, chunk, pol);
+                } else {
+                    for (size_t off = 0; off < total; off += chunk) bulk_store_s2g(obase + off, zero_row, chunk);
+                }
+                bulk_commit();
+            }
+            bulk_wait_all();
+            fence_proxy_async_all();
+            st_release_cta(zeros_done, 1);
+        }
+    } else {
+        // ===== row workers (3 or 4 warps): exact refine, then vector_quantizer.py:40-56 =====
+        constexpr int DV = NSLAB * 8;
+        const int NW = have_oh ? 96 : 128;
+        const int wt = have_oh ? threadIdx.x - 416 : threadIdx.x - 384;
+        float sse = 0.0f;
+        int it = 0;
+        for (int w = pair; w < n_items; w += n_pairs, ++it) {
+            const long long row0 = static_cast<long long>(2 * w + static_cast<int>(cta_rank)) * TC_ROWS;
+            const long long left = N - row0;
+            const int rows_here = left <= 0 ? 0 : (left < TC_ROWS ? static_cast<int>(left) : TC_ROWS);
+            mbar_wait(bar_idx_ready + (it & 1), (it >> 1) & 1);
+            if (wt == 0) VQ_TR(5, 4 * it);
+            const int* cand = h_cand + (it & 1) * TC_ROWS * 4;
+            const int* ncs = h_nc + (it & 1) * TC_ROWS;
+            const float* ans = h_an + (it & 1) * TC_ROWS;
+            // -- refine: exact fp32 distances (oracle order) of every (row, code) pair that is still undecided -------
+            const int* locs = h_loc + (it & 1) * TC_ROWS * 2;
+            for (int r = wt; r < rows_here; r += NW) {       // 1. enumerate the pairs
+                const int st = ncs[r];
+                int rng = 0;
+                if (st == SC_NC_OVERFLOW) {
+                    s_ovf[atomicAdd(ovf_count, 1)] = r;
+                } else {
+                    const int nc = st & 0xff, nloc = st >> 8;
+                    const int cnt = (nc > 1 || nloc > 0) ? nc + 32 * nloc : 0;
+                    if (cnt == 0) {
+                        s_idx[r] = cand[r * 4];              // a single candidate IS the argmin: nothing to compute
+                    } else {
+                        const int base = atomicAdd(pair_count, cnt);
+                        if (base + cnt > SC_PMAX) {          // list full (pathological margin): rescan the row instead
+                            for (int p = base; p < SC_PMAX; ++p) pair_rc[p] = -1;
+                            s_ovf[atomicAdd(ovf_count, 1)] = r;
+                        } else {
+                            int p = base;
+                            for (int j = 0; j < nc; ++j) pair_rc[p++] = (r << 20) | cand[r * 4 + j];
+                            for (int l = 0; l < nloc; ++l) {
+                                const int loc = locs[r * 2 + l];
+                                const int kb = (loc >> 3) * TC2_CODES + ((loc >> 2) & 1) * 128 + (loc & 3);
+                                for (int j = 0; j < 32; ++j) pair_rc[p++] = (r << 20) | (kb + 4 * j);
+                            }
+                            rng = base | (cnt << 16);
+                        }
+                    }
+                }
+                s_rng[r] = rng;
+            }
+            named_bar_sync(4, NW);
+            {                                                // 2. one exact distance per thread and pass
+                const int np = min(*pair_count, SC_PMAX);
+                for (int p = wt; p < np; p += NW) {
+                    const int rc = pair_rc[p];
+                    if (rc >= 0) {
+                        const int r = rc >> 20, k = rc & 0xfffff;
+                        const float c = dot_chain_exact<D>(fr.z + (row0 + r) * D, fr.E + static_cast<size_t>(k) * D);
+                        pair_dist[p] = fmaf(-2.0f, c, ans[r] + __ldg(e_norm2 + k));
+                    }
+                }
+            }
+            named_bar_sync(4, NW);
+            for (int r = wt; r < rows_here; r += NW) {       // 3. per row: smallest distance, first index on ties
+                const int rng = s_rng[r];
+                if (rng != 0) {
+                    const int base = rng & 0xffff, cnt = rng >> 16;
+                    float best = INFINITY;
+                    int code = 0x7fffffff;
+                    for (int p = base; p < base + cnt; ++p) {
+                        const float dist = pair_dist[p];
+                        const int k = pair_rc[p] & 0xfffff;
+                        if (dist < best || (dist == best && k < code)) {
+                            best = dist;
+                            code = k;
+                        }
+                    }
+                    s_idx[r] = code;
+                }
+            }
+            named_bar_sync(4, NW);
+            if (wt == 0) VQ_TR(5, 4 * it + 1);
+            // -- rare: rows whose candidate set could not be bounded -> exact scan of the whole codebook ---------
+            const int n_ovf = *ovf_count;
+#ifdef VQ_TRACE
+            if (wt == 0 && fr.trace != nullptr) {
+                fr.trace[(blockIdx.x * 8 + 6) * 64 + 34] += n_ovf;
+                fr.trace[(blockIdx.x * 8 + 6) * 64 + 35] += *pair_count;
+            }
+#endif
+            for (int o = 0; o < n_ovf; ++o) {
+                const int r = s_ovf[o];
+                if (wt == 0) *ovf_key = ~0ull;
+                named_bar_sync(4, NW);
+                const float4* z4r = reinterpret_cast<const float4*>(fr.z + (row0 + r) * D);
+                const float a = ans[r];
+                unsigned long long key = ~0ull;
+                // 4 codes per thread at a time, interleaved: their loads overlap, each code keeps its own d-ordered chain
+                for (int kb = wt; kb < K; kb += 4 * NW) {
+                    float acc[4];
+                    const float4* e4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[j] = 0.0f;
+                        const int k = kb + j * NW;
+                        e4[j] = reinterpret_cast<const float4*>(fr.E + static_cast<size_t>(k < K ? k : 0) * D);
+                    }
+#pragma unroll 2
+                    for (int i = 0; i < D / 4; ++i) {
+                        const float4 zv = __ldg(z4r + i);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 ev = __ldg(e4[j] + i);
+                            acc[j] = fmaf(zv.x, ev.x, acc[j]);
+                            acc[j] = fmaf(zv.y, ev.y, acc[j]);
+                            acc[j] = fmaf(zv.z, ev.z, acc[j]);
+                            acc[j] = fmaf(zv.w, ev.w, acc[j]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = kb + j * NW;
+                        if (k < K) {
+                            const float dist = fmaf(-2.0f, acc[j], a + __ldg(e_norm2 + k));
+                            const unsigned long long kk = pack_key(dist, k);
+                            key = kk < key ? kk : key;
+                        }
+                    }
+                }
+                atomicMin(ovf_key, key);
+                named_bar_sync(4, NW);
+                if (wt == 0) s_idx[r] = static_cast<int>(*ovf_key & 0xffffffffu);
+                named_bar_sync(4, NW);
+            }
+            if (wt == 0) {
+                *ovf_count = 0;
+                *pair_count = 0;
+            }
+            named_bar_sync(4, NW);
+            if (wt == 0) VQ_TR(5, 4 * it + 2);
+            // -- indices, usage histogram -----------------------------------------------------------------------
+            for (int r = wt; r < rows_here; r += NW) {
+                const int code = s_idx[r];
+                idx_out[row0 + r] = code;
+                atomicAdd(fr.hist + code, 1.0f);
+            }
+            // -- q_out = fl(z + fl(E[idx] - z)), sse += (E[idx] - z)^2 ---------------------------------------------
+            if (quant) {
+                const float4* z4 = reinterpret_cast<const float4*>(fr.z + row0 * D);
+                float4* q4 = reinterpret_cast<float4*>(fr.q_out + row0 * D);
+                const int n_el = rows_here * DV;
+                constexpr int PER_T = (TC_ROWS * DV + 95) / 96;
+                constexpr int UB = 8;
+#pragma unroll 1
+                for (int ub = 0; ub < PER_T; ub += UB) {
+                    if (wt + ub * NW >= n_el) break;
+                    float4 zv[UB], ev[UB];
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) {
+                        const int e = wt + (ub + u) * NW;
+                        if (e < n_el) {
+                            zv[u] = __ldg(z4 + e);
+                            ev[u] = __ldg(reinterpret_cast<const float4*>(fr.E + static_cast<size_t>(s_idx[e / DV]) * D) + (e % DV));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) {
+                        const int e = wt + (ub + u) * NW;
+                        if (e < n_el) {
+                            const float4 zz = zv[u];
+                            float4 df, qv;
+                            df.x = ev[u].x - zz.x; df.y = ev[u].y - zz.y; df.z = ev[u].z - zz.z; df.w = ev[u].w - zz.w;
+                            qv.x = zz.x + df.x; qv.y = zz.y + df.y; qv.z = zz.z + df.z; qv.w = zz.w + df.w;
+                            __stcs(q4 + e, qv);
+                            sse = fmaf(df.x, df.x, sse); sse = fmaf(df.y, df.y, sse);
+                            sse = fmaf(df.z, df.z, sse); sse = fmaf(df.w, df.w, sse);
+                        }
+                    }
+                }
+            }
+            named_bar_sync(4, NW);                       // everyone is done with s_idx and the handoff slot
+            if (lane == 0) mbar_arrive(bar_idx_free + (it & 1));
+            if (wt == 0) VQ_TR(5, 4 * it + 3);
+        }
+        if (have_oh) {
+            while (ld_acquire_cta(zeros_done) == 0) {
+            }
+            for (int w = pair; w < n_items; w += n_pairs) {
+                const long long row0 = static_cast<long long>(2 * w + static_cast<int>(cta_rank)) * TC_ROWS;
+                for (int r = wt; r < TC_ROWS; r += NW) {
+                    const long long gr = row0 + r;
+                    if (gr < N) __stcs(fr.onehot + gr * K + __ldcg(idx_out + gr), 1.0f);
+                }
+            }
+        }
+        // per-CTA SSE partial, then last-CTA-done reduction in a fixed order (+ loss / perplexity)
+        const int wwarp = have_oh ? warp - 13 : warp - 12;
+        double sd = warp_sum_d(static_cast<double>(sse));
+        if (lane == 0) red[wwarp] = sd;
+        named_bar_sync(4, NW);
+        volatile int* last_flag = reinterpret_cast<volatile int*>(red + 4);
+        if (wt == 0) {
+            fr.partials[blockIdx.x] = red[0] + red[1] + red[2] + (have_oh ? 0.0 : red[3]);
+            __threadfence();
+            const unsigned int done = atomicAdd(fr.counter, 1u);
+            *last_flag = (done == gridDim.x - 1) ? 1 : 0;
+        }
+        named_bar_sync(4, NW);
+        if (*last_flag) {
+            __threadfence();
+            double t = 0.0;
+            for (int i = wt; i < static_cast<int>(gridDim.x); i += NW) t += __ldcg(fr.partials + i);
+            t = warp_sum_d(t);
+            named_bar_sync(4, NW);
+            if (lane == 0) red[wwarp] = t;
+            named_bar_sync(4, NW);
+            const double total = red[0] + red[1] + red[2] + (have_oh ? 0.0 : red[3]);
+            if (wt == 0) {
+                *fr.sse_out = static_cast<float>(total);
+                *fr.counter = 0u;
+            }
+            if (fr.finalize) {
+                if (wt == 0 && quant) {
+                    const float m = static_cast<float>(total / (static_cast<double>(N) * static_cast<double>(D)));
+                    *fr.loss = __fadd_rn(m, __fmul_rn(fr.beta, m));
+                }
+                double ent = 0.0;
+                const float nf = static_cast<float>(N);
+                for (int k = wt; k < K; k += NW) {
+                    const float p = __fdiv_rn(__ldcg(fr.hist + k), nf);
+                    ent += static_cast<double>(p * logf(p + 1e-10f));
+                }
+                ent = warp_sum_d(ent);
+                named_bar_sync(4, NW);
+                if (lane == 0) red[wwarp] = ent;
+                named_bar_sync(4, NW);
+                if (wt == 0) *fr.perplexity = expf(static_cast<float>(-(red[0] + red[1] + red[2] + (have_oh ? 0.0 : red[3]))));
+            }
+        }
+    }
+
+    if (threadIdx.x == 0) VQ_TR(7, 1);
+    pdl_launch_dependents();
+    tc_fence_before();
+    cluster_sync_all();
+    if (threadIdx.x == 0) {
+        VQ_TR(7, 2);
+#ifdef VQ_TRACE
+        if (fr.trace != nullptr) fr.trace[(blockIdx.x * 8 + 7) * 64 + 4] = static_cast<long long>(global_timer_ns());
+#endif
+    }
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, TC2_TMEM_COLS);
+    }
+}
+
+}  // namespace b200vq

@@ -41,6 +41,8 @@ WORKLOADS = {
     "sweep_k4096_d128": (1024, 128, 1024, 4096, "configs[3]: N=1M rows, K=4096, D=128"),
     "sweep_k8192_d128": (1024, 128, 1024, 8192, "configs[3]: N=1M rows, K=8192, D=128"),
     "sweep_k512_d64": (1024, 64, 1024, 512, "configs[3]: N=1M rows, K=512, D=64"),
+    "sweep_k2048_d256": (1024, 256, 1024, 2048, "configs[3]: N=1M rows, K=2048, D=256"),
+    "sweep_k8192_d256": (512, 256, 1024, 8192, "configs[3]: N=512k rows, K=8192, D=256"),
 }
 BETA = 0.25
 L2_BYTES = 126 * 1024 * 1024
@@ -169,6 +171,8 @@ def main():
     ap.add_argument("--exact", action="store_true", help="CUDA-core exact path instead of tcgen05")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-fuse", action="store_true", help="argmin and row epilogue as two kernels (VQ_FLAG_NO_FUSE)")
+    ap.add_argument("--no-screen", action="store_true", help="3xTF32 tensor kernels instead of screen + exact refine (VQ_FLAG_NO_SCREEN)")
+    ap.add_argument("--screen", action="store_true", help="force screen + exact refine (VQ_FLAG_SCREEN)")
     ap.add_argument("--nccl", action="store_true", help="N > 1: use NCCL for the per-step all-reduce instead of vq_allreduce_sum")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -251,7 +255,7 @@ def main():
     dz = torch.empty(N, D, device=dev)
     g_loss = torch.ones((), device=dev)
     fwd_flags = ((L.FLAG_ONEHOT if emit_onehot else 0) | (L.FLAG_EXACT if args.exact else 0) |
-                 (L.FLAG_NO_FUSE if args.no_fuse else 0) | L.FLAG_STATE_READY)
+                 (L.FLAG_NO_FUSE if args.no_fuse else 0) | (L.FLAG_NO_SCREEN if args.no_screen else 0) | (L.FLAG_SCREEN if args.screen else 0) | L.FLAG_STATE_READY)
     bwd_flags = L.FLAG_TRAIN_VQ
     wsb = lib.vq_workspace_bytes(N, K, D, fwd_flags)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
@@ -416,7 +420,8 @@ def main():
         line = {
             "metric": "quantized vectors/sec (VQ fwd+bwd)", "value": value, "unit": "vectors/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tcgen05 3xTF32 contraction, fp32 accumulate)" if not args.exact else "f32",
+            "scaling": "weak", "vs_baseline": None, "dtype": ("f32" if args.exact else ("f32 (tcgen05 3xTF32 contraction, fp32 accumulate)" if (args.no_screen or args.no_fuse or (D <= 64 and emit_onehot and not args.screen)) else
+                      "f32 (tcgen05 TF32 screening pass + exact fp32 refine of the candidates: indices bit-exact vs the fp32 oracle)")),
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "B": B, "D": D, "T": T, "K": K, "rows_per_gpu": N, "beta": BETA,
                        "encodings": "dense one-hot emitted" if emit_onehot else "indices only",

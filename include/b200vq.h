@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VQ_ABI_VERSION 11
+#define VQ_ABI_VERSION 13
 
 /* error codes */
 #define VQ_OK            0
@@ -47,6 +47,8 @@ extern "C" {
 #define VQ_FLAG_TC_1CTA    (1 << 6)  /* forward: single-CTA tensor kernel (M=128,N=128) even when the CTA-pair kernel applies */
 #define VQ_FLAG_NO_FUSE    (1 << 7)  /* forward: keep argmin and the row epilogue as two kernels (default: fused into one) */
 #define VQ_FLAG_STATE_READY (1 << 8) /* forward: vq_prepare_step already reset hist and the workspace counter for this call */
+#define VQ_FLAG_NO_SCREEN  (1 << 9)  /* forward: 3xTF32 tensor kernels, never the screen (1xTF32) + exact-refine kernel */
+#define VQ_FLAG_SCREEN     (1 << 10) /* forward: force the screen + exact-refine kernel wherever its shape constraints allow */
 #define VQ_FLAG_ZERO_DE    (1 << 5)  /* backward: zero dE (memset on `stream`) before accumulating into it */
 
 typedef void* vq_stream_t;   /* cudaStream_t */

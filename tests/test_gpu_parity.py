@@ -131,40 +131,58 @@ def test_exact_path_abi(lib, golden, name):
 
 
 TENSOR_CASES = [n for n, c in CASES.items() if c["D"] in (32, 64, 96, 128) and c["K"] % 128 == 0]
+SCREEN_CASES = [n for n, c in CASES.items() if c["D"] in (32, 64, 96, 128, 192, 256) and c["K"] % 256 == 0]
+FLAG_TC_1CTA, FLAG_NO_FUSE, FLAG_NO_SCREEN, FLAG_SCREEN = 1 << 6, 1 << 7, 1 << 9, 1 << 10
 
 
-@pytest.mark.parametrize("name", [n for n in TENSOR_CASES if CASES[n]["K"] % 256 == 0])
-def test_tensor_path_single_cta_kernel(lib, golden, name):
-    """The M=128/N=128 single-CTA tcgen05 kernel (used when K % 256 != 0), forced with VQ_FLAG_TC_1CTA."""
+def _run_case(lib, name, flags):
     c = CASES[name]
     E, z, g = make_inputs(c)
     D = c["D"]
-    out = run_abi(lib, z.numpy().reshape(-1, D), E.numpy(), g.numpy().reshape(-1, D), c["g_loss"], c["beta"],
-                  c["train_vq"], flags_extra=1 << 6)
-    check_against_oracle_and_golden(out, name, golden, exact=False)
+    return run_abi(lib, z.numpy().reshape(-1, D), E.numpy(), g.numpy().reshape(-1, D), c["g_loss"], c["beta"],
+                   c["train_vq"], flags_extra=flags)
+
+
+@pytest.mark.parametrize("name", SCREEN_CASES)
+def test_screen_refine_path_is_bit_exact(lib, golden, name):
+    """Default tensor path: one TF32 screening pass + exact fp32 refine of the candidates (vq_screen_kernel).
+    Indices must equal oracle/vq_oracle.c bit for bit -- not merely up to near-ties -- for D up to 256."""
+    c = CASES[name]
+    N = int(np.prod(c["shape"])) // c["D"]
+    assert lib.vq_forward_uses_tensor_path(N, c["K"], c["D"], 0) == 1
+    out = _run_case(lib, name, FLAG_SCREEN)                        # with the dense one-hot (run_abi asks for it)
+    check_against_oracle_and_golden(out, name, golden, exact=True)
+    E, z, g = make_inputs(c)
+    out = run_abi(lib, z.numpy().reshape(-1, c["D"]), E.numpy(), g.numpy().reshape(-1, c["D"]), c["g_loss"], c["beta"],
+                  c["train_vq"], flags_extra=0, want_onehot=False)     # the default choice without a one-hot
+    check_against_oracle_and_golden(out, name, golden, exact=True)
 
 
 @pytest.mark.parametrize("name", [n for n in TENSOR_CASES if CASES[n]["K"] % 256 == 0])
-def test_tensor_path_unfused(lib, golden, name):
+def test_3xtf32_fused_kernel(lib, golden, name):
+    """The 3xTF32 persistent CTA-pair kernel with the fused row epilogue (VQ_FLAG_NO_SCREEN)."""
+    check_against_oracle_and_golden(_run_case(lib, name, FLAG_NO_SCREEN), name, golden, exact=False)
+
+
+@pytest.mark.parametrize("name", [n for n in TENSOR_CASES if CASES[n]["K"] % 256 == 0])
+def test_3xtf32_unfused_kernels(lib, golden, name):
     """CTA-pair argmin kernel + separate rows kernel (VQ_FLAG_NO_FUSE): the path taken when the codebook is split."""
-    c = CASES[name]
-    E, z, g = make_inputs(c)
-    D = c["D"]
-    out = run_abi(lib, z.numpy().reshape(-1, D), E.numpy(), g.numpy().reshape(-1, D), c["g_loss"], c["beta"],
-                  c["train_vq"], flags_extra=1 << 7)
-    check_against_oracle_and_golden(out, name, golden, exact=False)
+    check_against_oracle_and_golden(_run_case(lib, name, FLAG_NO_FUSE), name, golden, exact=False)
+
+
+@pytest.mark.parametrize("name", [n for n in TENSOR_CASES if CASES[n]["K"] % 256 == 0])
+def test_3xtf32_single_cta_kernel(lib, golden, name):
+    """The M=128/N=128 single-CTA tcgen05 kernel (used when K % 256 != 0), forced with VQ_FLAG_TC_1CTA."""
+    check_against_oracle_and_golden(_run_case(lib, name, FLAG_TC_1CTA), name, golden, exact=False)
 
 
 @pytest.mark.parametrize("name", TENSOR_CASES)
 def test_tensor_path_abi(lib, golden, name):
+    """Whatever vq_forward picks by default for tensor-eligible shapes."""
     c = CASES[name]
     N = int(np.prod(c["shape"])) // c["D"]
     assert lib.vq_forward_uses_tensor_path(N, c["K"], c["D"], 0) == 1
-    E, z, g = make_inputs(c)
-    D = c["D"]
-    out = run_abi(lib, z.numpy().reshape(-1, D), E.numpy(), g.numpy().reshape(-1, D), c["g_loss"], c["beta"],
-                  c["train_vq"], flags_extra=0)
-    n_mis, gap = check_against_oracle_and_golden(out, name, golden, exact=False)
+    n_mis, gap = check_against_oracle_and_golden(_run_case(lib, name, 0), name, golden, exact=False)
     print(f"[tensor path] {name}: {n_mis} near-tie rows, worst relative fp64 gap {gap:.2e}")
 
 

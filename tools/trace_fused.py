@@ -37,8 +37,9 @@ for rep in range(3):
     torch.cuda.synchronize()
 t = trace.cpu().numpy().reshape(148, 8, 64)
 roles = {0: "epi tiles (wait start | acc full | scanned) x12", 1: "mma  (wait z_ready | got | item issued)", 2: "zpipe(tma issue | z landed | converted)", 3: "epi  (a_ready | first acc | last acc | idx out)",
-         4: "fill (issue start | issued)", 5: "work (idx got | q done | ones done)", 6: "zeros_done published (per item)", 7: "cta  (start | roles done | after cluster sync)"}
-for cta in (0, 1, 73, 147):
+         4: "fill (issue start | issued)", 5: "work (cand got | refined | overflow done | item done)", 6: "zeros_done published (per item)", 7: "cta  (start | roles done | after cluster sync)"}
+slowest = int(np.argmax(t[:, 7, 2] - t[:, 7, 0]))
+for cta in (0, 73, slowest, slowest ^ 1):
     t0 = t[cta, 7, 0]
     print(f"--- CTA {cta} (us since role dispatch, 1.9 GHz nominal) ---")
     for r, name in roles.items():
@@ -49,5 +50,9 @@ print("effective SM clock during the kernel: %.0f MHz (median over CTAs)" % np.m
 ld = t[0::2, 6, :]
 print("leader MMA thread: cycles waiting on acc_empty: median %.0f ; on full (E TMA): median %.0f ; residency cycles median %.0f" % (
     np.median(ld[:, 32]), np.median(ld[:, 33]), np.median(cyc)))
+print("screen kernel: full-rescan rows per CTA: total %d, max %d ; exact pairs per CTA: mean %.0f max %d" % (
+    t[:, 6, 34].sum(), t[:, 6, 34].max(), t[:, 6, 35].mean(), t[:, 6, 35].max()))
+slow = int(np.argmax(t[:, 7, 2] - t[:, 7, 0]))
+print("slowest CTA:", slow, "full-rescan rows:", int(t[slow, 6, 34]), "pairs:", int(t[slow, 6, 35]))
 ends = (t[:, 7, 2] - t[:, 7, 0]) / 1900.0
 print("kernel residency per CTA (us): min %.1f  median %.1f  max %.1f" % (ends.min(), np.median(ends), ends.max()))
