@@ -149,3 +149,48 @@ def test_uniform_init_ties_at_full_size(lib):
     x = _forward(lib, z, E, 4)
     n_mis, gap = _near_tie_gap(z, E, t["idx"], x["idx"])
     assert gap <= NEAR_TIE_TENSOR and n_mis <= N // 200, (n_mis, gap)
+
+
+def _oracle_idx(z, E):
+    from oracle import c_oracle
+    return torch.from_numpy(c_oracle.argmin(z.cpu().numpy(), E.cpu().numpy()))
+
+
+ADVERSARIAL = ["duplicates", "clustered", "rows_are_codes", "huge_scale", "tiny_scale", "one_dominant_code", "few_rows", "constant_rows"]
+
+
+@pytest.mark.parametrize("kind", ADVERSARIAL)
+@pytest.mark.parametrize("D,K", [(64, 512), (128, 1024), (256, 256)])
+def test_screen_kernel_adversarial_inputs(lib, kind, D, K):
+    """The screen + refine kernel must stay BIT-EXACT vs oracle/vq_oracle.c when its rare paths fire: exact ties
+    (duplicated codewords: first index wins), clustered codebooks (many candidates per row: chain-instance
+    rescans, pair-list overflow, whole-codebook rescans), rows equal to codewords, extreme scales."""
+    dev = _dev()
+    g = torch.Generator().manual_seed(hash((kind, D, K)) % (1 << 31))
+    N = 1500 if kind != "few_rows" else 3
+    E = torch.randn(K, D, generator=g)
+    z = torch.randn(N, D, generator=g)
+    if kind == "duplicates":
+        E[5::7] = E[3:3 + len(E[5::7])]                 # many exact duplicates: ties must go to the lower index
+        z[:200] = E[torch.randint(0, K, (200,), generator=g)] + 1e-3 * torch.randn(200, D, generator=g)
+    elif kind == "clustered":
+        base = torch.randn(8, D, generator=g)
+        E = base[torch.randint(0, 8, (K,), generator=g)] + 2e-4 * torch.randn(K, D, generator=g)   # ~K/8 near-ties per row
+    elif kind == "rows_are_codes":
+        z = E[torch.randint(0, K, (N,), generator=g)].clone()
+    elif kind == "huge_scale":
+        E, z = E * 3e3, z * 3e3
+    elif kind == "tiny_scale":
+        E, z = E * 1e-4, z * 1e-4
+    elif kind == "one_dominant_code":
+        E[17] *= 50.0                                   # inflates max|E_k| and with it every row's margin
+    elif kind == "constant_rows":
+        z[:] = z[0]
+    E, z = E.contiguous().to(dev), z.contiguous().to(dev)
+    out = _forward(lib, z, E, 1 << 10)                  # VQ_FLAG_SCREEN
+    ref = _oracle_idx(z, E)
+    assert torch.equal(out["idx"].cpu(), ref), f"{kind} D={D} K={K}: {(out['idx'].cpu() != ref).sum().item()} rows differ from the oracle"
+    assert float(out["hist"].sum()) == N
+    out_oh = _forward(lib, z, E, 1 << 10, want_onehot=True)
+    assert torch.equal(out_oh["idx"].cpu(), ref) and torch.equal(out_oh["onehot"].argmax(1).int().cpu(), ref)
+    assert float(out_oh["onehot"].sum()) == N
