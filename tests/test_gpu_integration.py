@@ -1,0 +1,180 @@
+"""GPU integration tests: the quantizer inside the callers' graphs (BASELINE.json configs[2] and configs[4]).
+
+The reference's model classes cannot travel to the GPU box and its conv stacks are out of scope, so the callers
+are re-expressed here as small stand-ins with the same dataflow and shapes:
+  * `_ConvVQVAE`      convolutional_vq_vae.py:93-100   encoder conv -> _pre_vq_conv -> _vq -> decoder
+  * jitter            modules/jitter.py:47-70          in-place edit of the quantizer's output before the decoder
+  * echoed model      echoed_speech_model.py:36-56     two frozen quantizers, pad + concat, (un)detached
+  * location model    train_location.py:69-75          encodings.reshape(B, T, K) -> MLP
+Both the B200 quantizer and the torch oracle quantizer (oracle/vq_oracle.py, same aten ops as the reference) are
+fed the SAME z (cudnn TF32 convs must not be re-run under different flags), and everything
+downstream -- losses, reconstructions, gradients, Adam-updated weights -- must agree to 1e-5 relative.
+"""
+import copy
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from oracle import vq_oracle
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+class _OracleVQ(nn.Module):
+    """Reference-equivalent quantizer (torch ops) with the reference's surface."""
+
+    def __init__(self, K, D, beta):
+        super().__init__()
+        self._embedding = nn.Embedding(K, D)
+        self._embedding.weight.data.uniform_(-1 / K, 1 / K)
+        self._commitment_cost = beta
+        self._train_vq = True
+
+    def set_train_vq(self, flag):
+        self._train_vq = flag
+
+    def forward(self, inputs):
+        r = vq_oracle.forward_dense(inputs, self._embedding.weight, self._commitment_cost, self._train_vq)
+        return r.loss, r.quantized, r.perplexity, r.encodings
+
+
+class _ConvVQVAE(nn.Module):
+    def __init__(self, in_ch, hidden, D, vq):
+        super().__init__()
+        self._encoder = nn.Conv1d(in_ch, hidden, 3, padding=1)
+        self._pre_vq_conv = nn.Conv1d(hidden, D, 3, padding=1)      # convolutional_vq_vae.py:32-38
+        self._vq = vq
+        self._decoder = nn.Conv1d(D, in_ch, 3, padding=1)
+
+    def latent(self, x):
+        return self._pre_vq_conv(F.relu(self._encoder(x)))
+
+    def forward(self, x, jitter_cols=None):
+        z = self.latent(x)
+        loss, q, perp, _ = self._vq(z)                                # :98
+        if jitter_cols is not None:                                   # jitter.py:53-68: IN-PLACE on the VQ output
+            orig = q.detach().clone()
+            for i, j in jitter_cols:
+                q[:, :, i] = orig[:, :, j]
+        return loss, self._decoder(q), perp
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max() / max(float(b.double().abs().max()), 1e-30))
+
+
+def _pair(K, D, beta, dev, seed, **kw):
+    import b200vq
+    torch.manual_seed(seed)
+    ref = _OracleVQ(K, D, beta).to(dev)
+    ref._embedding.weight.data.normal_()
+    mine = b200vq.VectorQuantizer(K, D, beta, **kw).to(dev)
+    mine._embedding.weight.data.copy_(ref._embedding.weight.data)
+    return mine, ref
+
+
+@pytest.mark.parametrize("shape,K,jitter", [((32, 201, 500, 128), 1024, True),     # train_speech.py: B,in,T,D
+                                             ((16, 500, 201, 64), 1024, False)])   # train_rir.py (no jitter)
+def test_training_step_inside_conv_stack(shape, K, jitter):
+    """One optimiser step of an encoder -> quantizer -> decoder model (configs[0]/[1] shapes): same z into both
+    quantizers, then loss, reconstruction, every gradient and the Adam-updated weights must agree."""
+    dev = torch.device("cuda:0")
+    B, C, T, D = shape
+    mine, ref = _pair(K, D, 0.25, dev, 0)
+    torch.manual_seed(1)
+    model = _ConvVQVAE(C, 64, D, mine).to(dev)
+    twin = copy.deepcopy(model)
+    twin._vq = ref
+    x = torch.randn(B, C, T, device=dev)
+    cols = [(0, 1), (7, 6), (T - 1, T - 2), (100, 101)] if jitter else None
+    outs = []
+    for m in (model, twin):
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+        z = model.latent(x).detach().requires_grad_(True)             # the SAME z for both quantizers
+        loss, q, perp, enc = m._vq(z)
+        if cols is not None:
+            orig = q.detach().clone()
+            for i, j in cols:
+                q[:, :, i] = orig[:, :, j]                            # in-place, like Jitter
+        recon = m._decoder(q)
+        total = F.mse_loss(recon, x) + loss                           # train_speech.py:74,88
+        opt.zero_grad()
+        total.backward()
+        opt.step()
+        outs.append(dict(loss=loss.detach(), perp=perp, total=total.detach(), dz=z.grad, enc=enc,
+                         dE=m._vq._embedding.weight.grad, E=m._vq._embedding.weight.detach(),
+                         dec=m._decoder.weight.detach(), recon=recon.detach()))
+    a, b = outs
+    assert torch.equal(a["enc"], b["enc"])                            # identical codes
+    for k in ("loss", "perp", "total", "dz", "dE", "E", "dec", "recon"):
+        assert _rel(a[k], b[k]) <= RTOL, (k, _rel(a[k], b[k]))
+
+
+def test_echoed_model_dataflow():
+    """echoed_speech_model.py:36-56: both quantizers frozen (`set_train_vq(False)`), RIR latent padded on time and
+    concatenated on channels, detached unless flag_train_encoder; encoder_training_echoed_model.py:44 flips it."""
+    dev = torch.device("cuda:0")
+    B = 8
+    sp_m, sp_r = _pair(1024, 128, 0.25, dev, 2)
+    rir_m, rir_r = _pair(1024, 64, 0.25, dev, 3)
+    for v in (sp_m, sp_r, rir_m, rir_r):
+        v.set_train_vq(False)
+    torch.manual_seed(4)
+    dec = nn.Conv1d(192, 201, 3, padding=1).to(dev)
+    z_sp = torch.randn(B, 128, 500, device=dev)
+    z_rir = torch.randn(B, 64, 201, device=dev)
+    x = torch.randn(B, 201, 500, device=dev)
+    for train_encoder in (False, True):
+        res = []
+        for sp, rir in ((sp_m, rir_m), (sp_r, rir_r)):
+            a = z_sp.clone().requires_grad_(True)
+            b = z_rir.clone().requires_grad_(True)
+            _, q_rir, p_rir, _ = rir(b)
+            _, q_sp, p_sp, _ = sp(a)
+            q_rir = F.pad(q_rir, (0, q_sp.size(2) - q_rir.size(2)))   # :41-49
+            cat = torch.cat((q_sp, q_rir), 1) if train_encoder else torch.cat((q_sp.detach(), q_rir.detach()), 1)
+            loss = F.mse_loss(dec(cat), x)
+            dec.zero_grad()
+            loss.backward()
+            res.append(dict(loss=loss.detach(), p=torch.stack((p_sp, p_rir)), g=dec.weight.grad.clone(),
+                            da=a.grad, db=b.grad, dE=sp._embedding.weight.grad))
+        m, r = res
+        assert _rel(m["loss"], r["loss"]) <= RTOL and _rel(m["p"], r["p"]) <= RTOL and _rel(m["g"], r["g"]) <= RTOL
+        assert m["dE"] is None and r["dE"] is None                    # frozen codebooks never get a gradient
+        if train_encoder:                                             # pure straight-through: dz == upstream gradient
+            assert _rel(m["da"], r["da"]) <= RTOL and _rel(m["db"], r["db"]) <= RTOL
+        else:
+            assert m["da"] is None and r["da"] is None
+
+
+def test_location_model_consumes_encodings():
+    """train_location.py:69-75: the RIR quantizer's one-hot `encodings` reshaped to (B, T, K) feeds the MLP."""
+    dev = torch.device("cuda:0")
+    B, T, K, D = 16, 201, 1024, 64
+    mine, ref = _pair(K, D, 0.25, dev, 5)
+    mine.set_train_vq(False)
+    ref.set_train_vq(False)
+    torch.manual_seed(6)
+    fc1 = nn.Linear(T * K, 64).to(dev)                                # location_model.py:10 (1024 wide there)
+    z = torch.randn(B, D, T, device=dev)
+    target = torch.rand(B, 1, device=dev)
+    outs = []
+    for vq in (mine, ref):
+        _, _, _, enc = vq(z)
+        feat = enc.reshape(B, T, K)                                   # :74
+        y = fc1(torch.flatten(feat, start_dim=1)).mean(1, keepdim=True)
+        loss = F.mse_loss(y, target)
+        fc1.zero_grad()
+        loss.backward()
+        outs.append((loss.detach(), fc1.weight.grad.clone(), enc))
+    assert torch.equal(outs[0][2], outs[1][2])
+    assert _rel(outs[0][0], outs[1][0]) <= RTOL and _rel(outs[0][1], outs[1][1]) <= RTOL
+    # the same features without the dense one-hot: indices + gather
+    idx = mine.last_indices.view(B, T).long()
+    cols = (torch.arange(T, device=dev) * K)[None, :] + idx          # column t*K + idx[b,t] of fc1.weight
+    y2 = fc1.weight[:, cols].sum(-1).t() + fc1.bias                   # == fc1(one_hot) exactly up to summation order
+    y1 = fc1(torch.flatten(outs[0][2].reshape(B, T, K), start_dim=1))
+    assert _rel(y2, y1) <= 1e-5
