@@ -8,8 +8,9 @@ The directory name carries a hyphen; import it as `b200vq` (repo-root shim) or w
 from . import _lib, build as _build
 from ._lib import B200VQError, load as load_library
 from .quantizer import VectorQuantizer, swap_quantizers
+from .onehot_linear import OneHotLinear
 
 build_extension = _build.build
 SO_PATH = _build.SO_PATH
 
-__all__ = ["VectorQuantizer", "swap_quantizers", "load_library", "build_extension", "B200VQError", "SO_PATH"]
+__all__ = ["VectorQuantizer", "swap_quantizers", "OneHotLinear", "load_library", "build_extension", "B200VQError", "SO_PATH"]

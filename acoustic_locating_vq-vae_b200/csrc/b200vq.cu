@@ -642,6 +642,33 @@ int vq_allreduce_push(const void* const* recv_buffers, void* multicast_or_null, 
     return VQ_OK;
 }
 
+// fc_1(one_hot) as an index gather (location_model.py:10,21; train_location.py:74-75).
+int vq_gather_sum_rows(const int32_t* idx, const float* Wt, const float* bias, float* y, int B, int T, int K, int O,
+                       vq_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    if (idx == nullptr || Wt == nullptr || y == nullptr || B < 0 || T < 1 || K < 1 || O < 4 || O % 4 != 0 || !aligned16(Wt) ||
+        !aligned16(y) || (bias != nullptr && !aligned16(bias)))
+        return fail(VQ_ERR_ARG, "vq_gather_sum_rows: bad argument (B=%d T=%d K=%d O=%d; O must be a multiple of 4, pointers 16-byte aligned)", B, T, K, O);
+    if (B == 0) return VQ_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid(static_cast<unsigned>(B), static_cast<unsigned>((O / 4 + 255) / 256));
+    gather_sum_rows_kernel<<<grid, 256, sizeof(int) * T, st>>>(idx, Wt, bias, y, T, K, O);
+    LAUNCH_CHECK("gather_sum_rows_kernel");
+    return VQ_OK;
+}
+
+int vq_scatter_add_rows(const int32_t* idx, const float* g, float* dWt, int B, int T, int K, int O, vq_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    if (idx == nullptr || g == nullptr || dWt == nullptr || B < 0 || T < 1 || K < 1 || O < 4 || O % 4 != 0 || !aligned16(g) ||
+        !aligned16(dWt) || T > 65535)
+        return fail(VQ_ERR_ARG, "vq_scatter_add_rows: bad argument (B=%d T=%d K=%d O=%d)", B, T, K, O);
+    if (B == 0) return VQ_OK;
+    dim3 grid(static_cast<unsigned>(B), static_cast<unsigned>(T));
+    scatter_add_rows_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(idx, g, dWt, T, K, O);
+    LAUNCH_CHECK("scatter_add_rows_kernel");
+    return VQ_OK;
+}
+
 // =========================================================================================================
 // host-buffer context: two lanes (stream + staging) so the H2D copy of step i+1 overlaps the kernels of step i
 // =========================================================================================================

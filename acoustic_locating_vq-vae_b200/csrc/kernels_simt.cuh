@@ -560,4 +560,53 @@ __global__ void __launch_bounds__(256) allreduce_push_kernel(PeerBuffers recv, f
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// SURVEY 8(f) rank 1 -- the consumer of the dense one-hot as an index gather.
+// LocationModule.fc_1 (location_model.py:10,21) multiplies flatten(one_hot(B, T, K)) by a (O, T*K) weight: a
+// 205 824 x 1024 GEMM on a matrix that is 99.9 % zeros.  With the weight stored transposed, Wt (T*K, O),
+//     y[b, :] = bias + sum_t Wt[t*K + idx[b, t], :]
+// is T coalesced row reads per sample.  One CTA per (sample, 1024-wide slab of O); thread = one float4 of O.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_sum_rows_kernel(const int* __restrict__ idx, const float* __restrict__ Wt,
+                                                              const float* __restrict__ bias, float* __restrict__ y, int T,
+                                                              int K, int O) {
+    extern __shared__ int s_rows[];                       // [T] row of Wt for every position of this sample
+    const int b = blockIdx.x;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) s_rows[t] = t * K + idx[b * T + t];
+    __syncthreads();
+    const int o4 = blockIdx.y * blockDim.x + threadIdx.x;  // float4 index along O
+    if (o4 * 4 >= O) return;
+    const float4* W4 = reinterpret_cast<const float4*>(Wt);
+    const int O4 = O >> 2;
+    float4 acc = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias) + o4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    int t = 0;
+    for (; t + 4 <= T; t += 4) {                           // 4 independent row reads in flight
+        const float4 v0 = __ldg(W4 + static_cast<size_t>(s_rows[t]) * O4 + o4);
+        const float4 v1 = __ldg(W4 + static_cast<size_t>(s_rows[t + 1]) * O4 + o4);
+        const float4 v2 = __ldg(W4 + static_cast<size_t>(s_rows[t + 2]) * O4 + o4);
+        const float4 v3 = __ldg(W4 + static_cast<size_t>(s_rows[t + 3]) * O4 + o4);
+        acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+        acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+        acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+        acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+    }
+    for (; t < T; ++t) {
+        const float4 v = __ldg(W4 + static_cast<size_t>(s_rows[t]) * O4 + o4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(y + static_cast<size_t>(b) * O)[o4] = acc;
+}
+
+// backward of the above w.r.t. Wt (dense gradient): dWt[t*K + idx[b,t], :] += g[b, :]  (rows collide across samples)
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(const int* __restrict__ idx, const float* __restrict__ g,
+                                                               float* __restrict__ dWt, int T, int K, int O) {
+    const int b = blockIdx.x, t = blockIdx.y;
+    const size_t row = static_cast<size_t>(t) * K + idx[b * T + t];
+    const int O4 = O >> 2;
+    for (int o4 = threadIdx.x; o4 < O4; o4 += blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(g + static_cast<size_t>(b) * O) + o4);
+        atomicAdd(reinterpret_cast<float4*>(dWt + row * O) + o4, v);
+    }
+}
+
 }  // namespace b200vq

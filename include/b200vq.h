@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VQ_ABI_VERSION 13
+#define VQ_ABI_VERSION 14
 
 /* error codes */
 #define VQ_OK            0
@@ -122,6 +122,14 @@ int vq_onehot(const int32_t* idx, int64_t n_rows, int K, float* onehot, vq_strea
 int vq_backward(const float* g_q, const float* g_loss, const float* z, const float* E,
                 const int32_t* idx, int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE,
                 int K, int D, float beta, int flags, float* dz, float* dE, vq_stream_t stream);
+
+/* -- the consumer of `encodings` as an index gather ------------------------------------ */
+/* LocationModule.fc_1 (location_model.py:10,21) applied to flatten(one_hot(B,T,K)) (train_location.py:74-75):
+ *   y[b,:] = bias + sum_t Wt[t*K + idx[b,t], :]        Wt = fc_1.weight transposed, (T*K, O) row-major, O % 4 == 0
+ * and the dense gradient of its weight, dWt[t*K + idx[b,t], :] += g[b,:] (dWt zeroed by the caller). */
+int vq_gather_sum_rows(const int32_t* idx, const float* Wt, const float* bias_or_null, float* y,
+                       int B, int T, int K, int O, vq_stream_t stream);
+int vq_scatter_add_rows(const int32_t* idx, const float* g, float* dWt, int B, int T, int K, int O, vq_stream_t stream);
 
 /* -- data parallel: one-shot all-reduce over NVLink peer memory ------------------------------------------ */
 /* out[i] = sum over ranks (in rank order: bit-identical everywhere) of rank p's payload[i], i < n_floats.

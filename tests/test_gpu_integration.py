@@ -178,3 +178,39 @@ def test_location_model_consumes_encodings():
     y2 = fc1.weight[:, cols].sum(-1).t() + fc1.bias                   # == fc1(one_hot) exactly up to summation order
     y1 = fc1(torch.flatten(outs[0][2].reshape(B, T, K), start_dim=1))
     assert _rel(y2, y1) <= 1e-5
+
+
+@pytest.mark.parametrize("B,T,K,O,bias", [(16, 201, 1024, 1024, True),      # train_location.py / location_model.py shapes
+                                           (5, 20, 64, 32, True), (3, 7, 37, 8, False)])
+def test_onehot_linear_equals_linear_on_onehot(B, T, K, O, bias):
+    """`fc_1(flatten(one_hot))` (location_model.py:21) == gather of T weight rows per sample."""
+    import b200vq
+    dev = torch.device("cuda:0")
+    torch.manual_seed(7)
+    lin = nn.Linear(T * K, O, bias=bias).to(dev)
+    idx = torch.randint(0, K, (B, T), device=dev)
+    onehot = F.one_hot(idx, K).float()                               # (B, T, K) as train_location.py:74 builds it
+    y_ref = lin(torch.flatten(onehot, start_dim=1))
+    g = torch.randn(B, O, device=dev)
+    gw_ref, = torch.autograd.grad(y_ref, lin.weight, g, retain_graph=bias)
+    for sparse in (True, False):
+        m = b200vq.OneHotLinear.from_linear(lin, T, K, sparse_grad=sparse)
+        y = m(idx.int())
+        assert _rel(y, y_ref) <= 1e-5
+        y.backward(g)
+        gw = m.weight_t.grad
+        assert gw.is_sparse == sparse
+        gw = gw.to_dense() if sparse else gw
+        assert _rel(gw.t(), gw_ref) <= 1e-6
+        if bias:
+            assert _rel(m.bias.grad, g.sum(0)) <= 1e-6
+    assert torch.equal(m.to_linear().weight, lin.weight)
+    # straight from the quantizer: no dense one-hot is ever built
+    if K % 256 == 0:
+        vq = b200vq.VectorQuantizer(K, 64, 0.25, return_encodings=False).to(dev)
+        z = torch.randn(B, 64, T, device=dev)
+        _, _, _, enc = vq(z)
+        assert enc is None
+        feats = m(vq.last_indices.view(B, T))
+        ref = lin(torch.flatten(F.one_hot(vq.last_indices.view(B, T).long(), K).float(), start_dim=1))
+        assert _rel(feats, ref) <= 1e-5
