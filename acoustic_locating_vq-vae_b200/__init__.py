@@ -9,8 +9,9 @@ from . import _lib, build as _build
 from ._lib import B200VQError, load as load_library
 from .quantizer import VectorQuantizer, swap_quantizers
 from .onehot_linear import OneHotLinear
+from .jitter import Jitter
 
 build_extension = _build.build
 SO_PATH = _build.SO_PATH
 
-__all__ = ["VectorQuantizer", "swap_quantizers", "OneHotLinear", "load_library", "build_extension", "B200VQError", "SO_PATH"]
+__all__ = ["VectorQuantizer", "swap_quantizers", "OneHotLinear", "Jitter", "load_library", "build_extension", "B200VQError", "SO_PATH"]

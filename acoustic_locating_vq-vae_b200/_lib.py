@@ -9,7 +9,7 @@ import os
 
 from .build import SO_PATH
 
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 FLAG_ONEHOT = 1 << 0
 FLAG_TRAIN_VQ = 1 << 1
@@ -49,6 +49,8 @@ SIGNATURES = {
     "vq_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp]),
     "vq_gather_sum_rows": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp]),
     "vq_scatter_add_rows": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _vp]),
+    "vq_jitter_apply": (_int, [_vp, _vp, _i64, _int, _vp]),
+    "vq_jitter_backward": (_int, [_vp, _vp, _i64, _int, _vp]),
     "vq_allreduce_sum": (_int, [ctypes.POINTER(_vp), _int, _int, _i64, _i64, ctypes.c_uint32, _vp, _vp]),
     "vq_allreduce_push": (_int, [ctypes.POINTER(_vp), _vp, _int, _int, _vp, _i64, ctypes.c_uint32, _vp, _vp]),
     "vq_host_ctx_create": (_int, [_i64, _int, _int, ctypes.POINTER(_vp)]),

@@ -669,6 +669,28 @@ int vq_scatter_add_rows(const int32_t* idx, const float* g, float* dWt, int B, i
     return VQ_OK;
 }
 
+// Jitter (modules/jitter.py:47-70) -- in-place gather along time of a (rows, T) tensor.
+int vq_jitter_apply(float* q, const int32_t* src, int64_t rows, int T, vq_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    if (q == nullptr || src == nullptr || rows < 0 || T < 1 || T > 12288 || rows > 2147483647ll)
+        return fail(VQ_ERR_ARG, "vq_jitter_apply: bad argument (rows=%lld T=%d; T <= 12288)", (long long)rows, T);
+    if (rows == 0) return VQ_OK;
+    jitter_gather_kernel<<<static_cast<unsigned>(rows), 256, sizeof(float) * T, static_cast<cudaStream_t>(stream)>>>(q, src, T);
+    LAUNCH_CHECK("jitter_gather_kernel");
+    return VQ_OK;
+}
+
+int vq_jitter_backward(float* g, const int32_t* src, int64_t rows, int T, vq_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    if (g == nullptr || src == nullptr || rows < 0 || T < 1) return fail(VQ_ERR_ARG, "vq_jitter_backward: bad argument");
+    if (rows == 0) return VQ_OK;
+    long long blocks = (rows * T + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    jitter_backward_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, src, rows, T);
+    LAUNCH_CHECK("jitter_backward_kernel");
+    return VQ_OK;
+}
+
 // =========================================================================================================
 // host-buffer context: two lanes (stream + staging) so the H2D copy of step i+1 overlaps the kernels of step i
 // =========================================================================================================

@@ -609,4 +609,30 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const int* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// SURVEY 8(f) rank 3 -- Jitter (modules/jitter.py:47-70) as one gather along time.
+// q is (rows = B*D, T); column t becomes the ORIGINAL column src[t] (src[t] in {t-1, t, t+1}).  One CTA per row:
+// the row is staged in shared memory first, so the edit is in place without the reference's full clone.
+// `backward` zeroes the gradient of replaced columns (their values came from a detached clone).
+// ---------------------------------------------------------------------------------------------
+// whole row staged in shared memory (T floats), then rewritten in place: no clone of the tensor is needed
+__global__ void __launch_bounds__(256) jitter_gather_kernel(float* __restrict__ q, const int* __restrict__ src, int T) {
+    extern __shared__ float jrow[];
+    float* qr = q + static_cast<long long>(blockIdx.x) * T;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) jrow[t] = qr[t];
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        const int sc = src[t];
+        if (sc != t) qr[t] = jrow[sc];
+    }
+}
+__global__ void __launch_bounds__(256) jitter_backward_kernel(float* __restrict__ g, const int* __restrict__ src, long long rows, int T) {
+    const long long n = rows * T;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int t = static_cast<int>(i % T);
+        if (src[t] != t) g[i] = 0.0f;
+    }
+}
+
 }  // namespace b200vq

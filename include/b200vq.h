@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VQ_ABI_VERSION 14
+#define VQ_ABI_VERSION 15
 
 /* error codes */
 #define VQ_OK            0
@@ -130,6 +130,12 @@ int vq_backward(const float* g_q, const float* g_loss, const float* z, const flo
 int vq_gather_sum_rows(const int32_t* idx, const float* Wt, const float* bias_or_null, float* y,
                        int B, int T, int K, int O, vq_stream_t stream);
 int vq_scatter_add_rows(const int32_t* idx, const float* g, float* dWt, int B, int T, int K, int O, vq_stream_t stream);
+
+/* -- Jitter on the quantizer's output (modules/jitter.py:47-70) ------------------------- */
+/* In place on q (rows = B*D, T): column t becomes the ORIGINAL column src[t] (src[t] in {t-1, t, t+1}; the host
+ * draws src with the reference's np.random calls).  Backward zeroes the gradient of the replaced columns. */
+int vq_jitter_apply(float* q, const int32_t* src, int64_t rows, int T, vq_stream_t stream);
+int vq_jitter_backward(float* g, const int32_t* src, int64_t rows, int T, vq_stream_t stream);
 
 /* -- data parallel: one-shot all-reduce over NVLink peer memory ------------------------------------------ */
 /* out[i] = sum over ranks (in rank order: bit-identical everywhere) of rank p's payload[i], i < n_floats.

@@ -214,3 +214,30 @@ def test_onehot_linear_equals_linear_on_onehot(B, T, K, O, bias):
         feats = m(vq.last_indices.view(B, T))
         ref = lin(torch.flatten(F.one_hot(vq.last_indices.view(B, T).long(), K).float(), start_dim=1))
         assert _rel(feats, ref) <= 1e-5
+
+
+@pytest.mark.parametrize("shape,p", [((32, 128, 500), 0.25), ((4, 64, 201), 0.12), ((2, 3, 2), 0.25), ((1, 1, 1500), 0.5)])
+def test_jitter_matches_reference_semantics(shape, p):
+    """same np.random seed -> same tensor as modules/jitter.py:47-70, mutated in place; replaced
+    columns carry no gradient."""
+    import numpy as np
+    import b200vq
+    from oracle import jitter_oracle
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    x = torch.randn(*shape)
+    np.random.seed(99)
+    ref = jitter_oracle.jitter(x.clone(), p)
+    src = None
+    np.random.seed(99)
+    src = jitter_oracle.source_columns(shape[2], p)
+    z = x.to(dev).requires_grad_(True)
+    q = z * 1.0                                      # a non-leaf, like the quantizer's output
+    np.random.seed(99)
+    out = b200vq.Jitter(p)(q)
+    assert out.data_ptr() == q.data_ptr()            # in place, like the reference
+    assert torch.equal(out.detach().cpu(), ref)
+    g = torch.randn(*shape, device=dev)
+    out.backward(g)
+    keep = torch.from_numpy(src == np.arange(shape[2])).to(dev)
+    assert torch.equal(z.grad, g * keep)

@@ -138,3 +138,21 @@ def test_frozen_codebook_semantics():
     a = vq_oracle.forward_backward_dense(z, E, 0.25, train_vq=True, g_quantized=g)
     b = vq_oracle.forward_backward_dense(z, E, 0.25, train_vq=False, g_quantized=g)
     assert torch.equal(a.loss, b.loss) and torch.equal(a.dz, b.dz) and b.dE is None and a.dE is not None
+
+
+def test_jitter_oracle_pinned():
+    """oracle/jitter_oracle.py vs the reference Jitter (when present) and vs the committed decision fixture."""
+    import os
+    from oracle import jitter_oracle
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "jitter_golden.npz"))
+    np.random.seed(int(g["seed"]))
+    src = jitter_oracle.source_columns(int(g["T"]), float(g["p"]))
+    assert np.array_equal(src, g["src"].astype(np.int64))
+    assert 0.7 < (src != np.arange(len(src))).mean() < 0.8       # jitter.py:50 replaces with probability 1 - p
+    if os.path.isdir("/root/reference"):
+        assert jitter_oracle.check_against_reference() and jitter_oracle.check_against_reference(5, (2, 8, 500), 0.12)
+    # the product's host-side draw consumes np.random identically
+    from importlib import import_module
+    jit = import_module("acoustic_locating_vq-vae_b200.jitter")
+    np.random.seed(int(g["seed"]))
+    assert np.array_equal(jit.draw_source_columns(int(g["T"]), float(g["p"])), g["src"].astype(np.int32))
