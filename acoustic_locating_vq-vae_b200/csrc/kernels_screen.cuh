@@ -356,20 +356,20 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                     m2[q] = INFINITY;
                     i1f[q] = 0.0f;
                 }
-                uint32_t va[16], vb[16];
+                uint32_t va[32], vb[32];
                 // The scan is bound by the ALU pipe (compare / select / min-max issue every 2 cycles per warp), so the
                 // two conditional updates are done as predicated FMA-pipe moves (d = s*1 + 0) and the column index is
                 // carried as a float: per element 3 FMA-pipe ops (score, 2 moves) and 3 ALU-pipe ops (setp, max, min).
-                auto consume = [&](const uint32_t (&v)[16], int cc) {
+                auto consume = [&](const uint32_t (&v)[32], int cc) {       // 32 columns starting at cc*32
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        const float4 b = b4[cc * 4 + j4];
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 b = b4[cc * 8 + j4];
                         const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const float s = fmaf(-2.0f, __uint_as_float(v[j4 * 4 + q]), bb[q]);
                             m2[q] = fminf(m2[q], fmaxf(s, m1[q]));                 // runner-up of the chain
-                            const float colf = static_cast<float>(cc * 16 + j4 * 4 + q);
+                            const float colf = static_cast<float>(cc * 32 + j4 * 4 + q);
                             asm("{\n"
                                 ".reg .pred p;\n"
                                 "setp.lt.f32 p, %2, %0;\n"
@@ -381,22 +381,23 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                         }
                     }
                 };
-                tmem_ld_32x32b_x16(t_addr, va);
-#pragma unroll
-                for (int cc = 0; cc < 8; cc += 2) {
-                    tmem_ld_wait();
-                    tmem_ld_32x32b_x16(t_addr + (cc + 1) * 16, vb);
-                    consume(va, cc);
-                    tmem_ld_wait();
-                    if (cc + 2 < 8) {
-                        tmem_ld_32x32b_x16(t_addr + (cc + 2) * 16, va);
-                    } else {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster_relaxed(bar_acc_empty + buf, 0);
-                    }
-                    consume(vb, cc + 1);
-                }
+                // 32-column chunks, double buffered: every tcgen05.wait::ld is covered by a whole chunk of scanning
+                tmem_ld_32x32b_x32(t_addr, va);
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(t_addr + 32, vb);
+                consume(va, 0);
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(t_addr + 64, va);
+                consume(vb, 1);
+                tmem_ld_wait();
+                tmem_ld_32x32b_x32(t_addr + 96, vb);
+                consume(va, 2);
+                tmem_ld_wait();
+                // this warp's share of the accumulator is in registers: hand the buffer back early
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster_relaxed(bar_acc_empty + buf, 0);
+                consume(vb, 3);
                 // fold the tile's four chains into the candidate list
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {

@@ -241,3 +241,43 @@ def test_jitter_matches_reference_semantics(shape, p):
     out.backward(g)
     keep = torch.from_numpy(src == np.arange(shape[2])).to(dev)
     assert torch.equal(z.grad, g * keep)
+
+
+def test_module_is_cuda_graph_capturable():
+    """The whole forward + backward of the module (prepare, fused forward, backward; no host sync, no allocation
+    outside the caching allocator) can be captured in a CUDA graph and replayed on new data."""
+    import b200vq
+    dev = torch.device("cuda:0")
+    B, D, T, K = 32, 64, 201, 1024
+    torch.manual_seed(8)
+    vq = b200vq.VectorQuantizer(K, D, 0.25).to(dev)
+    vq._embedding.weight.data.normal_()
+    static_z = torch.randn(B, D, T, device=dev, requires_grad=True)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            static_z.grad = None
+            vq._embedding.weight.grad = None
+            loss, q, perp, enc = vq(static_z)
+            (loss + q.sum()).backward()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    static_z.grad = None
+    vq._embedding.weight.grad = None
+    with torch.cuda.graph(g):
+        loss, q, perp, enc = vq(static_z)
+        (loss + q.sum()).backward()
+    new = torch.randn(B, D, T, device=dev)
+    static_z.data.copy_(new)
+    g.replay()
+    torch.cuda.synchronize()
+    eager = b200vq.VectorQuantizer(K, D, 0.25).to(dev)
+    eager._embedding.weight.data.copy_(vq._embedding.weight.data)
+    z2 = new.clone().requires_grad_(True)
+    l2, q2, p2, e2 = eager(z2)
+    (l2 + q2.sum()).backward()
+    assert torch.equal(enc, e2) and torch.equal(q.detach(), q2.detach())
+    assert _rel(loss.detach(), l2.detach()) <= 1e-6 and _rel(perp, p2) <= 1e-6
+    assert _rel(static_z.grad, z2.grad) <= 1e-6 and _rel(vq._embedding.weight.grad, eager._embedding.weight.grad) <= RTOL

@@ -15,6 +15,9 @@ for name, (res, args) in L.SIGNATURES.items():
     fn = getattr(lib, name); fn.restype = res; fn.argtypes = args
 onehot_on = "--no-onehot" not in sys.argv
 Bn, D, T, K = 256, 64, 201, 1024
+for a in sys.argv[1:]:
+    if a.startswith("--shape="):
+        Bn, D, T, K = [int(v) for v in a.split("=")[1].split(",")]
 N = Bn * T
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
