@@ -200,7 +200,10 @@ WsLayout ws_layout(long long N) {
     w.partials_off = 0;
     w.counter_off = static_cast<size_t>(kMaxRowsGrid) * sizeof(double);
     w.keys_off = w.counter_off + 256;
-    w.total = w.keys_off + static_cast<size_t>(N) * sizeof(unsigned long long);
+    // the per-row key buffer (unfused paths) and the screen kernel's spill lists (fused path) share the tail
+    const size_t keys_bytes = static_cast<size_t>(N) * sizeof(unsigned long long);
+    const size_t spill_bytes = static_cast<size_t>(kNumSMs) * 4 * SC_SPILL * sizeof(int4);
+    w.total = w.keys_off + (keys_bytes > spill_bytes ? keys_bytes : spill_bytes);
     return w;
 }
 
@@ -412,6 +415,7 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
             fr.z = z; fr.E = E; fr.q_out = quant ? q_out : nullptr; fr.onehot = want_onehot ? onehot : nullptr; fr.hist = hist;
             fr.partials = partials; fr.counter = counter; fr.sse_out = sse; fr.loss = loss; fr.perplexity = perplexity;
             fr.beta = beta; fr.finalize = defer ? 0 : 1; fr.trace = g_trace_buf;
+            fr.spill = reinterpret_cast<int4*>(keys_buf);   // 16-byte aligned: keys_off is a multiple of 256
             static const int evict_first = [] { const char* e = getenv("B200VQ_ONEHOT_EVICT_FIRST"); return e != nullptr && e[0] == '0' ? 0 : 1; }();
             fr.onehot_evict_first = evict_first;
             CUtensorMap tz, thi;

@@ -15,10 +15,14 @@
 //            for any input, not merely equal up to fp32 near-ties.
 //
 // Candidate bookkeeping in the epilogue (thread = (row, column half)): per 256-code tile four running chains
-// (columns j mod 4) keep (best, index, second-best value); at the end of the tile a chain's best enters a sorted
-// 4-entry candidate list if it is within the margin of the running minimum, and anything that is within the margin
-// but cannot be kept (a chain's second best, an evicted entry) lowers `lost`.  If `lost` ends up within the margin
-// of the final minimum (~0.2 % of rows) the row is rescanned exactly over the whole codebook.
+// (columns j mod 4) keep (best, index, second-best value).  At the end of the tile every chain minimum within the
+// margin of the running minimum is APPENDED to the thread's 4-entry candidate log in shared memory (score, code) --
+// the running minimum only decreases, so everything that can matter at the end is logged; a new minimum that beats
+// the old one by more than the margin empties the log, and a full log is first compacted against the running minimum.
+// A chain's second best within the margin is remembered as `lost` together with the 32 columns it hides in.  The
+// logs of the two halves are filtered against the final minimum once per item.  Rows whose `lost` ends up within the
+// margin of the final minimum rescan those 32 columns, or -- when that is not enough (~0.01 % of rows) -- the whole
+// codebook, exactly.
 //
 // Structure (persistent CTA pairs, cta_group::2, M=256 N=256 K=8) and the fused row epilogue are those of
 // argmin_tc2_kernel<..., FUSE=true>; only E_hi is streamed and only tf32(z) is kept in shared memory, which is
@@ -32,12 +36,15 @@ namespace b200vq {
 constexpr int SC_THREADS = 512;
 constexpr int SC_NC_OVERFLOW = 255;   // status: candidate set could not be bounded -> exact scan of the whole codebook
 constexpr int SC_PMAX = 384;          // (row, code) pairs evaluated exactly per 128-row item
+constexpr int SC_LOG = 4;             // candidate log entries per epilogue thread (compacted when full)
+constexpr int SC_SPILL = 128;         // per CTA and in-flight item: candidates that fit neither the log nor the handoff (global memory)
 
 __host__ __device__ constexpr int sc_smem_bytes(int nslab, int nstage, int zbuf) {
     return zbuf * nslab * TC_SLAB_BYTES + nstage * TC_SLAB_BYTES + 2 * TC2_CODES * 4 /* b tile */ +
-           TC2_ARING * TC_ROWS * 4 /* a ring */ + 2 * TC_ROWS * 10 * 4 /* half merge */ +
-           2 * TC_ROWS * 8 * 4 /* handoff: 4 candidates, status, a_n, 2 rescan locations */ + TC_ROWS * 4 /* final idx */ +
-           TC_ROWS * 4 /* full-rescan list */ + TC_ROWS * 4 /* pair ranges */ + SC_PMAX * 8 /* pair list */ +
+           TC2_ARING * TC_ROWS * 4 /* a ring */ + TC_ROWS * 16 /* half merge */ + SC_LOG * 256 * 8 /* candidate logs */ +
+           2 * TC_ROWS * 9 * 4 /* handoff: 4 candidates, status, a_n, threshold, 2 rescan locations */ + TC_ROWS * 8 /* row keys */ +
+           TC_ROWS * 4 /* final idx */ +
+           TC_ROWS * 4 /* full-rescan list */ + TC_ROWS * 4 /* pair ranges */ + SC_PMAX * 4 /* pair list */ +
            TC2_ZERO_BYTES + 512 /* barriers + scratch */ + 1024 /* align */;
 }
 
@@ -90,17 +97,19 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
     uint8_t* stages = zbufs + ZBUF * ZBYTES;
     float* b_tile = reinterpret_cast<float*>(stages + NSTAGE * TC_SLAB_BYTES);   // [2][256]
     float* a_ring = b_tile + 2 * TC2_CODES;                                      // [TC2_ARING][128]
-    float* mrg = a_ring + TC2_ARING * TC_ROWS;                                   // [2][128][10]: half-1 list -> half 0
-    int* h_cand = reinterpret_cast<int*>(mrg + 2 * TC_ROWS * 10);                // [2][128][4]
+    float4* mrg = reinterpret_cast<float4*>(a_ring + TC2_ARING * TC_ROWS);       // [128] half 1 -> half 0: min, n, lost, loc
+    float2* clog = reinterpret_cast<float2*>(mrg + TC_ROWS);                     // [SC_LOG][256] candidate logs: score, code
+    int* h_cand = reinterpret_cast<int*>(clog + SC_LOG * 256);                   // [2][128][4]
     int* h_nc = h_cand + 2 * TC_ROWS * 4;                                        // [2][128] status: nc | nloc << 8, or 255
     float* h_an = reinterpret_cast<float*>(h_nc + 2 * TC_ROWS);                  // [2][128]
-    int* h_loc = reinterpret_cast<int*>(h_an + 2 * TC_ROWS);                     // [2][128][2] chain-instances to rescan
-    int* s_idx = h_loc + 2 * TC_ROWS * 2;                                        // [128] final codes of the workers' item
+    float* h_thr = h_an + 2 * TC_ROWS;                                           // [2][128] final minimum + margin
+    int* h_loc = reinterpret_cast<int*>(h_thr + 2 * TC_ROWS);                    // [2][128][2] chain-instances to rescan
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(h_loc + 2 * TC_ROWS * 2);   // [128] (distance, code) minima
+    int* s_idx = reinterpret_cast<int*>(s_key + TC_ROWS);                        // [128] final codes of the workers' item
     int* s_ovf = s_idx + TC_ROWS;                                                // [128] rows that need the full rescan
-    int* s_rng = s_ovf + TC_ROWS;                                                // [128] pair range of a row: base | count << 16
+    int* s_rng = s_ovf + TC_ROWS;                                                // [128] row state: 0 decided, 1 has pairs, 2 full rescan
     int* pair_rc = s_rng + TC_ROWS;                                              // [SC_PMAX] row << 20 | code
-    float* pair_dist = reinterpret_cast<float*>(pair_rc + SC_PMAX);              // [SC_PMAX]
-    float* zero_row = reinterpret_cast<float*>(pair_dist + SC_PMAX);
+    float* zero_row = reinterpret_cast<float*>(pair_rc + SC_PMAX);
     uint64_t* bars = reinterpret_cast<uint64_t*>(zero_row + TC2_ZERO_BYTES / 4);
     uint64_t* bar_z_full = bars;                        // [ZBUF]
     uint64_t* bar_z_free = bar_z_full + ZBUF;           // [ZBUF]
@@ -119,6 +128,7 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
     unsigned long long* ovf_key = reinterpret_cast<unsigned long long*>(zeros_done + 2);
     float* s_bmax = reinterpret_cast<float*>(ovf_key + 1);    // [8] warp maxima, then [0] = max_k |E_k|^2
     int* pair_count = reinterpret_cast<int*>(s_bmax + 8);
+    int* spill_cnt = pair_count + 1;                          // [4] entries spilled for item it & 3
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = cluster_ctarank();
@@ -160,6 +170,7 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
             *zeros_done = 0;
             *ovf_count = 0;
             *pair_count = 0;
+            for (int i = 0; i < 4; ++i) spill_cnt[i] = 0;
         }
         fence_proxy_async_smem();
     }
@@ -324,25 +335,32 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
             named_bar_sync(5, 320);
         }
         int it = 0, ctg = 0;
+        float b_next = __ldg(e_norm2 + et);
         for (int w = pair; w < n_items; w += n_pairs, ++it) {
             mbar_wait(bar_a_ready + (it % TC2_ARING), (it / TC2_ARING) & 1);
             const float a_n = a_ring[(it % TC2_ARING) * TC_ROWS + row];
             // margin on the score scale: 2*eta = 4*eps + rounding slack (see the header)
             const float margin = 1.0001f * (0.00398438f * sqrtf(a_n * b_max) + 1.9073486e-6f * (a_n + b_max));
-            float lv[4];     // candidate list, ascending
-            int lk[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                lv[q] = INFINITY;
-                lk[q] = 0;
-            }
-            float lost = INFINITY;   // smallest score that is within the margin but could not be kept in the list ...
+            float rmin = INFINITY;   // running minimum of the screening scores of this (row, half)
+            int n = 0;               // entries in this thread's candidate log
+            float lost = INFINITY;   // smallest score that is within the margin but is not in the log ...
             int lost_loc = -1;       // ... and where it hides: chain-instance ct*8 + half*4 + q, or -2 = anywhere
+            float2* my_log = clog + et;
+            bool spilled = false;    // this row has entries in the CTA's spill list (global memory)
+            // what fits neither the log nor the registers goes to a small per-item list in global memory (rare)
+            auto spill = [&](float v, int x, int type) -> bool {
+                const int pos = atomicAdd(spill_cnt + (it & 3), 1);
+                if (pos >= SC_SPILL) return false;
+                fr.spill[(static_cast<size_t>(blockIdx.x) * 4 + (it & 3)) * SC_SPILL + pos] = make_int4(row, __float_as_int(v), x, type);
+                spilled = true;
+                return true;
+            };
             for (int ct = 0; ct < n_ctiles; ++ct, ++ctg) {
                 const int buf = ctg & 1;
                 const int k0 = ct * TC2_CODES;
-                b_tile[buf * TC2_CODES + et] = __ldg(e_norm2 + k0 + et);
+                b_tile[buf * TC2_CODES + et] = b_next;
                 named_bar_sync(1, 256);
+                b_next = __ldg(e_norm2 + (ct + 1 == n_ctiles ? 0 : k0 + TC2_CODES) + et);   // for the next tile
                 if (et == 0) VQ_TR(0, 3 * ctg);
                 mbar_wait(bar_acc_full + buf, (ctg >> 1) & 1);
                 if (et == 0) VQ_TR(0, 3 * ctg + 1);
@@ -398,46 +416,56 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster_relaxed(bar_acc_empty + buf, 0);
                 consume(vb, 3);
-                // fold the tile's four chains into the candidate list
+                // log the chain minima that cannot be ruled out yet
+                {
+                    const float rnew = fminf(fminf(rmin, fminf(m1[0], m1[1])), fminf(m1[2], m1[3]));
+                    const float t = rnew + margin;
+                    if (t < rmin) n = 0;            // the new minimum beats everything logged so far by more than the margin
+                    rmin = rnew;
+                    int slot[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float v = m1[q];
-                    if (v <= lv[0] + margin) {     // cannot be ruled out yet (the running minimum only decreases)
-                        const int kk = k0 + half * 128 + static_cast<int>(i1f[q]);
-                        float ev;                  // what falls off the list
-                        if (v < lv[3]) {
-                            ev = lv[3];
-                            if (v < lv[2]) {
-                                lv[3] = lv[2]; lk[3] = lk[2];
-                                if (v < lv[1]) {
-                                    lv[2] = lv[1]; lk[2] = lk[1];
-                                    if (v < lv[0]) {
-                                        lv[1] = lv[0]; lk[1] = lk[0];
-                                        lv[0] = v; lk[0] = kk;
-                                    } else {
-                                        lv[1] = v; lk[1] = kk;
-                                    }
-                                } else {
-                                    lv[2] = v; lk[2] = kk;
+                    for (int q = 0; q < 4; ++q) {
+                        slot[q] = n;
+                        n += m1[q] <= t ? 1 : 0;
+                    }
+                    if (n <= SC_LOG) {              // the common case: predicated appends
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (m1[q] <= t)
+                                my_log[slot[q] * 256] = make_float2(m1[q], __int_as_float(k0 + half * 128 + static_cast<int>(i1f[q])));
+                        }
+                    } else {                        // log full (rare): drop what the minimum has ruled out, then append
+                        int m = 0;
+                        for (int j = 0; j < slot[0]; ++j) {
+                            const float2 o = my_log[j * 256];
+                            if (o.x <= t) my_log[(m++) * 256] = o;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (m1[q] <= t) {
+                                if (m < SC_LOG) {
+                                    my_log[(m++) * 256] = make_float2(m1[q], __int_as_float(k0 + half * 128 + static_cast<int>(i1f[q])));
+                                } else if (!spill(m1[q], k0 + half * 128 + static_cast<int>(i1f[q]), 0)) {
+                                    lost = (lost <= t) ? fminf(lost, m1[q]) : m1[q];    // nowhere to keep it: can be anywhere
+                                    lost_loc = -2;
                                 }
-                            } else {
-                                lv[3] = v; lk[3] = kk;
                             }
-                        } else {
-                            ev = v;
                         }
-                        if (ev <= lv[0] + margin) {                 // a listed candidate fell off: no cheap way to find it again
-                            lost = fminf(lost, ev);
-                            lost_loc = -2;
-                        }
-                        if (m2[q] <= lv[0] + margin) {              // hidden behind the chain's best: remember the 32 columns
-                            const int loc = ct * 8 + half * 4 + q;
-                            if (lost_loc == -1 || !(lost <= lv[0] + margin)) {   // nothing (still relevant) recorded yet
-                                lost = m2[q];
-                                lost_loc = loc;
-                            } else {
-                                lost = fminf(lost, m2[q]);
-                                if (lost_loc != loc) lost_loc = -2;
+                        n = m;
+                    }
+                    const float w = fminf(fminf(m2[0], m2[1]), fminf(m2[2], m2[3]));
+                    if (w <= t) {                   // a chain's runner-up is hidden behind its best: remember the 32 columns
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (m2[q] <= t) {
+                                const int loc = ct * 8 + half * 4 + q;
+                                if (lost_loc == -1 || !(lost <= t)) {   // nothing (still relevant) recorded yet
+                                    lost = m2[q];
+                                    lost_loc = loc;
+                                } else if (lost_loc == -2 || !spill(m2[q], loc, 1)) {   // a second place to look: spill it
+                                    lost = fminf(lost, m2[q]);
+                                    lost_loc = -2;
+                                }
                             }
                         }
                     }
@@ -445,50 +473,53 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                 if (et == 0) VQ_TR(0, 3 * ctg + 2);
             }
             // merge the two column halves and publish the row's candidates
-            float* ms = mrg + ((it & 1) * TC_ROWS + row) * 10;
             if (half == 1) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    ms[q] = lv[q];
-                    ms[4 + q] = __int_as_float(lk[q]);
-                }
-                ms[8] = lost;
-                ms[9] = __int_as_float(lost_loc);
+                mrg[row] = make_float4(rmin, __int_as_float(n | (spilled ? 256 : 0)), lost, __int_as_float(lost_loc));
             } else {
                 mbar_wait(bar_idx_free + (it & 1), ((it >> 1) & 1) ^ 1);   // the workers are done with this handoff slot
             }
             named_bar_sync(2, 256);
             if (half == 0) {
-                const float smin = fminf(lv[0], ms[0]);
+                const float4 ms = mrg[row];
+                const float smin = fminf(rmin, ms.x);
                 const float thr = smin + margin;
                 int* cand = h_cand + ((it & 1) * TC_ROWS + row) * 4;
                 int* locs = h_loc + ((it & 1) * TC_ROWS + row) * 2;
                 int nc = 0, nloc = 0;
                 bool full = false;
+                const int n1 = __float_as_int(ms.y) & 255;
+                if (__float_as_int(ms.y) & 256) spilled = true;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (lv[q] <= thr) {
-                        if (nc < 4) cand[nc] = lk[q];
-                        ++nc;
+                for (int j = 0; j < SC_LOG; ++j) {
+                    if (j < n) {
+                        const float2 e = my_log[j * 256];
+                        if (e.x <= thr) {
+                            if (nc < 4) cand[nc++] = __float_as_int(e.y);
+                            else if (!spill(e.x, __float_as_int(e.y), 0)) full = true;
+                        }
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (ms[q] <= thr) {
-                        if (nc < 4) cand[nc] = __float_as_int(ms[4 + q]);
-                        ++nc;
+                for (int j = 0; j < SC_LOG; ++j) {
+                    if (j < n1) {
+                        const float2 e = my_log[j * 256 + 128];
+                        if (e.x <= thr) {
+                            if (nc < 4) cand[nc++] = __float_as_int(e.y);
+                            else if (!spill(e.x, __float_as_int(e.y), 0)) full = true;
+                        }
                     }
                 }
                 if (lost <= thr) {
                     if (lost_loc >= 0) locs[nloc++] = lost_loc; else full = true;
                 }
-                if (ms[8] <= thr) {
-                    const int l1 = __float_as_int(ms[9]);
+                if (ms.z <= thr) {
+                    const int l1 = __float_as_int(ms.w);
                     if (l1 >= 0) locs[nloc++] = l1; else full = true;
                 }
-                if (nc > 4 || nc == 0) full = true;
-                h_nc[(it & 1) * TC_ROWS + row] = full ? SC_NC_OVERFLOW : (nc | (nloc << 8));
+                if (nc == 0) full = true;
+                h_nc[(it & 1) * TC_ROWS + row] = full ? SC_NC_OVERFLOW : (nc | (nloc << 4) | (spilled ? 0x40 : 0));
                 h_an[(it & 1) * TC_ROWS + row] = a_n;
+                h_thr[(it & 1) * TC_ROWS + row] = thr;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_idx_ready + (it & 1));
                 if (et == 0) VQ_TR(3, 4 * it + 3);
@@ -535,36 +566,57 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
             const float* ans = h_an + (it & 1) * TC_ROWS;
             // -- refine: exact fp32 distances (oracle order) of every (row, code) pair that is still undecided -------
             const int* locs = h_loc + (it & 1) * TC_ROWS * 2;
+            auto push_pairs = [&](int r, int code, int nloc_entries, int loc0, int loc1) -> bool {
+                // appends (r, code) if code >= 0 and the 32 codes of every listed chain-instance; false if the list is full
+                const int cnt = (code >= 0 ? 1 : 0) + 32 * nloc_entries;
+                const int base = atomicAdd(pair_count, cnt);
+                if (base + cnt > SC_PMAX) {
+                    for (int p = base; p < SC_PMAX; ++p) pair_rc[p] = -1;
+                    return false;
+                }
+                int p = base;
+                if (code >= 0) pair_rc[p++] = (r << 20) | code;
+                for (int l = 0; l < nloc_entries; ++l) {
+                    const int loc = l == 0 ? loc0 : loc1;
+                    const int kb = (loc >> 3) * TC2_CODES + ((loc >> 2) & 1) * 128 + (loc & 3);
+                    for (int j = 0; j < 32; ++j) pair_rc[p++] = (r << 20) | (kb + 4 * j);
+                }
+                return true;
+            };
             for (int r = wt; r < rows_here; r += NW) {       // 1. enumerate the pairs
                 const int st = ncs[r];
-                int rng = 0;
+                int state = 0;
                 if (st == SC_NC_OVERFLOW) {
-                    s_ovf[atomicAdd(ovf_count, 1)] = r;
+                    state = 2;
                 } else {
-                    const int nc = st & 0xff, nloc = st >> 8;
-                    const int cnt = (nc > 1 || nloc > 0) ? nc + 32 * nloc : 0;
-                    if (cnt == 0) {
+                    const int nc = st & 0xf, nloc = (st >> 4) & 3;
+                    if (nc == 1 && nloc == 0 && !(st & 0x40)) {
                         s_idx[r] = cand[r * 4];              // a single candidate IS the argmin: nothing to compute
                     } else {
-                        const int base = atomicAdd(pair_count, cnt);
-                        if (base + cnt > SC_PMAX) {          // list full (pathological margin): rescan the row instead
-                            for (int p = base; p < SC_PMAX; ++p) pair_rc[p] = -1;
-                            s_ovf[atomicAdd(ovf_count, 1)] = r;
-                        } else {
-                            int p = base;
-                            for (int j = 0; j < nc; ++j) pair_rc[p++] = (r << 20) | cand[r * 4 + j];
-                            for (int l = 0; l < nloc; ++l) {
-                                const int loc = locs[r * 2 + l];
-                                const int kb = (loc >> 3) * TC2_CODES + ((loc >> 2) & 1) * 128 + (loc & 3);
-                                for (int j = 0; j < 32; ++j) pair_rc[p++] = (r << 20) | (kb + 4 * j);
-                            }
-                            rng = base | (cnt << 16);
-                        }
+                        state = 1;
+                        s_key[r] = ~0ull;
+                        for (int j = 0; j < nc && state == 1; ++j)
+                            if (!push_pairs(r, cand[r * 4 + j], 0, 0, 0)) state = 2;
+                        if (state == 1 && nloc > 0 && !push_pairs(r, -1, nloc, locs[r * 2], locs[r * 2 + 1])) state = 2;   // list full: rescan the row
                     }
                 }
-                s_rng[r] = rng;
+                if (state == 2) s_ovf[atomicAdd(ovf_count, 1)] = r;
+                s_rng[r] = state;
             }
             named_bar_sync(4, NW);
+            const int n_spill = min(spill_cnt[it & 3], SC_SPILL);
+            if (n_spill > 0) {                               // 1b. rows whose candidates overflowed into global memory
+                const int4* sp = fr.spill + (static_cast<size_t>(blockIdx.x) * 4 + (it & 3)) * SC_SPILL;
+                const float* thrs = h_thr + (it & 1) * TC_ROWS;
+                for (int e = wt; e < n_spill; e += NW) {
+                    const int4 en = __ldcg(sp + e);
+                    const int r = en.x;
+                    if (r >= rows_here || ncs[r] == SC_NC_OVERFLOW || !(__int_as_float(en.y) <= thrs[r])) continue;
+                    const bool ok = en.w == 0 ? push_pairs(r, en.z, 0, 0, 0) : push_pairs(r, -1, 1, en.z, 0);
+                    if (!ok && atomicExch(s_rng + r, 2) != 2) s_ovf[atomicAdd(ovf_count, 1)] = r;
+                }
+                named_bar_sync(4, NW);
+            }
             {                                                // 2. one exact distance per thread and pass
                 const int np = min(*pair_count, SC_PMAX);
                 for (int p = wt; p < np; p += NW) {
@@ -572,28 +624,13 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                     if (rc >= 0) {
                         const int r = rc >> 20, k = rc & 0xfffff;
                         const float c = dot_chain_exact<D>(fr.z + (row0 + r) * D, fr.E + static_cast<size_t>(k) * D);
-                        pair_dist[p] = fmaf(-2.0f, c, ans[r] + __ldg(e_norm2 + k));
+                        atomicMin(s_key + r, pack_key(fmaf(-2.0f, c, ans[r] + __ldg(e_norm2 + k)), k));
                     }
                 }
             }
             named_bar_sync(4, NW);
-            for (int r = wt; r < rows_here; r += NW) {       // 3. per row: smallest distance, first index on ties
-                const int rng = s_rng[r];
-                if (rng != 0) {
-                    const int base = rng & 0xffff, cnt = rng >> 16;
-                    float best = INFINITY;
-                    int code = 0x7fffffff;
-                    for (int p = base; p < base + cnt; ++p) {
-                        const float dist = pair_dist[p];
-                        const int k = pair_rc[p] & 0xfffff;
-                        if (dist < best || (dist == best && k < code)) {
-                            best = dist;
-                            code = k;
-                        }
-                    }
-                    s_idx[r] = code;
-                }
-            }
+            for (int r = wt; r < rows_here; r += NW)         // 3. per row: smallest distance, first index on ties
+                if (s_rng[r] == 1) s_idx[r] = static_cast<int>(s_key[r] & 0xffffffffu);
             named_bar_sync(4, NW);
             if (wt == 0) VQ_TR(5, 4 * it + 1);
             // -- rare: rows whose candidate set could not be bounded -> exact scan of the whole codebook ---------
@@ -651,6 +688,7 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
             if (wt == 0) {
                 *ovf_count = 0;
                 *pair_count = 0;
+                spill_cnt[it & 3] = 0;
             }
             named_bar_sync(4, NW);
             if (wt == 0) VQ_TR(5, 4 * it + 2);

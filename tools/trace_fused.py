@@ -14,6 +14,7 @@ lib = ctypes.CDLL(so)
 for name, (res, args) in L.SIGNATURES.items():
     fn = getattr(lib, name); fn.restype = res; fn.argtypes = args
 onehot_on = "--no-onehot" not in sys.argv
+force_screen = (1 << 10) if "--screen" in sys.argv else 0
 Bn, D, T, K = 256, 64, 201, 1024
 for a in sys.argv[1:]:
     if a.startswith("--shape="):
@@ -33,7 +34,7 @@ lib.vq_debug_set_trace(trace.data_ptr())
 for rep in range(3):
     trace.zero_()
     assert lib.vq_prepare_codebook(E.data_ptr(), K, D, e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(), st) == 0
-    rc = lib.vq_forward(z.data_ptr(), E.data_ptr(), e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(), N, K, D, 0.25, 1 if onehot_on else 0,
+    rc = lib.vq_forward(z.data_ptr(), E.data_ptr(), e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(), N, K, D, 0.25, (1 if onehot_on else 0) | force_screen,
                         q.data_ptr(), idx.data_ptr(), None if oh is None else oh.data_ptr(), stats.data_ptr(), stats.data_ptr() + 4 * K,
                         stats.data_ptr() + 4 * (K + 1), stats.data_ptr() + 4 * (K + 2), ws.data_ptr(), wsb, st)
     assert rc == 0, lib.vq_last_error()
