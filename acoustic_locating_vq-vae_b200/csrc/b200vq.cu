@@ -403,13 +403,13 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
     if (tensor_path_ok(N, K, D, flags, z, E_hi, E_lo, true)) {
         const long long row_tiles = (N + TC_ROWS - 1) / TC_ROWS;
         // ---- screen + refine (one TF32 pass, exact fp32 refine of the candidates): the default fused forward ----
-        // Measured on B200: with D <= 64 AND the dense one-hot emitted the forward is HBM-bound and the 3xTF32 kernel's
-        // lighter row workers win (61 vs 65 us on the RIR-256 workload); everywhere else screen + refine is faster
-        // (1.4x at D = 64, 2x at D = 128) -- and D > 128 only fits this kernel.  VQ_FLAG_SCREEN forces it.
+        // Indices are bit-identical to the fp32 oracle, and it is the faster kernel everywhere on B200 (RIR-256 with the
+        // dense one-hot: 69.0 vs 69.6 us per step; 1.5x at D = 64 and 2x at D = 128 without the one-hot); D > 128 only
+        // fits this kernel.  VQ_FLAG_NO_SCREEN / B200VQ_SCREEN=0 select the 3xTF32 kernel, VQ_FLAG_SCREEN forces this one.
         const bool screen_shape = (K % TC2_CODES == 0) && (D <= 128 || D == 192 || D == 256) && aligned16(E) &&
                                   (!quant || aligned16(q_out)) && (!want_onehot || aligned16(onehot)) &&
                                   !(flags & (VQ_FLAG_NO_SCREEN | VQ_FLAG_NO_FUSE | VQ_FLAG_TC_1CTA));
-        const bool screen = screen_shape && ((flags & VQ_FLAG_SCREEN) || (screen_enabled() && (D > 64 || !want_onehot)));
+        const bool screen = screen_shape && ((flags & VQ_FLAG_SCREEN) || screen_enabled());
         if (screen) {
             FusedRowArgs fr{};
             fr.z = z; fr.E = E; fr.q_out = quant ? q_out : nullptr; fr.onehot = want_onehot ? onehot : nullptr; fr.hist = hist;

@@ -90,6 +90,9 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                  const float* __restrict__ e_norm2, long long N, int K, int n_items, int* __restrict__ idx_out,
                  const FusedRowArgs fr) {
     extern __shared__ uint8_t smem_raw[];
+#ifdef VQ_TRACE
+    if (threadIdx.x == 0 && fr.trace != nullptr) fr.trace[(blockIdx.x * 8 + 7) * 64 + 5] = static_cast<long long>(global_timer_ns());
+#endif
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int D = NSLAB * TC_SLAB_FLOATS;
     constexpr int ZBYTES = NSLAB * TC_SLAB_BYTES;              // one z buffer: tf32(z) only
@@ -531,6 +534,7 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
             const uint32_t row_bytes = static_cast<uint32_t>(K) * 4u;
             const uint32_t chunk = row_bytes < TC2_ZERO_BYTES ? row_bytes : TC2_ZERO_BYTES;
             const uint64_t pol = l2_policy_evict_first();
+            VQ_TR(4, 0);
             for (int w = pair; w < n_items; w += n_pairs) {
                 const long long row0 = static_cast<long long>(2 * w + static_cast<int>(cta_rank)) * TC_ROWS;
                 const long long left = N - row0;
@@ -544,7 +548,9 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                 }
                 bulk_commit();
             }
+            VQ_TR(4, 1);
             bulk_wait_all();
+            VQ_TR(4, 2);
             fence_proxy_async_all();
             st_release_cta(zeros_done, 1);
         }
@@ -737,16 +743,11 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
             if (wt == 0) VQ_TR(5, 4 * it + 3);
         }
         if (have_oh) {
-            while (ld_acquire_cta(zeros_done) == 0) {
-            }
-            for (int w = pair; w < n_items; w += n_pairs) {
-                const long long row0 = static_cast<long long>(2 * w + static_cast<int>(cta_rank)) * TC_ROWS;
-                for (int r = wt; r < TC_ROWS; r += NW) {
-                    const long long gr = row0 + r;
-                    if (gr < N) __stcs(fr.onehot + gr * K + __ldcg(idx_out + gr), 1.0f);
-                }
-            }
+            if (wt == 0) VQ_TR(6, 0);
+            patch_onehot_ones(fr.onehot, idx_out, N, K, pair, n_items, n_pairs, wt, NW,
+                              [&](int w) { return static_cast<long long>(2 * w + static_cast<int>(cta_rank)) * TC_ROWS; }, zeros_done);
         }
+        if (wt == 0) VQ_TR(6, 2);
         // per-CTA SSE partial, then last-CTA-done reduction in a fixed order (+ loss / perplexity)
         const int wwarp = have_oh ? warp - 13 : warp - 12;
         double sd = warp_sum_d(static_cast<double>(sse));
@@ -763,7 +764,13 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
         if (*last_flag) {
             __threadfence();
             double t = 0.0;
-            for (int i = wt; i < static_cast<int>(gridDim.x); i += NW) t += __ldcg(fr.partials + i);
+            {
+                const int g = static_cast<int>(gridDim.x);
+                const double p0 = wt < g ? __ldcg(fr.partials + wt) : 0.0;
+                const double p1 = wt + NW < g ? __ldcg(fr.partials + wt + NW) : 0.0;
+                t = p0 + p1;
+                for (int i = wt + 2 * NW; i < g; i += NW) t += __ldcg(fr.partials + i);
+            }
             t = warp_sum_d(t);
             named_bar_sync(4, NW);
             if (lane == 0) red[wwarp] = t;
@@ -780,9 +787,17 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                 }
                 double ent = 0.0;
                 const float nf = static_cast<float>(N);
-                for (int k = wt; k < K; k += NW) {
-                    const float p = __fdiv_rn(__ldcg(fr.hist + k), nf);
-                    ent += static_cast<double>(p * logf(p + 1e-10f));
+                for (int kb = wt; kb < K; kb += 8 * NW) {      // 8 loads in flight: this runs on the kernel's critical tail
+                    float h[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) h[u] = kb + u * NW < K ? __ldcg(fr.hist + kb + u * NW) : 0.0f;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (kb + u * NW < K) {
+                            const float p = __fdiv_rn(h[u], nf);                     // vector_quantizer.py:55
+                            ent += static_cast<double>(p * logf(p + 1e-10f));        // :56
+                        }
+                    }
                 }
                 ent = warp_sum_d(ent);
                 named_bar_sync(4, NW);
@@ -807,6 +822,9 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
         tc_fence_after();
         tmem_dealloc_2sm(tmem_base, TC2_TMEM_COLS);
     }
+#ifdef VQ_TRACE
+    if (threadIdx.x == 64 && fr.trace != nullptr) fr.trace[(blockIdx.x * 8 + 7) * 64 + 6] = static_cast<long long>(global_timer_ns());
+#endif
 }
 
 }  // namespace b200vq

@@ -312,6 +312,46 @@ struct FusedRowArgs {
     long long* trace;          // VQ_TRACE builds only: [cta][role 0..7][64] clock64 stamps
 };
 
+// The '1's of the dense one-hot (vector_quantizer.py:40).  The filler thread zero-fills whole rows with bulk copies;
+// once they have all landed (`zeros_done`) every row's code is re-read from idx_out (written by this CTA, L2-resident)
+// and patched in.  The codes of the first items are fetched BEFORE the wait, and later ones a batch ahead, so the
+// patch costs stores only -- it sits on the kernel's critical tail.
+template <typename Row0Of>
+__device__ __forceinline__ void patch_onehot_ones(float* __restrict__ onehot, const int* __restrict__ idx_out, long long N, int K,
+                                                  int first_item, int n_items, int item_stride, int wt, int NW, Row0Of row0_of,
+                                                  const int* zeros_done) {
+    constexpr int IB = 4;
+    int codes[IB][2];
+    auto load = [&](int w0) {
+#pragma unroll
+        for (int u = 0; u < IB; ++u) {
+            const int w = w0 + u * item_stride;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = wt + h * NW;
+                const long long gr = row0_of(w) + r;
+                codes[u][h] = (w < n_items && r < TC_ROWS && gr < N) ? __ldcg(idx_out + gr) : -1;
+            }
+        }
+    };
+    load(first_item);
+    while (ld_acquire_cta(zeros_done) == 0) {
+    }
+    for (int w0 = first_item; w0 < n_items; w0 += IB * item_stride) {
+#pragma unroll
+        for (int u = 0; u < IB; ++u) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (codes[u][h] >= 0) {
+                    const long long gr = row0_of(w0 + u * item_stride) + (wt + h * NW);
+                    __stcs(onehot + gr * K + codes[u][h], 1.0f);
+                }
+            }
+        }
+        if (w0 + IB * item_stride < n_items) load(w0 + IB * item_stride);
+    }
+}
+
 #ifdef VQ_TRACE
 #define VQ_TR(role, slot)                                                                              \
     do {                                                                                               \
@@ -757,15 +797,9 @@ argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
         if (have_oh) {
             // the '1's of the one-hot (vector_quantizer.py:40): once all zero rows of this CTA have landed, every
             // row's code is re-read from idx_out (written by this CTA's epilogue, L2-resident) and patched in
-            while (ld_acquire_cta(zeros_done) == 0) {
-            }
-            for (int w = pair; w < n_items; w += n_pairs) {
-                const long long row0 = static_cast<long long>(2 * (w / splits) + static_cast<int>(cta_rank)) * TC_ROWS;
-                for (int r = wt; r < TC_ROWS; r += NW) {
-                    const long long gr = row0 + r;
-                    if (gr < N) __stcs(fr.onehot + gr * K + __ldcg(idx_out + gr), 1.0f);
-                }
-            }
+            patch_onehot_ones(fr.onehot, idx_out, N, K, pair, n_items, n_pairs, wt, NW,
+                              [&](int w) { return static_cast<long long>(2 * (w / splits) + static_cast<int>(cta_rank)) * TC_ROWS; },
+                              zeros_done);
             if (wt == 0) VQ_TR(5, 60);
         }
         // per-CTA SSE partial, then last-CTA-done reduction in a fixed order (+ loss / perplexity)
@@ -784,7 +818,13 @@ argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
         if (*last_flag) {
             __threadfence();
             double t = 0.0;
-            for (int i = wt; i < static_cast<int>(gridDim.x); i += NW) t += __ldcg(fr.partials + i);
+            {
+                const int g = static_cast<int>(gridDim.x);
+                const double p0 = wt < g ? __ldcg(fr.partials + wt) : 0.0;
+                const double p1 = wt + NW < g ? __ldcg(fr.partials + wt + NW) : 0.0;
+                t = p0 + p1;
+                for (int i = wt + 2 * NW; i < g; i += NW) t += __ldcg(fr.partials + i);
+            }
             t = warp_sum_d(t);
             named_bar_sync(4, NW);
             if (lane == 0) red[wwarp] = t;
@@ -801,9 +841,17 @@ argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
                 }
                 double ent = 0.0;
                 const float nf = static_cast<float>(N);
-                for (int k = wt; k < K; k += NW) {
-                    const float p = __fdiv_rn(__ldcg(fr.hist + k), nf);    // vector_quantizer.py:55
-                    ent += static_cast<double>(p * logf(p + 1e-10f));       // :56
+                for (int kb = wt; kb < K; kb += 8 * NW) {      // 8 loads in flight: this runs on the kernel's critical tail
+                    float h[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) h[u] = kb + u * NW < K ? __ldcg(fr.hist + kb + u * NW) : 0.0f;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (kb + u * NW < K) {
+                            const float p = __fdiv_rn(h[u], nf);                     // vector_quantizer.py:55
+                            ent += static_cast<double>(p * logf(p + 1e-10f));        // :56
+                        }
+                    }
                 }
                 ent = warp_sum_d(ent);
                 named_bar_sync(4, NW);

@@ -343,7 +343,11 @@ def main():
     else:
         bound, peak, achieved, unit = "hbm", peaks["hbm_gbs"], work["bytes"] / dur_s / 1e9, "GB/s"
         per_launch = work["bytes"]
-    roofline = {"kernel": ("fused forward (argmin_tc2 + row epilogue)" if fused and dom == "argmin_tc" else dom), "bound": bound,
+    screen_used = (not args.exact and not args.no_screen and not args.no_fuse and K % 256 == 0 and D in (32, 64, 96, 128, 192, 256)
+                   and os.environ.get("B200VQ_SCREEN", "1")[:1] != "0") or (args.screen and K % 256 == 0)
+    fused_name = ("fused forward (vq_screen_kernel: TF32 screen + exact refine + row epilogue)" if screen_used
+                  else "fused forward (argmin_tc2: 3xTF32 + row epilogue)")
+    roofline = {"kernel": (fused_name if fused and dom == "argmin_tc" else dom), "bound": bound,
                 "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": unit, "frac": round(achieved / peak, 4),
                 "traffic": traffic.get(args.workload, {}).get(dom),
                 "peak_source": peaks["source"] + (" bf16/2 (tf32 pipe)" if bound == "tensor" else " copy bandwidth"),
@@ -420,7 +424,7 @@ def main():
         line = {
             "metric": "quantized vectors/sec (VQ fwd+bwd)", "value": value, "unit": "vectors/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": ("f32" if args.exact else ("f32 (tcgen05 3xTF32 contraction, fp32 accumulate)" if (args.no_screen or args.no_fuse or (D <= 64 and emit_onehot and not args.screen)) else
+            "scaling": "weak", "vs_baseline": None, "dtype": ("f32" if args.exact else ("f32 (tcgen05 3xTF32 contraction, fp32 accumulate)" if not screen_used else
                       "f32 (tcgen05 TF32 screening pass + exact fp32 refine of the candidates: indices bit-exact vs the fp32 oracle)")),
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "B": B, "D": D, "T": T, "K": K, "rows_per_gpu": N, "beta": BETA,
