@@ -42,9 +42,9 @@ constexpr int SC_SPILL = 128;         // per CTA and in-flight item: candidates 
 __host__ __device__ constexpr int sc_smem_bytes(int nslab, int nstage, int zbuf) {
     return zbuf * nslab * TC_SLAB_BYTES + nstage * TC_SLAB_BYTES + 2 * TC2_CODES * 4 /* b tile */ +
            TC2_ARING * TC_ROWS * 4 /* a ring */ + TC_ROWS * 16 /* half merge */ + SC_LOG * 256 * 8 /* candidate logs */ +
-           2 * TC_ROWS * 9 * 4 /* handoff: 4 candidates, status, a_n, threshold, 2 rescan locations */ + TC_ROWS * 8 /* row keys */ +
-           TC_ROWS * 4 /* final idx */ +
-           TC_ROWS * 4 /* full-rescan list */ + TC_ROWS * 4 /* pair ranges */ + SC_PMAX * 4 /* pair list */ +
+           2 * TC_ROWS * 9 * 4 /* handoff: 4 candidates, status, a_n, threshold, 2 rescan locations */ +
+           2 * TC_ROWS * 8 /* row keys, per worker group */ + 2 * TC_ROWS * 4 /* final idx */ +
+           2 * TC_ROWS * 4 /* full-rescan lists */ + 2 * TC_ROWS * 4 /* row states */ + SC_PMAX * 4 /* pair lists */ +
            TC2_ZERO_BYTES + 512 /* barriers + scratch */ + 1024 /* align */;
 }
 
@@ -107,11 +107,12 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
     float* h_an = reinterpret_cast<float*>(h_nc + 2 * TC_ROWS);                  // [2][128]
     float* h_thr = h_an + 2 * TC_ROWS;                                           // [2][128] final minimum + margin
     int* h_loc = reinterpret_cast<int*>(h_thr + 2 * TC_ROWS);                    // [2][128][2] chain-instances to rescan
-    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(h_loc + 2 * TC_ROWS * 2);   // [128] (distance, code) minima
-    int* s_idx = reinterpret_cast<int*>(s_key + TC_ROWS);                        // [128] final codes of the workers' item
-    int* s_ovf = s_idx + TC_ROWS;                                                // [128] rows that need the full rescan
-    int* s_rng = s_ovf + TC_ROWS;                                                // [128] row state: 0 decided, 1 has pairs, 2 full rescan
-    int* pair_rc = s_rng + TC_ROWS;                                              // [SC_PMAX] row << 20 | code
+    // worker-group state ([2]: the row workers run as two independent groups when no one-hot is emitted)
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(h_loc + 2 * TC_ROWS * 2);   // [2][128] (distance, code) minima
+    int* s_idx = reinterpret_cast<int*>(s_key + 2 * TC_ROWS);                    // [2][128] final codes of the group's item
+    int* s_ovf = s_idx + 2 * TC_ROWS;                                            // [2][128] rows that need the full rescan
+    int* s_rng = s_ovf + 2 * TC_ROWS;                                            // [2][128] row state: 0 decided, 1 has pairs, 2 full rescan
+    int* pair_rc = s_rng + 2 * TC_ROWS;                                          // [SC_PMAX] row << 20 | code (split between the groups)
     float* zero_row = reinterpret_cast<float*>(pair_rc + SC_PMAX);
     uint64_t* bars = reinterpret_cast<uint64_t*>(zero_row + TC2_ZERO_BYTES / 4);
     uint64_t* bar_z_full = bars;                        // [ZBUF]
@@ -127,11 +128,11 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_idx_free + 2);
     double* red = reinterpret_cast<double*>(tmem_slot + 2);   // [4] + flag
     int* zeros_done = reinterpret_cast<int*>(red + 5);
-    int* ovf_count = zeros_done + 1;
-    unsigned long long* ovf_key = reinterpret_cast<unsigned long long*>(zeros_done + 2);
-    float* s_bmax = reinterpret_cast<float*>(ovf_key + 1);    // [8] warp maxima, then [0] = max_k |E_k|^2
-    int* pair_count = reinterpret_cast<int*>(s_bmax + 8);
-    int* spill_cnt = pair_count + 1;                          // [4] entries spilled for item it & 3
+    unsigned long long* ovf_key = reinterpret_cast<unsigned long long*>(zeros_done + 2);   // [2]
+    float* s_bmax = reinterpret_cast<float*>(ovf_key + 2);    // [8] warp maxima, then [0] = max_k |E_k|^2
+    int* pair_count = reinterpret_cast<int*>(s_bmax + 8);     // [2]
+    int* ovf_count = pair_count + 2;                          // [2]
+    int* spill_cnt = ovf_count + 2;                           // [4] entries spilled for item it & 3
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = cluster_ctarank();
@@ -158,7 +159,7 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
             mbar_init(bar_acc_full + b, 1);
             mbar_init(bar_acc_empty + b, 16);
             mbar_init(bar_idx_ready + b, 4);
-            mbar_init(bar_idx_free + b, have_oh ? 3 : 4);
+            mbar_init(bar_idx_free + b, have_oh ? 3 : 2);    // one arrival per warp of the worker group that owns the slot
         }
         fence_mbar_init();
     }
@@ -171,8 +172,7 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
             reinterpret_cast<float4*>(zero_row)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (threadIdx.x == 384) {
             *zeros_done = 0;
-            *ovf_count = 0;
-            *pair_count = 0;
+            for (int i = 0; i < 2; ++i) ovf_count[i] = pair_count[i] = 0;
             for (int i = 0; i < 4; ++i) spill_cnt[i] = 0;
         }
         fence_proxy_async_smem();
@@ -380,25 +380,31 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                 uint32_t va[32], vb[32];
                 // The scan is bound by the ALU pipe (compare / select / min-max issue every 2 cycles per warp), so the
                 // two conditional updates are done as predicated FMA-pipe moves (d = s*1 + 0) and the column index is
-                // carried as a float: per element 3 FMA-pipe ops (score, 2 moves) and 3 ALU-pipe ops (setp, max, min).
+                // carried as a float: per element 3 FMA-pipe ops (score, 2 moves) and 2.5 ALU-pipe ops (setp, max, half of a
+                // 3-input min).
                 auto consume = [&](const uint32_t (&v)[32], int cc) {       // 32 columns starting at cc*32
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 b = b4[cc * 8 + j4];
-                        const float bb[4] = {b.x, b.y, b.z, b.w};
+                    for (int j4 = 0; j4 < 8; j4 += 2) {
+                        const float4 ba = b4[cc * 8 + j4], bb = b4[cc * 8 + j4 + 1];
+                        const float bq[2][4] = {{ba.x, ba.y, ba.z, ba.w}, {bb.x, bb.y, bb.z, bb.w}};
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float s = fmaf(-2.0f, __uint_as_float(v[j4 * 4 + q]), bb[q]);
-                            m2[q] = fminf(m2[q], fmaxf(s, m1[q]));                 // runner-up of the chain
-                            const float colf = static_cast<float>(cc * 32 + j4 * 4 + q);
-                            asm("{\n"
-                                ".reg .pred p;\n"
-                                "setp.lt.f32 p, %2, %0;\n"
-                                "@p fma.rn.f32 %0, %2, 0f3F800000, 0f00000000;\n"
-                                "@p fma.rn.f32 %1, %3, 0f3F800000, 0f00000000;\n"
-                                "}\n"
-                                : "+f"(m1[q]), "+f"(i1f[q])
-                                : "f"(s), "f"(colf));
+                            float t[2];                    // max(score, best so far): what the runner-up can fall to
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const float s = fmaf(-2.0f, __uint_as_float(v[(j4 + h) * 4 + q]), bq[h][q]);
+                                t[h] = fmaxf(s, m1[q]);
+                                const float colf = static_cast<float>(cc * 32 + (j4 + h) * 4 + q);
+                                asm("{\n"
+                                    ".reg .pred p;\n"
+                                    "setp.lt.f32 p, %2, %0;\n"
+                                    "@p fma.rn.f32 %0, %2, 0f3F800000, 0f00000000;\n"
+                                    "@p fma.rn.f32 %1, %3, 0f3F800000, 0f00000000;\n"
+                                    "}\n"
+                                    : "+f"(m1[q]), "+f"(i1f[q])
+                                    : "f"(s), "f"(colf));
+                            }
+                            m2[q] = fminf(fminf(m2[q], t[0]), t[1]);   // one 3-input FMNMX3 per two elements
                         }
                     }
                 };
@@ -556,12 +562,26 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
         }
     } else {
         // ===== row workers (3 or 4 warps): exact refine, then vector_quantizer.py:40-56 =====
+        // Per item the work is a chain of short, latency-bound phases, so without the one-hot filler the four warps
+        // run as TWO independent groups, one per handoff slot (even / odd items), which overlaps those latencies.
         constexpr int DV = NSLAB * 8;
-        const int NW = have_oh ? 96 : 128;
-        const int wt = have_oh ? threadIdx.x - 416 : threadIdx.x - 384;
+        const int NW_all = have_oh ? 96 : 128;
+        const int wt_all = have_oh ? threadIdx.x - 416 : threadIdx.x - 384;
+        const int groups = have_oh ? 1 : 2;
+        const int NW = NW_all / groups;                      // threads of this group
+        const int grp = wt_all / NW, wt = wt_all - grp * NW; // group, thread within the group
+        const int gbar = 4 + 2 * grp;                        // the group's named barrier
+        const int pmax = SC_PMAX / groups;
+        unsigned long long* const g_key = s_key + grp * TC_ROWS;
+        int* const g_idx = s_idx + grp * TC_ROWS;
+        int* const g_ovf = s_ovf + grp * TC_ROWS;
+        int* const g_rng = s_rng + grp * TC_ROWS;
+        int* const g_pair = pair_rc + grp * pmax;
+        int* const g_pcount = pair_count + grp;
+        int* const g_ocount = ovf_count + grp;
+        unsigned long long* const g_okey = ovf_key + grp;
         float sse = 0.0f;
-        int it = 0;
-        for (int w = pair; w < n_items; w += n_pairs, ++it) {
+        for (int w = pair + grp * n_pairs, it = grp; w < n_items; w += groups * n_pairs, it += groups) {
             const long long row0 = static_cast<long long>(2 * w + static_cast<int>(cta_rank)) * TC_ROWS;
             const long long left = N - row0;
             const int rows_here = left <= 0 ? 0 : (left < TC_ROWS ? static_cast<int>(left) : TC_ROWS);
@@ -575,17 +595,17 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
             auto push_pairs = [&](int r, int code, int nloc_entries, int loc0, int loc1) -> bool {
                 // appends (r, code) if code >= 0 and the 32 codes of every listed chain-instance; false if the list is full
                 const int cnt = (code >= 0 ? 1 : 0) + 32 * nloc_entries;
-                const int base = atomicAdd(pair_count, cnt);
-                if (base + cnt > SC_PMAX) {
-                    for (int p = base; p < SC_PMAX; ++p) pair_rc[p] = -1;
+                const int base = atomicAdd(g_pcount, cnt);
+                if (base + cnt > pmax) {
+                    for (int p = base; p < pmax; ++p) g_pair[p] = -1;
                     return false;
                 }
                 int p = base;
-                if (code >= 0) pair_rc[p++] = (r << 20) | code;
+                if (code >= 0) g_pair[p++] = (r << 20) | code;
                 for (int l = 0; l < nloc_entries; ++l) {
                     const int loc = l == 0 ? loc0 : loc1;
                     const int kb = (loc >> 3) * TC2_CODES + ((loc >> 2) & 1) * 128 + (loc & 3);
-                    for (int j = 0; j < 32; ++j) pair_rc[p++] = (r << 20) | (kb + 4 * j);
+                    for (int j = 0; j < 32; ++j) g_pair[p++] = (r << 20) | (kb + 4 * j);
                 }
                 return true;
             };
@@ -597,19 +617,19 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                 } else {
                     const int nc = st & 0xf, nloc = (st >> 4) & 3;
                     if (nc == 1 && nloc == 0 && !(st & 0x40)) {
-                        s_idx[r] = cand[r * 4];              // a single candidate IS the argmin: nothing to compute
+                        g_idx[r] = cand[r * 4];              // a single candidate IS the argmin: nothing to compute
                     } else {
                         state = 1;
-                        s_key[r] = ~0ull;
+                        g_key[r] = ~0ull;
                         for (int j = 0; j < nc && state == 1; ++j)
                             if (!push_pairs(r, cand[r * 4 + j], 0, 0, 0)) state = 2;
                         if (state == 1 && nloc > 0 && !push_pairs(r, -1, nloc, locs[r * 2], locs[r * 2 + 1])) state = 2;   // list full: rescan the row
                     }
                 }
-                if (state == 2) s_ovf[atomicAdd(ovf_count, 1)] = r;
-                s_rng[r] = state;
+                if (state == 2) g_ovf[atomicAdd(g_ocount, 1)] = r;
+                g_rng[r] = state;
             }
-            named_bar_sync(4, NW);
+            named_bar_sync(gbar, NW);
             const int n_spill = min(spill_cnt[it & 3], SC_SPILL);
             if (n_spill > 0) {                               // 1b. rows whose candidates overflowed into global memory
                 const int4* sp = fr.spill + (static_cast<size_t>(blockIdx.x) * 4 + (it & 3)) * SC_SPILL;
@@ -619,38 +639,38 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                     const int r = en.x;
                     if (r >= rows_here || ncs[r] == SC_NC_OVERFLOW || !(__int_as_float(en.y) <= thrs[r])) continue;
                     const bool ok = en.w == 0 ? push_pairs(r, en.z, 0, 0, 0) : push_pairs(r, -1, 1, en.z, 0);
-                    if (!ok && atomicExch(s_rng + r, 2) != 2) s_ovf[atomicAdd(ovf_count, 1)] = r;
+                    if (!ok && atomicExch(g_rng + r, 2) != 2) g_ovf[atomicAdd(g_ocount, 1)] = r;
                 }
-                named_bar_sync(4, NW);
+                named_bar_sync(gbar, NW);
             }
             {                                                // 2. one exact distance per thread and pass
-                const int np = min(*pair_count, SC_PMAX);
+                const int np = min(*g_pcount, pmax);
                 for (int p = wt; p < np; p += NW) {
-                    const int rc = pair_rc[p];
+                    const int rc = g_pair[p];
                     if (rc >= 0) {
                         const int r = rc >> 20, k = rc & 0xfffff;
                         const float c = dot_chain_exact<D>(fr.z + (row0 + r) * D, fr.E + static_cast<size_t>(k) * D);
-                        atomicMin(s_key + r, pack_key(fmaf(-2.0f, c, ans[r] + __ldg(e_norm2 + k)), k));
+                        atomicMin(g_key + r, pack_key(fmaf(-2.0f, c, ans[r] + __ldg(e_norm2 + k)), k));
                     }
                 }
             }
-            named_bar_sync(4, NW);
+            named_bar_sync(gbar, NW);
             for (int r = wt; r < rows_here; r += NW)         // 3. per row: smallest distance, first index on ties
-                if (s_rng[r] == 1) s_idx[r] = static_cast<int>(s_key[r] & 0xffffffffu);
-            named_bar_sync(4, NW);
+                if (g_rng[r] == 1) g_idx[r] = static_cast<int>(g_key[r] & 0xffffffffu);
+            named_bar_sync(gbar, NW);
             if (wt == 0) VQ_TR(5, 4 * it + 1);
             // -- rare: rows whose candidate set could not be bounded -> exact scan of the whole codebook ---------
-            const int n_ovf = *ovf_count;
+            const int n_ovf = *g_ocount;
 #ifdef VQ_TRACE
             if (wt == 0 && fr.trace != nullptr) {
                 fr.trace[(blockIdx.x * 8 + 6) * 64 + 34] += n_ovf;
-                fr.trace[(blockIdx.x * 8 + 6) * 64 + 35] += *pair_count;
+                fr.trace[(blockIdx.x * 8 + 6) * 64 + 35] += *g_pcount;
             }
 #endif
             for (int o = 0; o < n_ovf; ++o) {
-                const int r = s_ovf[o];
-                if (wt == 0) *ovf_key = ~0ull;
-                named_bar_sync(4, NW);
+                const int r = g_ovf[o];
+                if (wt == 0) *g_okey = ~0ull;
+                named_bar_sync(gbar, NW);
                 const float4* z4r = reinterpret_cast<const float4*>(fr.z + (row0 + r) * D);
                 const float a = ans[r];
                 unsigned long long key = ~0ull;
@@ -686,21 +706,21 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                         }
                     }
                 }
-                atomicMin(ovf_key, key);
-                named_bar_sync(4, NW);
-                if (wt == 0) s_idx[r] = static_cast<int>(*ovf_key & 0xffffffffu);
-                named_bar_sync(4, NW);
+                atomicMin(g_okey, key);
+                named_bar_sync(gbar, NW);
+                if (wt == 0) g_idx[r] = static_cast<int>(*g_okey & 0xffffffffu);
+                named_bar_sync(gbar, NW);
             }
             if (wt == 0) {
-                *ovf_count = 0;
-                *pair_count = 0;
+                *g_ocount = 0;
+                *g_pcount = 0;
                 spill_cnt[it & 3] = 0;
             }
-            named_bar_sync(4, NW);
+            named_bar_sync(gbar, NW);
             if (wt == 0) VQ_TR(5, 4 * it + 2);
             // -- indices, usage histogram -----------------------------------------------------------------------
             for (int r = wt; r < rows_here; r += NW) {
-                const int code = s_idx[r];
+                const int code = g_idx[r];
                 idx_out[row0 + r] = code;
                 atomicAdd(fr.hist + code, 1.0f);
             }
@@ -709,18 +729,16 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                 const float4* z4 = reinterpret_cast<const float4*>(fr.z + row0 * D);
                 float4* q4 = reinterpret_cast<float4*>(fr.q_out + row0 * D);
                 const int n_el = rows_here * DV;
-                constexpr int PER_T = (TC_ROWS * DV + 95) / 96;
                 constexpr int UB = 8;
 #pragma unroll 1
-                for (int ub = 0; ub < PER_T; ub += UB) {
-                    if (wt + ub * NW >= n_el) break;
+                for (int ub = 0; wt + ub * NW < n_el; ub += UB) {
                     float4 zv[UB], ev[UB];
 #pragma unroll
                     for (int u = 0; u < UB; ++u) {
                         const int e = wt + (ub + u) * NW;
                         if (e < n_el) {
                             zv[u] = __ldg(z4 + e);
-                            ev[u] = __ldg(reinterpret_cast<const float4*>(fr.E + static_cast<size_t>(s_idx[e / DV]) * D) + (e % DV));
+                            ev[u] = __ldg(reinterpret_cast<const float4*>(fr.E + static_cast<size_t>(g_idx[e / DV]) * D) + (e % DV));
                         }
                     }
 #pragma unroll
@@ -738,72 +756,72 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                     }
                 }
             }
-            named_bar_sync(4, NW);                       // everyone is done with s_idx and the handoff slot
+            named_bar_sync(gbar, NW);                       // everyone is done with g_idx and the handoff slot
             if (lane == 0) mbar_arrive(bar_idx_free + (it & 1));
             if (wt == 0) VQ_TR(5, 4 * it + 3);
         }
         if (have_oh) {
-            if (wt == 0) VQ_TR(6, 0);
-            patch_onehot_ones(fr.onehot, idx_out, N, K, pair, n_items, n_pairs, wt, NW,
+            if (wt_all == 0) VQ_TR(6, 0);
+            patch_onehot_ones(fr.onehot, idx_out, N, K, pair, n_items, n_pairs, wt_all, NW_all,
                               [&](int w) { return static_cast<long long>(2 * w + static_cast<int>(cta_rank)) * TC_ROWS; }, zeros_done);
         }
-        if (wt == 0) VQ_TR(6, 2);
+        if (wt_all == 0) VQ_TR(6, 2);
         // per-CTA SSE partial, then last-CTA-done reduction in a fixed order (+ loss / perplexity)
         const int wwarp = have_oh ? warp - 13 : warp - 12;
         double sd = warp_sum_d(static_cast<double>(sse));
         if (lane == 0) red[wwarp] = sd;
-        named_bar_sync(4, NW);
+        named_bar_sync(7, NW_all);
         volatile int* last_flag = reinterpret_cast<volatile int*>(red + 4);
-        if (wt == 0) {
+        if (wt_all == 0) {
             fr.partials[blockIdx.x] = red[0] + red[1] + red[2] + (have_oh ? 0.0 : red[3]);
             __threadfence();
             const unsigned int done = atomicAdd(fr.counter, 1u);
             *last_flag = (done == gridDim.x - 1) ? 1 : 0;
         }
-        named_bar_sync(4, NW);
+        named_bar_sync(7, NW_all);
         if (*last_flag) {
             __threadfence();
             double t = 0.0;
             {
                 const int g = static_cast<int>(gridDim.x);
-                const double p0 = wt < g ? __ldcg(fr.partials + wt) : 0.0;
-                const double p1 = wt + NW < g ? __ldcg(fr.partials + wt + NW) : 0.0;
+                const double p0 = wt_all < g ? __ldcg(fr.partials + wt_all) : 0.0;
+                const double p1 = wt_all + NW_all < g ? __ldcg(fr.partials + wt_all + NW_all) : 0.0;
                 t = p0 + p1;
-                for (int i = wt + 2 * NW; i < g; i += NW) t += __ldcg(fr.partials + i);
+                for (int i = wt_all + 2 * NW_all; i < g; i += NW_all) t += __ldcg(fr.partials + i);
             }
             t = warp_sum_d(t);
-            named_bar_sync(4, NW);
+            named_bar_sync(7, NW_all);
             if (lane == 0) red[wwarp] = t;
-            named_bar_sync(4, NW);
+            named_bar_sync(7, NW_all);
             const double total = red[0] + red[1] + red[2] + (have_oh ? 0.0 : red[3]);
-            if (wt == 0) {
+            if (wt_all == 0) {
                 *fr.sse_out = static_cast<float>(total);
                 *fr.counter = 0u;
             }
             if (fr.finalize) {
-                if (wt == 0 && quant) {
+                if (wt_all == 0 && quant) {
                     const float m = static_cast<float>(total / (static_cast<double>(N) * static_cast<double>(D)));
                     *fr.loss = __fadd_rn(m, __fmul_rn(fr.beta, m));
                 }
                 double ent = 0.0;
                 const float nf = static_cast<float>(N);
-                for (int kb = wt; kb < K; kb += 8 * NW) {      // 8 loads in flight: this runs on the kernel's critical tail
+                for (int kb = wt_all; kb < K; kb += 8 * NW_all) {      // 8 loads in flight: this runs on the kernel's critical tail
                     float h[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) h[u] = kb + u * NW < K ? __ldcg(fr.hist + kb + u * NW) : 0.0f;
+                    for (int u = 0; u < 8; ++u) h[u] = kb + u * NW_all < K ? __ldcg(fr.hist + kb + u * NW_all) : 0.0f;
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        if (kb + u * NW < K) {
+                        if (kb + u * NW_all < K) {
                             const float p = __fdiv_rn(h[u], nf);                     // vector_quantizer.py:55
                             ent += static_cast<double>(p * logf(p + 1e-10f));        // :56
                         }
                     }
                 }
                 ent = warp_sum_d(ent);
-                named_bar_sync(4, NW);
+                named_bar_sync(7, NW_all);
                 if (lane == 0) red[wwarp] = ent;
-                named_bar_sync(4, NW);
-                if (wt == 0) *fr.perplexity = expf(static_cast<float>(-(red[0] + red[1] + red[2] + (have_oh ? 0.0 : red[3]))));
+                named_bar_sync(7, NW_all);
+                if (wt_all == 0) *fr.perplexity = expf(static_cast<float>(-(red[0] + red[1] + red[2] + (have_oh ? 0.0 : red[3]))));
             }
         }
     }
