@@ -16,15 +16,21 @@ import torch
 import torch.nn as nn
 
 from . import _lib, parallel
-from ._lib import (FLAG_DEFER_STATS, FLAG_EXACT, FLAG_NO_QUANT, FLAG_ONEHOT, FLAG_STATE_READY, FLAG_TRAIN_VQ, check)
+from ._lib import (FLAG_DEFER_STATS, FLAG_EXACT, FLAG_NO_QUANT, FLAG_ONEHOT, FLAG_STATE_READY, FLAG_TRAIN_VQ, FLAG_ZERO_DE, check)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+def _stream(dev: Optional[torch.device] = None) -> int:
+    """Raw handle of the current CUDA stream (the fast accessor when this torch has it: this sits on the eager path)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device() if dev is None or dev.index is None else dev.index)
+    return torch.cuda.current_stream(dev).cuda_stream
 
 
 class _Buffers:
@@ -33,6 +39,7 @@ class _Buffers:
     def __init__(self):
         self.ws = None
         self.code = None     # (e_norm2, E_hi, E_lo)
+        self.ws_bytes = {}   # (N, K, D, flags) -> vq_workspace_bytes
 
     def workspace(self, nbytes: int, device) -> torch.Tensor:
         if self.ws is None or self.ws.numel() < nbytes or self.ws.device != device:
@@ -58,7 +65,7 @@ class _VQFunction(torch.autograd.Function):
         flat = inputs.view(-1, D)                     # vector_quantizer.py:32 (raises like the reference)
         N = flat.shape[0]
         dev = inputs.device
-        st = _stream()
+        st = _stream(dev)
         w = weight.detach()
         if not w.is_contiguous():
             w = w.contiguous()
@@ -71,7 +78,10 @@ class _VQFunction(torch.autograd.Function):
         perplexity = torch.empty((), dtype=torch.float32, device=dev)
         onehot = torch.empty(N, K, dtype=torch.float32, device=dev) if want_onehot else None
         fl = flags | (FLAG_ONEHOT if want_onehot else 0)
-        nbytes = lib.vq_workspace_bytes(N, K, D, fl)
+        key = (N, K, D, fl)
+        nbytes = bufs.ws_bytes.get(key)
+        if nbytes is None:
+            nbytes = bufs.ws_bytes[key] = lib.vq_workspace_bytes(N, K, D, fl)
         ws = bufs.workspace(nbytes, dev)
         sp = stats.data_ptr()
         # codebook norms, tf32 hi/lo split and the reset of hist / completion counter in ONE launch
@@ -91,7 +101,7 @@ class _VQFunction(torch.autograd.Function):
             ctx.mark_non_differentiable(perplexity, idx, onehot)
         else:
             ctx.mark_non_differentiable(perplexity, idx)
-        module._last_stats = stats
+        module.__dict__["_last_stats"] = stats      # plain attribute: skip nn.Module.__setattr__ on the eager path
         return loss, q_out, perplexity, onehot, idx
 
     @staticmethod
@@ -102,7 +112,7 @@ class _VQFunction(torch.autograd.Function):
         K, D = weight.shape
         N = idx.shape[0]
         dev = inputs.device
-        st = _stream()
+        st = _stream(dev)
         need_dz = ctx.needs_input_grad[0]
         need_dE = ctx.needs_input_grad[1] and ctx.train_vq
         if g_loss is None:
@@ -131,12 +141,12 @@ class _VQFunction(torch.autograd.Function):
                     packed.zero_()
                 dE = parallel.packed_views(packed, K, D)[0]
             else:
-                dE = torch.zeros(K, D, dtype=torch.float32, device=dev)
+                dE = torch.empty(K, D, dtype=torch.float32, device=dev)     # zeroed inside vq_backward (VQ_FLAG_ZERO_DE)
         dz = torch.empty_like(inputs)
         w = weight.detach()
         if not w.is_contiguous():
             w = w.contiguous()
-        flags = FLAG_TRAIN_VQ if need_dE else 0
+        flags = (FLAG_TRAIN_VQ | (FLAG_ZERO_DE if packed is None else 0)) if need_dE else 0
         check(lib.vq_backward(_ptr(g_q), _ptr(g_loss), _ptr(inputs), _ptr(w), _ptr(idx), N, max(N, 1),
                               max(N, 1) * world, K, D, float(module._commitment_cost), flags, _ptr(dz), _ptr(dE), st))
         if packed is not None:
@@ -144,10 +154,10 @@ class _VQFunction(torch.autograd.Function):
             if push is not None:
                 reduced = push.reduce(st)
                 dE = reduced[:K * D].view(K, D).clone()       # `reduced` is reused by the next step
-                module._global_stats = (reduced[K * D:].clone(), N * world)
+                module.__dict__["_global_stats"] = (reduced[K * D:].clone(), N * world)
             else:
                 parallel.all_reduce_packed(packed, pg)
-                module._global_stats = (packed[K * D:], N * world)
+                module.__dict__["_global_stats"] = (packed[K * D:], N * world)
         return (dz if need_dz else None), dE, None, None, None
 
 
@@ -157,9 +167,10 @@ class VectorQuantizer(nn.Module):
     Extra keyword-only options (defaults reproduce the reference exactly):
       return_encodings  False skips the dense (N, K) one-hot (4 K bytes per row of HBM traffic);
                         the 4th return value is then None.  `last_indices` always holds the codes.
-      exact             True computes distances on CUDA cores in the oracle's fp32 FMA-chain order
-                        (bit-exact indices vs oracle/vq_oracle.c); False (default) uses the tcgen05
-                        3xTF32 tensor-core path whenever the shape allows (D in {32,64,96,128}, K % 128 == 0).
+      exact             True computes every distance on CUDA cores in the oracle's fp32 FMA-chain order; False
+                        (default) uses the tcgen05 path whenever the shape allows: one TF32 screening pass plus an
+                        exact fp32 refine of the candidates (K % 256 == 0, D in {32,64,96,128,192,256}; indices
+                        bit-exact vs oracle/vq_oracle.c), else 3xTF32 (K % 128 == 0, D in {32,64,96,128}).
       process_group     set (or `data_parallel=True` for the default group) to all-reduce the packed
                         [dE | usage histogram | squared error] once per step across data-parallel ranks.
     """
@@ -225,9 +236,14 @@ class VectorQuantizer(nn.Module):
             raise RuntimeError("view size is not compatible with input tensor's size and stride "
                                "(b200vq needs a contiguous input, like the reference's .view)")
         flags = FLAG_EXACT if self.exact else 0
-        loss, quantized, perplexity, encodings, idx = _VQFunction.apply(
-            inputs, weight, self, flags, bool(self.return_encodings))
-        self.last_indices = idx
+        if inputs.device.index != torch.cuda.current_device():      # the C ABI launches on the current device
+            with torch.cuda.device(inputs.device):
+                loss, quantized, perplexity, encodings, idx = _VQFunction.apply(
+                    inputs, weight, self, flags, bool(self.return_encodings))
+        else:
+            loss, quantized, perplexity, encodings, idx = _VQFunction.apply(
+                inputs, weight, self, flags, bool(self.return_encodings))
+        self.__dict__["last_indices"] = idx
         return loss, quantized, perplexity, encodings
 
     def _push_allreduce(self, K, D, dev, pg):
