@@ -156,7 +156,8 @@ def _oracle_idx(z, E):
     return torch.from_numpy(c_oracle.argmin(z.cpu().numpy(), E.cpu().numpy()))
 
 
-ADVERSARIAL = ["duplicates", "clustered", "rows_are_codes", "huge_scale", "tiny_scale", "one_dominant_code", "few_rows", "constant_rows"]
+ADVERSARIAL = ["duplicates", "clustered", "rows_are_codes", "huge_scale", "tiny_scale", "one_dominant_code", "few_rows", "constant_rows",
+               "six_copies", "hidden_pairs"]
 
 
 @pytest.mark.parametrize("kind", ADVERSARIAL)
@@ -186,6 +187,19 @@ def test_screen_kernel_adversarial_inputs(lib, kind, D, K):
         E[17] *= 50.0                                   # inflates max|E_k| and with it every row's margin
     elif kind == "constant_rows":
         z[:] = z[0]
+    elif kind == "six_copies":
+        # six identical codewords spread over tiles and column halves: 6 exact ties per nearby row, more than the 4-entry
+        # candidate log and handoff hold -> the global spill list; the lowest index must win
+        copies = [(3 + j * (K // 6 + 1)) % K for j in range(6)]
+        E[copies] = E[copies[0]].clone()
+        z[:300] = E[copies[0]] + 1e-3 * torch.randn(300, D, generator=g)
+    elif kind == "hidden_pairs":
+        # two chain-instances (same tile half, columns equal mod 4) that each hide a second tied codeword behind their
+        # best: the second place to look goes through the spill list
+        E[7] = E[3].clone()
+        hi = K // 2 + 88
+        E[hi] = E[3].clone(); E[hi + 4] = E[3].clone()
+        z[:300] = E[3] + 1e-3 * torch.randn(300, D, generator=g)
     E, z = E.contiguous().to(dev), z.contiguous().to(dev)
     out = _forward(lib, z, E, 1 << 10)                  # VQ_FLAG_SCREEN
     ref = _oracle_idx(z, E)
