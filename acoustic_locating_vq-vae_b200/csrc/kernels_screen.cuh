@@ -767,63 +767,7 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
         }
         if (wt_all == 0) VQ_TR(6, 2);
         // per-CTA SSE partial, then last-CTA-done reduction in a fixed order (+ loss / perplexity)
-        const int wwarp = have_oh ? warp - 13 : warp - 12;
-        double sd = warp_sum_d(static_cast<double>(sse));
-        if (lane == 0) red[wwarp] = sd;
-        named_bar_sync(7, NW_all);
-        volatile int* last_flag = reinterpret_cast<volatile int*>(red + 4);
-        if (wt_all == 0) {
-            fr.partials[blockIdx.x] = red[0] + red[1] + red[2] + (have_oh ? 0.0 : red[3]);
-            __threadfence();
-            const unsigned int done = atomicAdd(fr.counter, 1u);
-            *last_flag = (done == gridDim.x - 1) ? 1 : 0;
-        }
-        named_bar_sync(7, NW_all);
-        if (*last_flag) {
-            __threadfence();
-            double t = 0.0;
-            {
-                const int g = static_cast<int>(gridDim.x);
-                const double p0 = wt_all < g ? __ldcg(fr.partials + wt_all) : 0.0;
-                const double p1 = wt_all + NW_all < g ? __ldcg(fr.partials + wt_all + NW_all) : 0.0;
-                t = p0 + p1;
-                for (int i = wt_all + 2 * NW_all; i < g; i += NW_all) t += __ldcg(fr.partials + i);
-            }
-            t = warp_sum_d(t);
-            named_bar_sync(7, NW_all);
-            if (lane == 0) red[wwarp] = t;
-            named_bar_sync(7, NW_all);
-            const double total = red[0] + red[1] + red[2] + (have_oh ? 0.0 : red[3]);
-            if (wt_all == 0) {
-                *fr.sse_out = static_cast<float>(total);
-                *fr.counter = 0u;
-            }
-            if (fr.finalize) {
-                if (wt_all == 0 && quant) {
-                    const float m = static_cast<float>(total / (static_cast<double>(N) * static_cast<double>(D)));
-                    *fr.loss = __fadd_rn(m, __fmul_rn(fr.beta, m));
-                }
-                double ent = 0.0;
-                const float nf = static_cast<float>(N);
-                for (int kb = wt_all; kb < K; kb += 8 * NW_all) {      // 8 loads in flight: this runs on the kernel's critical tail
-                    float h[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) h[u] = kb + u * NW_all < K ? __ldcg(fr.hist + kb + u * NW_all) : 0.0f;
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        if (kb + u * NW_all < K) {
-                            const float p = __fdiv_rn(h[u], nf);                     // vector_quantizer.py:55
-                            ent += static_cast<double>(p * logf(p + 1e-10f));        // :56
-                        }
-                    }
-                }
-                ent = warp_sum_d(ent);
-                named_bar_sync(7, NW_all);
-                if (lane == 0) red[wwarp] = ent;
-                named_bar_sync(7, NW_all);
-                if (wt_all == 0) *fr.perplexity = expf(static_cast<float>(-(red[0] + red[1] + red[2] + (have_oh ? 0.0 : red[3]))));
-            }
-        }
+        publish_and_finalize(fr, sse, N, K, D, wt_all, NW_all, lane, have_oh ? warp - 13 : warp - 12, have_oh ? 3 : 4, red, 7);
     }
 
     if (threadIdx.x == 0) VQ_TR(7, 1);

@@ -352,6 +352,76 @@ __device__ __forceinline__ void patch_onehot_ones(float* __restrict__ onehot, co
     }
 }
 
+// Per-CTA SSE partial, then the last CTA to finish reduces all partials in a fixed order and writes SSE, loss
+// (vector_quantizer.py:46-52) and perplexity (:55-56).  Called by all `nw` row-worker threads of a CTA (named barrier
+// `bar_id`); `red` is 5 doubles of shared scratch.  This is the tail of the kernel's critical path: the partials and
+// the first 12 histogram entries per thread are fetched in ONE round trip, later batches 12 at a time.
+__device__ __forceinline__ void publish_and_finalize(const FusedRowArgs& fr, float sse, long long N, int K, int D, int wt, int nw,
+                                                     int lane, int wwarp, int n_warps, double* red, int bar_id) {
+    auto red_total = [&]() {
+        double t = red[0];
+        for (int i = 1; i < n_warps; ++i) t += red[i];
+        return t;
+    };
+    const double sd = warp_sum_d(static_cast<double>(sse));
+    if (lane == 0) red[wwarp] = sd;
+    named_bar_sync(bar_id, nw);
+    volatile int* last_flag = reinterpret_cast<volatile int*>(red + 4);
+    if (wt == 0) {
+        fr.partials[blockIdx.x] = red_total();
+        __threadfence();
+        const unsigned int done = atomicAdd(fr.counter, 1u);
+        *last_flag = (done == gridDim.x - 1) ? 1 : 0;
+    }
+    named_bar_sync(bar_id, nw);
+    if (!*last_flag) return;
+    __threadfence();
+    constexpr int HB = 12;
+    const int g = static_cast<int>(gridDim.x);
+    const bool fin = fr.finalize != 0;
+    const double p0 = wt < g ? __ldcg(fr.partials + wt) : 0.0;
+    const double p1 = wt + nw < g ? __ldcg(fr.partials + wt + nw) : 0.0;
+    float h[HB];
+#pragma unroll
+    for (int u = 0; u < HB; ++u) h[u] = (fin && wt + u * nw < K) ? __ldcg(fr.hist + wt + u * nw) : 0.0f;
+    double t = p0 + p1;
+    for (int i = wt + 2 * nw; i < g; i += nw) t += __ldcg(fr.partials + i);
+    t = warp_sum_d(t);
+    named_bar_sync(bar_id, nw);
+    if (lane == 0) red[wwarp] = t;
+    named_bar_sync(bar_id, nw);
+    const double total = red_total();
+    if (wt == 0) {
+        *fr.sse_out = static_cast<float>(total);
+        *fr.counter = 0u;
+    }
+    if (!fin) return;
+    if (wt == 0 && fr.q_out != nullptr) {
+        const float m = static_cast<float>(total / (static_cast<double>(N) * static_cast<double>(D)));
+        *fr.loss = __fadd_rn(m, __fmul_rn(fr.beta, m));                      // vector_quantizer.py:52
+    }
+    double ent = 0.0;
+    const float nf = static_cast<float>(N);
+    for (int kb = wt; kb < K; kb += HB * nw) {
+        if (kb != wt) {
+#pragma unroll
+            for (int u = 0; u < HB; ++u) h[u] = kb + u * nw < K ? __ldcg(fr.hist + kb + u * nw) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < HB; ++u) {
+            if (kb + u * nw < K) {
+                const float p = __fdiv_rn(h[u], nf);                         // vector_quantizer.py:55
+                ent += static_cast<double>(p * logf(p + 1e-10f));            // :56
+            }
+        }
+    }
+    ent = warp_sum_d(ent);
+    named_bar_sync(bar_id, nw);
+    if (lane == 0) red[wwarp] = ent;
+    named_bar_sync(bar_id, nw);
+    if (wt == 0) *fr.perplexity = expf(static_cast<float>(-red_total()));
+}
+
 #ifdef VQ_TRACE
 #define VQ_TR(role, slot)                                                                              \
     do {                                                                                               \
@@ -803,63 +873,7 @@ argmin_tc2_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constan
             if (wt == 0) VQ_TR(5, 60);
         }
         // per-CTA SSE partial, then last-CTA-done reduction in a fixed order (+ loss / perplexity)
-        const int wwarp = have_oh ? warp - 13 : warp - 12;
-        double sd = warp_sum_d(static_cast<double>(sse));
-        if (lane == 0) red[wwarp] = sd;
-        named_bar_sync(4, NW);
-        volatile int* last_flag = reinterpret_cast<volatile int*>(red + 4);
-        if (wt == 0) {
-            fr.partials[blockIdx.x] = red[0] + red[1] + red[2] + (have_oh ? 0.0 : red[3]);
-            __threadfence();
-            const unsigned int done = atomicAdd(fr.counter, 1u);
-            *last_flag = (done == gridDim.x - 1) ? 1 : 0;
-        }
-        named_bar_sync(4, NW);
-        if (*last_flag) {
-            __threadfence();
-            double t = 0.0;
-            {
-                const int g = static_cast<int>(gridDim.x);
-                const double p0 = wt < g ? __ldcg(fr.partials + wt) : 0.0;
-                const double p1 = wt + NW < g ? __ldcg(fr.partials + wt + NW) : 0.0;
-                t = p0 + p1;
-                for (int i = wt + 2 * NW; i < g; i += NW) t += __ldcg(fr.partials + i);
-            }
-            t = warp_sum_d(t);
-            named_bar_sync(4, NW);
-            if (lane == 0) red[wwarp] = t;
-            named_bar_sync(4, NW);
-            const double total = red[0] + red[1] + red[2] + (have_oh ? 0.0 : red[3]);
-            if (wt == 0) {
-                *fr.sse_out = static_cast<float>(total);
-                *fr.counter = 0u;
-            }
-            if (fr.finalize) {
-                if (wt == 0) {
-                    const float m = static_cast<float>(total / (static_cast<double>(N) * static_cast<double>(D)));
-                    *fr.loss = __fadd_rn(m, __fmul_rn(fr.beta, m));   // vector_quantizer.py:52
-                }
-                double ent = 0.0;
-                const float nf = static_cast<float>(N);
-                for (int kb = wt; kb < K; kb += 8 * NW) {      // 8 loads in flight: this runs on the kernel's critical tail
-                    float h[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) h[u] = kb + u * NW < K ? __ldcg(fr.hist + kb + u * NW) : 0.0f;
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        if (kb + u * NW < K) {
-                            const float p = __fdiv_rn(h[u], nf);                     // vector_quantizer.py:55
-                            ent += static_cast<double>(p * logf(p + 1e-10f));        // :56
-                        }
-                    }
-                }
-                ent = warp_sum_d(ent);
-                named_bar_sync(4, NW);
-                if (lane == 0) red[wwarp] = ent;
-                named_bar_sync(4, NW);
-                if (wt == 0) *fr.perplexity = expf(static_cast<float>(-(red[0] + red[1] + red[2] + (have_oh ? 0.0 : red[3]))));
-            }
-        }
+        publish_and_finalize(fr, sse, N, K, D, wt, NW, lane, have_oh ? warp - 13 : warp - 12, have_oh ? 3 : 4, red, 4);
     }
 
     if (threadIdx.x == 0) VQ_TR(7, 1);
