@@ -9,7 +9,7 @@ import os
 
 from .build import SO_PATH
 
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 FLAG_ONEHOT = 1 << 0
 FLAG_TRAIN_VQ = 1 << 1
@@ -53,6 +53,8 @@ SIGNATURES = {
     "vq_jitter_backward": (_int, [_vp, _vp, _i64, _int, _vp]),
     "vq_allreduce_sum": (_int, [ctypes.POINTER(_vp), _int, _int, _i64, _i64, ctypes.c_uint32, _vp, _vp]),
     "vq_allreduce_push": (_int, [ctypes.POINTER(_vp), _vp, _int, _int, _vp, _i64, ctypes.c_uint32, _vp, _vp]),
+    "vq_backward_allreduce": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _i64,
+                                     ctypes.POINTER(_vp), _vp, _int, _int, ctypes.c_uint32, _vp, _vp, _vp]),
     "vq_host_ctx_create": (_int, [_i64, _int, _int, ctypes.POINTER(_vp)]),
     "vq_host_ctx_destroy": (None, [_vp]),
     "vq_host_set_codebook": (_int, [_vp, _vp]),

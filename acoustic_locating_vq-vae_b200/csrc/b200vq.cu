@@ -639,10 +639,73 @@ int vq_allreduce_push(const void* const* recv_buffers, void* multicast_or_null, 
     long long blocks = (lines + 255) / 256;
     if (blocks > kNumSMs) blocks = kNumSMs;
     ProfScope prof(KID_ALLREDUCE, st);
-    cudaError_t e = launch_pdl(allreduce_push_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, pb,
-                               static_cast<float*>(multicast_or_null), world, rank, lines, payload, static_cast<long long>(n_floats), seq, out);
+    // one step (every payload to every rank) up to 3 ranks; reduce-scatter + all-gather from 4 ranks on, where the
+    // world x payload that one step lands in every rank costs more than a second NVLink latency
+    // (B200VQ_AR_ALGO=1|2 forces either; both fit the same world x lines receive buffers)
+    static const int forced = [] { const char* e = getenv("B200VQ_AR_ALGO"); return e == nullptr ? 0 : atoi(e); }();
+    const long long S = (lines + world - 1) / world;
+    const bool two_step = world >= 2 && 2 * S <= lines + 2 && (forced == 2 || (forced != 1 && world >= 4));   // always true: see the header
+    cudaError_t e;
+    if (two_step)
+        e = launch_pdl(allreduce_push2_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, pb,
+                       static_cast<float*>(multicast_or_null), world, rank, lines, S, payload, static_cast<long long>(n_floats), seq, out);
+    else
+        e = launch_pdl(allreduce_push_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, pb,
+                       static_cast<float*>(multicast_or_null), world, rank, lines, payload, static_cast<long long>(n_floats), seq, out);
     if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of allreduce_push_kernel failed: %s", cudaGetErrorString(e));
     LAUNCH_CHECK("allreduce_push_kernel");
+    return VQ_OK;
+}
+
+// backward + all-reduce fused (see backward_allreduce_kernel): the transfer overlaps the dz pass.
+int vq_backward_allreduce(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx,
+                          int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags, float* dz,
+                          float* payload, int64_t n_floats, const void* const* recv_buffers, void* multicast_or_null,
+                          int world, int rank, uint32_t seq, uint32_t* grid_sync, float* out, vq_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    const long long N = n_rows;
+    if (z == nullptr || E == nullptr || idx == nullptr || dz == nullptr || payload == nullptr || out == nullptr ||
+        grid_sync == nullptr || recv_buffers == nullptr || K < 1 || D < 4 || D % 4 != 0 || N < 1 || n_rows_dz < 1 || n_rows_dE < 1 ||
+        world < 2 || world > AR_MAX_RANKS || rank < 0 || rank >= world || seq == 0 ||
+        n_floats < static_cast<int64_t>(K) * D || !(flags & VQ_FLAG_TRAIN_VQ))
+        return fail(VQ_ERR_ARG, "vq_backward_allreduce: bad argument (N=%lld K=%d D=%d world=%d rank=%d seq=%u flags=%d)", N, K, D, world,
+                    rank, seq, flags);
+    if (!aligned16(z) || !aligned16(dz) || !aligned16(payload) || !aligned16(E) || (g_q != nullptr && !aligned16(g_q)))
+        return fail(VQ_ERR_ARG, "vq_backward_allreduce: z / g_q / dz / E / payload must be 16-byte aligned");
+    PeerBuffers pb{};
+    for (int p = 0; p < world; ++p) {
+        if (recv_buffers[p] == nullptr || !aligned16(recv_buffers[p])) return fail(VQ_ERR_ARG, "vq_backward_allreduce: receive buffer %d is NULL or misaligned", p);
+        pb.buf[p] = static_cast<float*>(const_cast<void*>(recv_buffers[p]));
+    }
+    const long long lines = (n_floats + 1) / 2;
+    const long long S = (lines + world - 1) / world;
+    if (2 * S > lines + 2) return fail(VQ_ERR_ARG, "vq_backward_allreduce: payload too small for the two-step exchange");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float denom_dz = static_cast<float>(static_cast<double>(n_rows_dz) * static_cast<double>(D));
+    const float denom_dE = static_cast<float>(static_cast<double>(n_rows_dE) * static_cast<double>(D));
+    const long long n_el = N * (D / 4);
+    // persistent and fully resident: the kernel has a grid barrier (and the all-reduce must not wait on unscheduled CTAs)
+    static const int occ = [] {
+        int a = 0, b = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, backward_allreduce_kernel<true>, 256, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, backward_allreduce_kernel<false>, 256, 0);
+        const int o = a < b ? a : b;
+        return o < 1 ? 1 : (o > 4 ? 4 : o);
+    }();
+    long long g = (n_el + 255) / 256;
+    if (g > static_cast<long long>(kNumSMs) * occ) g = static_cast<long long>(kNumSMs) * occ;
+    ProfScope prof(KID_BACKWARD, st);
+    cudaError_t e;
+    if (g_q != nullptr)
+        e = launch_pdl(backward_allreduce_kernel<true>, dim3(static_cast<unsigned>(g)), dim3(256), 0, st, g_q, g_loss, z, E, idx, N, denom_dz,
+                       denom_dE, D, beta, dz, payload, static_cast<long long>(n_floats), pb, static_cast<float*>(multicast_or_null), world, rank,
+                       lines, S, seq, grid_sync, out);
+    else
+        e = launch_pdl(backward_allreduce_kernel<false>, dim3(static_cast<unsigned>(g)), dim3(256), 0, st, g_q, g_loss, z, E, idx, N, denom_dz,
+                       denom_dE, D, beta, dz, payload, static_cast<long long>(n_floats), pb, static_cast<float*>(multicast_or_null), world, rank,
+                       lines, S, seq, grid_sync, out);
+    if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of backward_allreduce_kernel failed: %s", cudaGetErrorString(e));
+    LAUNCH_CHECK("backward_allreduce_kernel");
     return VQ_OK;
 }
 

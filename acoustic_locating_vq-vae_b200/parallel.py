@@ -142,7 +142,7 @@ class PushAllReduce:
         self.bufs, self.ptr_arrays, self.mc_ptrs = [], [], []
         use_mc = os.environ.get("B200VQ_NVLS", "1") != "0"
         for _ in range(2):
-            t = symm_mem.empty(self.world * lines * 4, dtype=torch.float32, device=device)
+            t = symm_mem.empty(self.world * (lines + 2) * 4, dtype=torch.float32, device=device)   # include/b200vq.h: world x (lines + 2) lines
             t.zero_()
             hdl = symm_mem.rendezvous(t, self.group)
             self.bufs.append(t)
@@ -156,15 +156,31 @@ class PushAllReduce:
         dist.barrier(self.group)                      # zero-initialised receive buffers are in place everywhere
         self.payload_buf = torch.zeros(n_floats, dtype=torch.float32, device=device)
         self.out = torch.zeros(n_floats, dtype=torch.float32, device=device)
+        self.grid_sync = torch.zeros(2, dtype=torch.int32, device=device)     # grid barrier of the fused backward kernel
         self.seq = 0
 
     def payload(self) -> torch.Tensor:
         return self.payload_buf
 
-    def reduce(self, stream_ptr: int) -> torch.Tensor:
+    def _next(self):
         which = self.seq & 1
         self.seq += 1
-        seq_no = (self.seq + 1) // 2                  # 1, 1, 2, 2, ...: per-buffer sequence number (never 0)
+        return which, (self.seq + 1) // 2             # 1, 1, 2, 2, ...: per-buffer sequence number (never 0)
+
+    def backward_reduce(self, g_q_ptr, g_loss_ptr, z_ptr, E_ptr, idx_ptr, n_rows: int, n_rows_dE: int, K: int, D: int,
+                        beta: float, flags: int, dz_ptr: int, stream_ptr: int) -> torch.Tensor:
+        """vq_backward + all-reduce in one kernel (vq_backward_allreduce): dE accumulates into payload()[:K*D] (which the
+        caller has zeroed, with the histogram / squared error already behind it) and the NVLink exchange overlaps the
+        dz pass.  Returns the reduced buffer, like reduce()."""
+        which, seq_no = self._next()
+        self.check(self.lib.vq_backward_allreduce(g_q_ptr, g_loss_ptr, z_ptr, E_ptr, idx_ptr, n_rows, max(n_rows, 1), n_rows_dE,
+                                                  K, D, beta, flags, dz_ptr, self.payload_buf.data_ptr(), self.n,
+                                                  self.ptr_arrays[which], self.mc_ptrs[which], self.world, self.rank, seq_no,
+                                                  self.grid_sync.data_ptr(), self.out.data_ptr(), stream_ptr))
+        return self.out
+
+    def reduce(self, stream_ptr: int) -> torch.Tensor:
+        which, seq_no = self._next()
         self.check(self.lib.vq_allreduce_push(self.ptr_arrays[which], self.mc_ptrs[which], self.world, self.rank,
                                               self.payload_buf.data_ptr(), self.n, seq_no, self.out.data_ptr(), stream_ptr))
         return self.out

@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--no-fuse", action="store_true", help="argmin and row epilogue as two kernels (VQ_FLAG_NO_FUSE)")
     ap.add_argument("--no-screen", action="store_true", help="3xTF32 tensor kernels instead of screen + exact refine (VQ_FLAG_NO_SCREEN)")
     ap.add_argument("--screen", action="store_true", help="force screen + exact refine (VQ_FLAG_SCREEN)")
+    ap.add_argument("--fused-allreduce", action="store_true", help="N > 1: vq_backward_allreduce (one kernel, exchange overlaps the dz pass; measured slower) instead of vq_backward + vq_allreduce_push")
     ap.add_argument("--nccl", action="store_true", help="N > 1: use NCCL for the per-step all-reduce instead of vq_allreduce_sum")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -249,6 +250,9 @@ def main():
             collective = f"NCCL all_reduce (symmetric memory unavailable: {type(e).__name__})"
     elif world > 1:
         collective = "NCCL all_reduce"
+    fused_ar = sym is not None and D % 4 == 0 and args.fused_allreduce
+    if fused_ar:
+        collective = "backward + two-step push all-reduce fused in one kernel (vq_backward_allreduce, " + ("NVLS multimem.st" if sym.nvls else "P2P stores") + ")"
     packs = [sym.payload()] if sym is not None else [torch.zeros(n_packed, device=dev)]
     views = [(pk[:K * D], pk[K * D:K * D + K], pk[K * D + K:]) for pk in packs]
     scal = torch.empty(2, device=dev)                                 # loss, perplexity
@@ -270,6 +274,10 @@ def main():
         L.check(lib.vq_prepare_step(P(E), K, D, P(e2), P(ehi), P(elo), P(hist), P(ws), wsb, P(dE), st))
         L.check(lib.vq_forward(P(z), P(E), P(e2), P(ehi), P(elo), N, K, D, BETA, fwd_flags, P(q), P(idx), P(onehot),
                                P(hist), P(sse), scal.data_ptr(), scal.data_ptr() + 4, P(ws), wsb, st))
+        if fused_ar:
+            # backward + all-reduce in ONE kernel: the NVLink exchange overlaps the dz pass; result in sym.out
+            sym.backward_reduce(P(gs[i % nbuf]), P(g_loss), P(z), P(E), P(idx), N, n_dE, K, D, BETA, bwd_flags, P(dz), st)
+            return
         L.check(lib.vq_backward(P(gs[i % nbuf]), P(g_loss), P(z), P(E), P(idx), N, N, n_dE, K, D, BETA, bwd_flags,
                                 P(dz), P(dE), st))
         if sym is not None:

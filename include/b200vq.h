@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VQ_ABI_VERSION 15
+#define VQ_ABI_VERSION 16
 
 /* error codes */
 #define VQ_OK            0
@@ -146,13 +146,28 @@ int vq_jitter_backward(float* g, const int32_t* src, int64_t rows, int T, vq_str
 int vq_allreduce_sum(const void* const* peer_buffers, int world, int rank, int64_t flag_offset_floats,
                      int64_t n_floats, uint32_t seq, float* out, vq_stream_t stream);
 
-/* Push ("low-latency") variant: one NVLink one-way latency, no barrier.  recv_buffers[p] = rank p's symmetric
- * RECEIVE buffer as mapped into this process: `world` slots of ceil(n_floats/2) 16-byte lines {d0, seq, d1, seq},
- * zero-initialised.  Every rank stores its payload into slot [rank] of every receive buffer, then polls its own
- * slots until all lines carry `seq` and sums them in rank order.  `seq` >= 1 and increases by one per call on a
- * given buffer; callers alternate between TWO receive buffers. */
+/* Push ("low-latency") variant: no barrier.  recv_buffers[p] = rank p's symmetric RECEIVE buffer as mapped into this
+ * process: at least world x (ceil(n_floats/2) + 2) 16-byte lines {d0, seq, d1, seq}, zero-initialised.
+ *   up to 3 ranks: every rank stores its payload into slot [rank] of every receive buffer, then polls its own slots
+ *     until all lines carry `seq` and sums them in rank order (one NVLink one-way latency);
+ *   from 4 ranks: reduce-scatter + all-gather through the same buffers (rank j owns slice j: two latencies, but only
+ *     2 x payload instead of world x payload lands in every rank).  B200VQ_AR_ALGO=1|2 forces either.
+ * Results are bit-identical on every rank and between the two algorithms.  `seq` >= 1 and increases by one per call
+ * on a given buffer; callers alternate between TWO receive buffers. */
 int vq_allreduce_push(const void* const* recv_buffers, void* multicast_or_null, int world, int rank,
                       const float* payload, int64_t n_floats, uint32_t seq, float* out, vq_stream_t stream);
+
+/* Backward and the data-parallel all-reduce of the packed step buffer in ONE persistent kernel: the NVLink transfer
+ * overlaps the dz pass (replaces vq_backward + vq_allreduce_push; the reference has no counterpart -- DDP would
+ * all-reduce `_embedding.weight.grad` after backward).  `payload` = [dE (K*D, zeroed by the caller, e.g. by
+ * vq_prepare_step) | extra floats (usage histogram, squared error) already in place], n_floats in total; it is reduced
+ * into `out` on every rank, bit-identically.  Needs VQ_FLAG_TRAIN_VQ, D % 4 == 0, 16-byte aligned z / g_q / dz /
+ * payload, world >= 2.  `grid_sync`: two zero-initialised uint32 in device memory owned by the caller and used by no
+ * other stream.  recv_buffers / multicast_or_null / seq: as for vq_allreduce_push. */
+int vq_backward_allreduce(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx,
+                          int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags, float* dz,
+                          float* payload, int64_t n_floats, const void* const* recv_buffers, void* multicast_or_null,
+                          int world, int rank, uint32_t seq, uint32_t* grid_sync, float* out, vq_stream_t stream);
 /* multicast_or_null: the NVLS multicast mapping of the same receive buffer (torch symmetric memory's
  * `multicast_ptr`); when given, each line is sent with ONE multimem.st that the NVSwitch replicates to all ranks. */
 
