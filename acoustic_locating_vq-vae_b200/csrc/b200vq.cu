@@ -146,7 +146,7 @@ bool tensor_path_ok(long long N, int K, int D, int flags, const float* z = nullp
     if (D % TC_SLAB_FLOATS != 0 || D < 32 || D > 256) return false;
     if (K % TC_CODES != 0 || K < TC_CODES) return false;
     // D in (128, 256] (and D = 160, 224) only fits the screen+refine kernel (tf32(z) alone in shared memory)
-    const bool screen_shape = (K % TC2_CODES == 0) && (D <= 128 || D == 192 || D == 256) && !(flags & VQ_FLAG_NO_SCREEN) &&
+    const bool screen_shape = (K % TC2_CODES == 0) && K <= (1 << 20) && (D <= 128 || D == 192 || D == 256) && !(flags & VQ_FLAG_NO_SCREEN) &&
                               !(flags & VQ_FLAG_NO_FUSE) && !(flags & VQ_FLAG_TC_1CTA);
     if (D > 128 && !screen_shape) return false;
     if (check_ptrs && (ehi == nullptr || elo == nullptr || !aligned16(z) || !aligned16(ehi) || !aligned16(elo))) return false;
@@ -406,7 +406,8 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
         // Indices are bit-identical to the fp32 oracle, and it is the faster kernel everywhere on B200 (RIR-256 with the
         // dense one-hot: 69.0 vs 69.6 us per step; 1.5x at D = 64 and 2x at D = 128 without the one-hot); D > 128 only
         // fits this kernel.  VQ_FLAG_NO_SCREEN / B200VQ_SCREEN=0 select the 3xTF32 kernel, VQ_FLAG_SCREEN forces this one.
-        const bool screen_shape = (K % TC2_CODES == 0) && (D <= 128 || D == 192 || D == 256) && aligned16(E) &&
+        const bool screen_shape = (K % TC2_CODES == 0) && K <= (1 << 20) /* (row, code) pairs pack the code into 20 bits */ &&
+                                  (D <= 128 || D == 192 || D == 256) && aligned16(E) &&
                                   (!quant || aligned16(q_out)) && (!want_onehot || aligned16(onehot)) &&
                                   !(flags & (VQ_FLAG_NO_SCREEN | VQ_FLAG_NO_FUSE | VQ_FLAG_TC_1CTA));
         const bool screen = screen_shape && ((flags & VQ_FLAG_SCREEN) || screen_enabled());
