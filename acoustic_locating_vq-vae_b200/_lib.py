@@ -17,6 +17,7 @@ FLAG_EXACT = 1 << 2
 FLAG_DEFER_STATS = 1 << 3
 FLAG_NO_QUANT = 1 << 4
 FLAG_ZERO_DE = 1 << 5
+FLAG_NO_DZ = 1 << 11
 FLAG_TC_1CTA = 1 << 6
 FLAG_NO_FUSE = 1 << 7
 FLAG_STATE_READY = 1 << 8

@@ -560,8 +560,9 @@ int vq_backward(const float* g_q, const float* g_loss, const float* z, const flo
     if (int rc = check_device()) return rc;
     const long long N = n_rows;
     const bool train = (flags & VQ_FLAG_TRAIN_VQ) != 0 && dE != nullptr;
-    if (z == nullptr || E == nullptr || idx == nullptr || dz == nullptr || K < 1 || D < 1 || N < 0 || n_rows_dz < 1 ||
-        n_rows_dE < 1)
+    const bool no_dz = (flags & VQ_FLAG_NO_DZ) != 0;
+    if (z == nullptr || E == nullptr || idx == nullptr || (dz == nullptr && !no_dz) || K < 1 || D < 1 || N < 0 || n_rows_dz < 1 ||
+        n_rows_dE < 1 || (no_dz && !train))
         return fail(VQ_ERR_ARG, "vq_backward: bad argument");
     if (N == 0) {
         if (train && (flags & VQ_FLAG_ZERO_DE)) CUDA_TRY(cudaMemsetAsync(dE, 0, sizeof(float) * static_cast<size_t>(K) * D, static_cast<cudaStream_t>(stream)));
@@ -573,6 +574,18 @@ int vq_backward(const float* g_q, const float* g_loss, const float* z, const flo
                      (!train || aligned16(dE));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (train && (flags & VQ_FLAG_ZERO_DE)) CUDA_TRY(cudaMemsetAsync(dE, 0, sizeof(float) * static_cast<size_t>(K) * D, st));
+    if (no_dz) {   // codebook gradient only (data parallel: its all-reduce then overlaps the dz pass)
+        const bool v4 = (D % 4 == 0) && aligned16(z) && aligned16(E) && aligned16(dE);
+        const long long n_e = N * (v4 ? D / 4 : D);
+        long long gb = (n_e + 255) / 256;
+        if (gb > kNumSMs * 32) gb = kNumSMs * 32;
+        ProfScope prof(KID_BACKWARD, st);
+        cudaError_t e = v4 ? launch_pdl(backward_dE_kernel<4>, dim3(static_cast<unsigned>(gb)), dim3(256), 0, st, g_loss, z, E, idx, N, denom_dE, D, dE)
+                           : launch_pdl(backward_dE_kernel<1>, dim3(static_cast<unsigned>(gb)), dim3(256), 0, st, g_loss, z, E, idx, N, denom_dE, D, dE);
+        if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of backward_dE_kernel failed: %s", cudaGetErrorString(e));
+        LAUNCH_CHECK("backward_dE_kernel");
+        return VQ_OK;
+    }
     const long long n_el = N * (vec ? D / 4 : D);
     long long g = (n_el + 255) / 256;
     if (g > kNumSMs * 32) g = kNumSMs * 32;

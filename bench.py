@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--no-fuse", action="store_true", help="argmin and row epilogue as two kernels (VQ_FLAG_NO_FUSE)")
     ap.add_argument("--no-screen", action="store_true", help="3xTF32 tensor kernels instead of screen + exact refine (VQ_FLAG_NO_SCREEN)")
     ap.add_argument("--screen", action="store_true", help="force screen + exact refine (VQ_FLAG_SCREEN)")
+    ap.add_argument("--split-backward", action="store_true", help="N > 1: dE-only backward, all-reduce on a side stream while the dz pass runs (measured slower than the serial default: cross-stream events cost more than the overlap gains)")
     ap.add_argument("--fused-allreduce", action="store_true", help="N > 1: vq_backward_allreduce (one kernel, exchange overlaps the dz pass; measured slower) instead of vq_backward + vq_allreduce_push")
     ap.add_argument("--nccl", action="store_true", help="N > 1: use NCCL for the per-step all-reduce instead of vq_allreduce_sum")
     ap.add_argument("--skip-cpu", action="store_true")
@@ -251,6 +252,13 @@ def main():
     elif world > 1:
         collective = "NCCL all_reduce"
     fused_ar = sym is not None and D % 4 == 0 and args.fused_allreduce
+    split_bwd = sym is not None and not fused_ar and args.split_backward
+    main_stream = torch.cuda.current_stream()
+    side_stream = torch.cuda.Stream(device=dev) if split_bwd else None
+    ev_dE, ev_ar = torch.cuda.Event(), torch.cuda.Event()
+    if split_bwd:
+        collective = ("backward split in two (dE, then dz) so that the push all-reduce of [dE|hist|sse] over NVLink peer memory "
+                      "(vq_allreduce_push, " + ("NVLS multimem.st" if sym.nvls else "P2P stores") + ") runs on a side stream while dz is computed")
     if fused_ar:
         collective = "backward + two-step push all-reduce fused in one kernel (vq_backward_allreduce, " + ("NVLS multimem.st" if sym.nvls else "P2P stores") + ")"
     packs = [sym.payload()] if sym is not None else [torch.zeros(n_packed, device=dev)]
@@ -274,6 +282,17 @@ def main():
         L.check(lib.vq_prepare_step(P(E), K, D, P(e2), P(ehi), P(elo), P(hist), P(ws), wsb, P(dE), st))
         L.check(lib.vq_forward(P(z), P(E), P(e2), P(ehi), P(elo), N, K, D, BETA, fwd_flags, P(q), P(idx), P(onehot),
                                P(hist), P(sse), scal.data_ptr(), scal.data_ptr() + 4, P(ws), wsb, st))
+        if split_bwd:
+            # data parallel: codebook gradient first, then its all-reduce on a side stream WHILE the dz pass runs
+            L.check(lib.vq_backward(None, P(g_loss), P(z), P(E), P(idx), N, N, n_dE, K, D, BETA, bwd_flags | L.FLAG_NO_DZ,
+                                    None, P(dE), st))
+            ev_dE.record(main_stream)
+            side_stream.wait_event(ev_dE)
+            sym.reduce(side_stream.cuda_stream)          # reduced [dE | hist | sse] lands in sym.out
+            ev_ar.record(side_stream)
+            L.check(lib.vq_backward(P(gs[i % nbuf]), P(g_loss), P(z), P(E), P(idx), N, N, n_dE, K, D, BETA, 0, P(dz), None, st))
+            main_stream.wait_event(ev_ar)                # the step ends when both are done
+            return
         if fused_ar:
             # backward + all-reduce in ONE kernel: the NVLink exchange overlaps the dz pass; result in sym.out
             sym.backward_reduce(P(gs[i % nbuf]), P(g_loss), P(z), P(E), P(idx), N, n_dE, K, D, BETA, bwd_flags, P(dz), st)

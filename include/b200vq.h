@@ -49,6 +49,8 @@ extern "C" {
 #define VQ_FLAG_STATE_READY (1 << 8) /* forward: vq_prepare_step already reset hist and the workspace counter for this call */
 #define VQ_FLAG_NO_SCREEN  (1 << 9)  /* forward: 3xTF32 tensor kernels, never the screen (1xTF32) + exact-refine kernel */
 #define VQ_FLAG_SCREEN     (1 << 10) /* forward: force the screen + exact-refine kernel wherever its shape constraints allow */
+#define VQ_FLAG_NO_DZ      (1 << 11) /* backward: codebook gradient only (needs TRAIN_VQ; dz may be NULL).  Data parallel runs this, starts the
+                                      all-reduce of dE on a side stream and computes dz with a second call without TRAIN_VQ */
 #define VQ_FLAG_ZERO_DE    (1 << 5)  /* backward: zero dE (memset on `stream`) before accumulating into it */
 
 typedef void* vq_stream_t;   /* cudaStream_t */
