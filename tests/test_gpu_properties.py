@@ -10,6 +10,8 @@ oracle would take minutes: size-independent properties the domain offers.
   * linearity of backward in (g_loss, g_q);
   * a slice of the big problem checked against the CPU oracle.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -214,3 +216,47 @@ def test_screen_kernel_adversarial_inputs(lib, kind, D, K):
     out_oh = _forward(lib, z, E, 1 << 10, want_onehot=True)
     assert torch.equal(out_oh["idx"].cpu(), ref) and torch.equal(out_oh["onehot"].argmax(1).int().cpu(), ref)
     assert float(out_oh["onehot"].sum()) == N
+
+
+def test_screen_kernel_fuzz_against_exact_path(lib):
+    """Randomised sweep over shapes, scales and codebook geometries: the screen + refine kernel (append-only candidate
+    log, compaction, spill list, rescans) must return exactly the indices of the exact CUDA-core path (which is
+    bit-exact vs oracle/vq_oracle.c) -- with and without the dense one-hot (one / two row-worker groups)."""
+    dev = _dev()
+    rng = np.random.default_rng(20251018)
+    n_checked = 0
+    n_trials = int(os.environ.get("B200VQ_FUZZ_TRIALS", "48"))      # raise for a long soak run
+    for trial in range(n_trials):
+        D = int(rng.choice([32, 64, 96, 128, 192, 256]))
+        K = int(rng.choice([256, 512, 768, 1024, 2048]))
+        N = int(rng.integers(1, 6000))
+        g = torch.Generator().manual_seed(int(rng.integers(1 << 30)))
+        kind = trial % 6
+        E = torch.randn(K, D, generator=g)
+        z = torch.randn(N, D, generator=g)
+        if kind == 1:                                    # reference init: tiny codebook, ties galore
+            E = (torch.rand(K, D, generator=g) * 2 - 1) / K
+        elif kind == 2:                                  # clusters of near-identical codewords, noise level sets the
+            n_cl = int(rng.choice([4, 16, 64]))          # number of candidates per row (1 ... hundreds)
+            noise = float(rng.choice([1e-5, 1e-4, 1e-3, 1e-2]))
+            base = torch.randn(n_cl, D, generator=g)
+            E = base[torch.randint(0, n_cl, (K,), generator=g)] + noise * torch.randn(K, D, generator=g)
+        elif kind == 3:                                  # rows sit next to codewords, several exact copies of some codes
+            E[torch.randint(0, K, (K // 8,), generator=g)] = E[torch.randint(0, K, (K // 8,), generator=g)]
+            z = E[torch.randint(0, K, (N,), generator=g)] + 1e-3 * torch.randn(N, D, generator=g)
+        elif kind == 4:                                  # wild scales
+            s = float(rng.choice([1e-3, 30.0, 1e3]))
+            E, z = E * s, z * s
+        elif kind == 5:                                  # a few dominant codewords inflate the margin of every row
+            E[torch.randint(0, K, (3,), generator=g)] *= float(rng.choice([5.0, 40.0]))
+        E, z = E.contiguous().to(dev), z.contiguous().to(dev)
+        exact = _forward(lib, z, E, 4)["idx"]
+        for want_onehot in (False, True):
+            if want_onehot and N * K * 4 > (1 << 28):
+                continue
+            out = _forward(lib, z, E, 1 << 10, want_onehot=want_onehot)
+            bad = int((out["idx"] != exact).sum())
+            assert bad == 0, f"trial {trial}: kind {kind} N={N} K={K} D={D} onehot={want_onehot}: {bad} rows differ"
+            assert float(out["hist"].sum()) == N
+            n_checked += 1
+    assert n_checked >= 48
