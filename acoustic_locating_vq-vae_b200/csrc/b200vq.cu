@@ -653,12 +653,13 @@ int vq_allreduce_push(const void* const* recv_buffers, void* multicast_or_null, 
     long long blocks = (lines + 255) / 256;
     if (blocks > kNumSMs) blocks = kNumSMs;
     ProfScope prof(KID_ALLREDUCE, st);
-    // one step (every payload to every rank) up to 3 ranks; reduce-scatter + all-gather from 4 ranks on, where the
-    // world x payload that one step lands in every rank costs more than a second NVLink latency
-    // (B200VQ_AR_ALGO=1|2 forces either; both fit the same world x lines receive buffers)
+    // one step (every payload to every rank) below 8 ranks; reduce-scatter + all-gather from 8 ranks on, where the
+    // world x payload that one step lands in every rank costs more than a second NVLink latency (11.9 vs 14.8 us back
+    // to back at 8 GPUs; inside the training step the two are within run-to-run noise at 4 GPUs)
+    // (B200VQ_AR_ALGO=1|2 forces either; both fit the same world x (lines + 2) receive buffers)
     static const int forced = [] { const char* e = getenv("B200VQ_AR_ALGO"); return e == nullptr ? 0 : atoi(e); }();
     const long long S = (lines + world - 1) / world;
-    const bool two_step = world >= 2 && 2 * S <= lines + 2 && (forced == 2 || (forced != 1 && world >= 4));   // always true: see the header
+    const bool two_step = world >= 2 && 2 * S <= lines + 2 && (forced == 2 || (forced != 1 && world >= 8));   // always true: see the header
     cudaError_t e;
     if (two_step)
         e = launch_pdl(allreduce_push2_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, pb,

@@ -150,9 +150,9 @@ int vq_allreduce_sum(const void* const* peer_buffers, int world, int rank, int64
 
 /* Push ("low-latency") variant: no barrier.  recv_buffers[p] = rank p's symmetric RECEIVE buffer as mapped into this
  * process: at least world x (ceil(n_floats/2) + 2) 16-byte lines {d0, seq, d1, seq}, zero-initialised.
- *   up to 3 ranks: every rank stores its payload into slot [rank] of every receive buffer, then polls its own slots
+ *   below 8 ranks: every rank stores its payload into slot [rank] of every receive buffer, then polls its own slots
  *     until all lines carry `seq` and sums them in rank order (one NVLink one-way latency);
- *   from 4 ranks: reduce-scatter + all-gather through the same buffers (rank j owns slice j: two latencies, but only
+ *   from 8 ranks: reduce-scatter + all-gather through the same buffers (rank j owns slice j: two latencies, but only
  *     2 x payload instead of world x payload lands in every rank).  B200VQ_AR_ALGO=1|2 forces either.
  * Results are bit-identical on every rank and between the two algorithms.  `seq` >= 1 and increases by one per call
  * on a given buffer; callers alternate between TWO receive buffers. */
