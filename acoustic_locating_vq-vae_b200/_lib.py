@@ -23,6 +23,9 @@ FLAG_NO_FUSE = 1 << 7
 FLAG_STATE_READY = 1 << 8
 FLAG_NO_SCREEN = 1 << 9
 FLAG_SCREEN = 1 << 10
+FLAG_BWD_FLAT = 1 << 12
+FLAG_BWD_BUCKET = 1 << 13
+FLAG_BWD_PRIVATE = 1 << 14
 
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -48,6 +51,7 @@ SIGNATURES = {
     "vq_finalize_stats": (_int, [_vp, _vp, _i64, _int, _int, _f32, _vp, _vp, _vp]),
     "vq_onehot": (_int, [_vp, _i64, _int, _vp, _vp]),
     "vq_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp]),
+    "vq_backward_path": (_int, [_i64, _int, _int, _int]),
     "vq_gather_sum_rows": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp]),
     "vq_scatter_add_rows": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _vp]),
     "vq_jitter_apply": (_int, [_vp, _vp, _i64, _int, _vp]),

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libb200vq.so")
 SOURCES = ["b200vq.cu"]
-HEADERS = ["common.cuh", "kernels_simt.cuh", "kernels_tc.cuh", "kernels_screen.cuh", os.path.join("..", "..", "include", "b200vq.h")]
+HEADERS = ["common.cuh", "kernels_simt.cuh", "kernels_tc.cuh", "kernels_screen.cuh", "kernels_bwd.cuh", os.path.join("..", "..", "include", "b200vq.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -18,6 +18,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_screen.cuh"
+#include "kernels_bwd.cuh"
 
 using namespace b200vq;
 
@@ -94,6 +95,35 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize applies to the CURRENT device only: remember per kernel instantiation
+// (one static DeviceOnce per call site) which devices have been configured.  Thread safe.
+struct DeviceOnce {
+    std::atomic<unsigned long long> done{0};     // bit d = device d configured (devices >= 64: set it every time)
+    template <typename Kernel>
+    cudaError_t max_smem(Kernel* kernel, int bytes) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 64 && (done.load(std::memory_order_acquire) >> dev) & 1ull) return cudaSuccess;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess && dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
+        return e;
+    }
+};
+
+// SM count of the current device (grids of the persistent kernels are sized from it, not from a constant)
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = kNumSMs;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return kNumSMs;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached = n;
+        cached_dev = dev;
+    }
+    return cached;
+}
 
 // ---- device gate: this library only runs on sm_100 ------------------------------------------------
 int check_device() {
@@ -212,11 +242,8 @@ int launch_tc(const CUtensorMap& tz, const CUtensorMap& thi, const CUtensorMap& 
               int K, int codes_per_split, int splits, int* idx, unsigned long long* keys, float* hist,
               unsigned int* counter, cudaStream_t st) {
     constexpr int smem = tc_smem_bytes(NSLAB, NSTAGE);
-    static bool configured = false;
-    if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(argmin_tc_kernel<NSLAB, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    static DeviceOnce once;
+    CUDA_TRY(once.max_smem(argmin_tc_kernel<NSLAB, NSTAGE>, smem));
     dim3 grid(static_cast<unsigned>((N + TC_ROWS - 1) / TC_ROWS), static_cast<unsigned>(splits));
     ProfScope prof(KID_ARGMIN_TC, st);
     argmin_tc_kernel<NSLAB, NSTAGE><<<grid, TC_THREADS, smem, st>>>(tz, thi, tlo, e_norm2, N, K, codes_per_split, idx,
@@ -231,12 +258,9 @@ int launch_tc2(const CUtensorMap& tz, const CUtensorMap& thi, const CUtensorMap&
                unsigned int* counter, const FusedRowArgs* fused, bool state_ready, cudaStream_t st) {
     constexpr int smem = tc2_smem_bytes(NSLAB, NSTAGE, ZBUF);
     static_assert(smem <= 232448, "CTA-pair kernel exceeds 227 KB of shared memory");
-    static bool configured = false;
-    if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(argmin_tc2_kernel<NSLAB, NSTAGE, ZBUF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CUDA_TRY(cudaFuncSetAttribute(argmin_tc2_kernel<NSLAB, NSTAGE, ZBUF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    static DeviceOnce once_plain, once_fused;
+    CUDA_TRY(once_plain.max_smem(argmin_tc2_kernel<NSLAB, NSTAGE, ZBUF, false>, smem));
+    CUDA_TRY(once_fused.max_smem(argmin_tc2_kernel<NSLAB, NSTAGE, ZBUF, true>, smem));
     const long long row_tiles = (N + TC_ROWS - 1) / TC_ROWS;
     const long long n_items = ((row_tiles + 1) / 2) * splits;          // (row-tile pair, codebook split)
     const int pairs = static_cast<int>(n_items < kNumSMs / 2 ? n_items : kNumSMs / 2);
@@ -266,11 +290,8 @@ int launch_screen(const CUtensorMap& tz, const CUtensorMap& thi, const float* e_
                   float* hist, unsigned int* counter, const FusedRowArgs& fused, bool state_ready, cudaStream_t st) {
     constexpr int smem = sc_smem_bytes(NSLAB, NSTAGE, ZBUF);
     static_assert(smem <= 232448, "screen kernel exceeds 227 KB of shared memory");
-    static bool configured = false;
-    if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(vq_screen_kernel<NSLAB, NSTAGE, ZBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    static DeviceOnce once;
+    CUDA_TRY(once.max_smem(vq_screen_kernel<NSLAB, NSTAGE, ZBUF>, smem));
     const long long row_tiles = (N + TC_ROWS - 1) / TC_ROWS;
     const long long n_items = (row_tiles + 1) / 2;
     const int pairs = static_cast<int>(n_items < kNumSMs / 2 ? n_items : kNumSMs / 2);
@@ -346,10 +367,16 @@ static int prepare_impl(const float* E, int K, int D, float* e_norm2, float* E_h
                         unsigned int* counter, float* dE, cudaStream_t st) {
     if (int rc = check_device()) return rc;
     if (E == nullptr || e_norm2 == nullptr || K < 1 || D < 1) return fail(VQ_ERR_ARG, "vq_prepare: bad argument (K=%d D=%d)", K, D);
-    if ((E_hi == nullptr) != (E_lo == nullptr)) return fail(VQ_ERR_ARG, "vq_prepare: E_hi and E_lo must both be given or both be NULL");
-    const int blocks = (K + 7) / 8;
+    if (E_hi == nullptr && E_lo != nullptr) return fail(VQ_ERR_ARG, "vq_prepare: E_lo without E_hi");
     ProfScope prof(KID_PREP, st);
-    cudaError_t e = launch_pdl(prep_codebook_kernel, dim3(blocks), dim3(256), 0, st, E, K, D, e_norm2, E_hi, E_lo, hist, counter, dE);
+    cudaError_t e;
+    if (D % 4 == 0 && aligned16(E) && (E_hi == nullptr || (aligned16(E_hi) && aligned16(E_lo))) && (dE == nullptr || aligned16(dE))) {
+        // one thread per code runs the |E_k|^2 chain with its whole row in flight; split + state reset are coalesced
+        e = launch_pdl(prep_codebook_fast_kernel, dim3((K + 31) / 32), dim3(PREP_THREADS), 0, st, E, K, D, e_norm2, E_hi, E_lo, hist,
+                       counter, dE);
+    } else {
+        e = launch_pdl(prep_codebook_kernel, dim3((K + 7) / 8), dim3(256), 0, st, E, K, D, e_norm2, E_hi, E_lo, hist, counter, dE);
+    }
     if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of prep_codebook_kernel failed: %s", cudaGetErrorString(e));
     LAUNCH_CHECK("prep_codebook_kernel");
     return VQ_OK;
@@ -554,38 +581,127 @@ int vq_onehot(const int32_t* idx, int64_t n_rows, int K, float* onehot, vq_strea
     return VQ_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+// ---- backward strategy ------------------------------------------------------------
+enum BwdPath { BWD_FLAT = 0, BWD_BUCKET = 1, BWD_PRIVATE = 2 };
+
+// columns per lane of the private kernel (0: does not apply) -- the CTA's share of dE must fit shared memory
+int private_nc(int K, int D) {
+    if (D % 64 == 0 && pv_smem_bytes(K, 2) <= 227 * 1024) return 2;
+    if (D % 32 == 0 && pv_smem_bytes(K, 1) <= 227 * 1024) return 1;
+    return 0;
+}
+
+int choose_bwd_path(long long N, int K, int D, int flags, bool vec, bool idx_aligned) {
+    if (flags & VQ_FLAG_BWD_FLAT) return BWD_FLAT;
+    const bool bucket_ok = vec && idx_aligned && D % 32 == 0 && D <= 256 && (D / 32 <= 4 || D / 32 == 6 || D / 32 == 8) &&
+                           K <= BK_NB * BK_MAXLC && static_cast<long long>((K + BK_NB - 1) / BK_NB) * D <= BK_TABLE && N < (1ll << 24);
+    const bool private_ok = vec && private_nc(K, D) != 0 && N < (1ll << 40);
+    if (flags & VQ_FLAG_BWD_BUCKET) return bucket_ok ? BWD_BUCKET : BWD_FLAT;
+    if (flags & VQ_FLAG_BWD_PRIVATE) return private_ok ? BWD_PRIVATE : BWD_FLAT;
+    // every owner CTA scans all of idx (4 N bytes from L2): fine up to a few 100 k rows
+    if (bucket_ok && N <= 196608) return BWD_BUCKET;
+    // the private tables are flushed with (row chunks) * K * D atomics: worth it once a chunk holds several rows per code
+    if (private_ok && N >= 64ll * K) return BWD_PRIVATE;
+    return BWD_FLAT;
+}
+
+template <bool HAS_GQ, typename Sink>
+cudaError_t launch_bucket(int ni, dim3 grid, cudaStream_t st, const float* g_q, const float* g_loss, const float* z, const float* E,
+                          const int* idx, long long N, float denom_dz, float denom_dE, int K, int D, float beta, float* dz,
+                          const Sink& sink) {
+#define BK_CASE(NI_)                                                                                                   \
+    case NI_:                                                                                                         \
+        return launch_pdl(backward_bucket_kernel<HAS_GQ, NI_, Sink>, grid, dim3(BK_THREADS), 0, st, g_q, g_loss, z, E, idx, N, \
+                          denom_dz, denom_dE, K, D, beta, dz, sink);
+    switch (ni) {
+        BK_CASE(1) BK_CASE(2) BK_CASE(3) BK_CASE(4) BK_CASE(6) BK_CASE(8)
+        default: return cudaErrorInvalidValue;
+    }
+#undef BK_CASE
+}
+
+template <typename Sink>
+int run_bucket(const float* g_q, const float* g_loss, const float* z, const float* E, const int* idx, long long N, float denom_dz,
+               float denom_dE, int K, int D, float beta, float* dz, const Sink& sink, cudaStream_t st) {
+    const long long n_el = N * (D / 4);
+    long long dz_ctas = dz != nullptr ? (n_el + BK_THREADS * BK_DZ_EPT - 1) / (BK_THREADS * BK_DZ_EPT) : 0;
+    if (dz_ctas > 65535) dz_ctas = 65535;
+    const dim3 grid(static_cast<unsigned>(BK_NB + dz_ctas));
+    ProfScope prof(KID_BACKWARD, st);
+    const cudaError_t e = g_q != nullptr ? launch_bucket<true>(D / 32, grid, st, g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, K, D, beta, dz, sink)
+                                         : launch_bucket<false>(D / 32, grid, st, g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, K, D, beta, dz, sink);
+    if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of backward_bucket_kernel failed: %s", cudaGetErrorString(e));
+    LAUNCH_CHECK("backward_bucket_kernel");
+    return VQ_OK;
+}
+
+template <bool HAS_GQ, int NC>
+int run_private(const float* g_q, const float* g_loss, const float* z, const float* E, const int* idx, long long N, float denom_dz,
+                float denom_dE, int K, int D, float beta, float* dz, float* dE, cudaStream_t st) {
+    const int smem = pv_smem_bytes(K, NC);
+    static DeviceOnce once;
+    CUDA_TRY(once.max_smem(backward_private_kernel<HAS_GQ, NC>, smem));
+    const int slices = D / (32 * NC);
+    int chunks = sm_count() / slices;                     // one CTA per SM (the table fills its shared memory)
+    if (chunks < 1) chunks = 1;
+    const long long max_chunks = (N + PV_WIN - 1) / PV_WIN;
+    if (chunks > max_chunks) chunks = static_cast<int>(max_chunks);
+    const long long rows_per_cta = (N + chunks - 1) / chunks;
+    ProfScope prof(KID_BACKWARD, st);
+    const cudaError_t e = launch_pdl(backward_private_kernel<HAS_GQ, NC>, dim3(chunks, slices), dim3(PV_THREADS), smem, st, g_q, g_loss, z,
+                                     E, idx, N, rows_per_cta, denom_dz, denom_dE, K, D, beta, dz, dE);
+    if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of backward_private_kernel failed: %s", cudaGetErrorString(e));
+    LAUNCH_CHECK("backward_private_kernel");
+    return VQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vq_backward_path(int64_t n_rows, int K, int D, int flags) {
+    return choose_bwd_path(n_rows, K, D, flags, D % 4 == 0, true);
+}
+
 int vq_backward(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx,
                 int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags, float* dz,
                 float* dE, vq_stream_t stream) {
     if (int rc = check_device()) return rc;
     const long long N = n_rows;
     const bool train = (flags & VQ_FLAG_TRAIN_VQ) != 0 && dE != nullptr;
-    const bool no_dz = (flags & VQ_FLAG_NO_DZ) != 0;
-    if (z == nullptr || E == nullptr || idx == nullptr || (dz == nullptr && !no_dz) || K < 1 || D < 1 || N < 0 || n_rows_dz < 1 ||
-        n_rows_dE < 1 || (no_dz && !train))
+    if (z == nullptr || E == nullptr || idx == nullptr || (dz == nullptr && !train) || K < 1 || D < 1 || N < 0 || n_rows_dz < 1 ||
+        n_rows_dE < 1)
         return fail(VQ_ERR_ARG, "vq_backward: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool zero_dE = train && (flags & VQ_FLAG_ZERO_DE) != 0;
     if (N == 0) {
-        if (train && (flags & VQ_FLAG_ZERO_DE)) CUDA_TRY(cudaMemsetAsync(dE, 0, sizeof(float) * static_cast<size_t>(K) * D, static_cast<cudaStream_t>(stream)));
+        if (zero_dE) CUDA_TRY(cudaMemsetAsync(dE, 0, sizeof(float) * static_cast<size_t>(K) * D, st));
         return VQ_OK;
     }
     const float denom_dz = static_cast<float>(static_cast<double>(n_rows_dz) * static_cast<double>(D));
     const float denom_dE = static_cast<float>(static_cast<double>(n_rows_dE) * static_cast<double>(D));
-    const bool vec = (D % 4 == 0) && aligned16(z) && aligned16(E) && aligned16(dz) && (g_q == nullptr || aligned16(g_q)) &&
+    const bool vec = (D % 4 == 0) && aligned16(z) && aligned16(E) && (dz == nullptr || aligned16(dz)) && (g_q == nullptr || aligned16(g_q)) &&
                      (!train || aligned16(dE));
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (train && (flags & VQ_FLAG_ZERO_DE)) CUDA_TRY(cudaMemsetAsync(dE, 0, sizeof(float) * static_cast<size_t>(K) * D, st));
-    if (no_dz) {   // codebook gradient only (data parallel: its all-reduce then overlaps the dz pass)
-        const bool v4 = (D % 4 == 0) && aligned16(z) && aligned16(E) && aligned16(dE);
-        const long long n_e = N * (v4 ? D / 4 : D);
-        long long gb = (n_e + 255) / 256;
-        if (gb > kNumSMs * 32) gb = kNumSMs * 32;
-        ProfScope prof(KID_BACKWARD, st);
-        cudaError_t e = v4 ? launch_pdl(backward_dE_kernel<4>, dim3(static_cast<unsigned>(gb)), dim3(256), 0, st, g_loss, z, E, idx, N, denom_dE, D, dE)
-                           : launch_pdl(backward_dE_kernel<1>, dim3(static_cast<unsigned>(gb)), dim3(256), 0, st, g_loss, z, E, idx, N, denom_dE, D, dE);
-        if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of backward_dE_kernel failed: %s", cudaGetErrorString(e));
-        LAUNCH_CHECK("backward_dE_kernel");
-        return VQ_OK;
+    const int path = train ? choose_bwd_path(N, K, D, flags, vec, aligned16(idx)) : BWD_FLAT;
+    if (path == BWD_BUCKET) {
+        // every dE element has one writer: VQ_FLAG_ZERO_DE becomes "overwrite" (no memset), otherwise dE += ...
+        const StoreDE sink{dE, D, !zero_dE};
+        return run_bucket(g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, K, D, beta, dz, sink, st);
     }
+    if (zero_dE) CUDA_TRY(cudaMemsetAsync(dE, 0, sizeof(float) * static_cast<size_t>(K) * D, st));
+    if (path == BWD_PRIVATE) {
+        const int nc = private_nc(K, D);
+        if (g_q != nullptr)
+            return nc == 2 ? run_private<true, 2>(g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, K, D, beta, dz, dE, st)
+                           : run_private<true, 1>(g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, K, D, beta, dz, dE, st);
+        return nc == 2 ? run_private<false, 2>(g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, K, D, beta, dz, dE, st)
+                       : run_private<false, 1>(g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, K, D, beta, dz, dE, st);
+    }
+    if (dz == nullptr) return fail(VQ_ERR_ARG, "vq_backward: dz == NULL needs the bucket or private path (shape / alignment rules them out here)");
     const long long n_el = N * (vec ? D / 4 : D);
     long long g = (n_el + 255) / 256;
     if (g > kNumSMs * 32) g = kNumSMs * 32;

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) prep_codebook_kernel(const float* __restr
         if (E_hi != nullptr && d < D) {
             const float hi = tf32_rna(v);
             E_hi[static_cast<size_t>(warp) * D + d] = hi;
-            E_lo[static_cast<size_t>(warp) * D + d] = tf32_rna(v - hi);
+            if (E_lo != nullptr) E_lo[static_cast<size_t>(warp) * D + d] = tf32_rna(v - hi);
         }
         const int n = min(32, D - d0);
         for (int l = 0; l < n; ++l) {

@@ -269,6 +269,11 @@ def main():
     fwd_flags = ((L.FLAG_ONEHOT if emit_onehot else 0) | (L.FLAG_EXACT if args.exact else 0) |
                  (L.FLAG_NO_FUSE if args.no_fuse else 0) | (L.FLAG_NO_SCREEN if args.no_screen else 0) | (L.FLAG_SCREEN if args.screen else 0) | L.FLAG_STATE_READY)
     bwd_flags = L.FLAG_TRAIN_VQ
+    # the bucket backward writes every dE element exactly once (VQ_FLAG_ZERO_DE = plain stores); the other paths
+    # accumulate with atomics into a buffer that the prepare launch zeroes
+    zero_in_prepare = lib.vq_backward_path(N, K, D, 0) != 1
+    if not zero_in_prepare:
+        bwd_flags |= L.FLAG_ZERO_DE
     wsb = lib.vq_workspace_bytes(N, K, D, fwd_flags)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
@@ -279,7 +284,7 @@ def main():
         z = zs[i % nbuf]
         dE, hist, sse = views[0]
         # one launch: codebook norms + tf32 split + reset of hist / completion counter / dE accumulator
-        L.check(lib.vq_prepare_step(P(E), K, D, P(e2), P(ehi), P(elo), P(hist), P(ws), wsb, P(dE), st))
+        L.check(lib.vq_prepare_step(P(E), K, D, P(e2), P(ehi), P(elo), P(hist), P(ws), wsb, P(dE) if zero_in_prepare else None, st))
         L.check(lib.vq_forward(P(z), P(E), P(e2), P(ehi), P(elo), N, K, D, BETA, fwd_flags, P(q), P(idx), P(onehot),
                                P(hist), P(sse), scal.data_ptr(), scal.data_ptr() + 4, P(ws), wsb, st))
         if split_bwd:

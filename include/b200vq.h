@@ -51,7 +51,11 @@ extern "C" {
 #define VQ_FLAG_SCREEN     (1 << 10) /* forward: force the screen + exact-refine kernel wherever its shape constraints allow */
 #define VQ_FLAG_NO_DZ      (1 << 11) /* backward: codebook gradient only (needs TRAIN_VQ; dz may be NULL).  Data parallel runs this, starts the
                                       all-reduce of dE on a side stream and computes dz with a second call without TRAIN_VQ */
-#define VQ_FLAG_ZERO_DE    (1 << 5)  /* backward: zero dE (memset on `stream`) before accumulating into it */
+#define VQ_FLAG_ZERO_DE    (1 << 5)  /* backward: dE = gradient instead of dE += gradient (a memset on `stream`, or plain stores on
+                                        the bucket path, which writes every element exactly once) */
+#define VQ_FLAG_BWD_FLAT    (1 << 12) /* backward: force the flat kernel (one 16-byte red.global.add per element of dE) */
+#define VQ_FLAG_BWD_BUCKET  (1 << 13) /* backward: force the bucket kernel (code-owner CTAs, no atomics) where the shape allows */
+#define VQ_FLAG_BWD_PRIVATE (1 << 14) /* backward: force the shared-memory-private kernel where the shape allows */
 
 typedef void* vq_stream_t;   /* cudaStream_t */
 
@@ -124,6 +128,11 @@ int vq_onehot(const int32_t* idx, int64_t n_rows, int K, float* onehot, vq_strea
 int vq_backward(const float* g_q, const float* g_loss, const float* z, const float* E,
                 const int32_t* idx, int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE,
                 int K, int D, float beta, int flags, float* dz, float* dE, vq_stream_t stream);
+/* Which kernel vq_backward takes for dE (16-byte aligned pointers assumed): 0 flat (one red.global.add per element),
+ * 1 bucket (code-owner CTAs sum their rows in registers: no atomics, every dE element written once; N up to ~200 k),
+ * 2 private (per-CTA copy of dE in shared memory, flushed once; N >= 64 K).  dz may be NULL on paths 1 and 2
+ * (codebook gradient only). */
+int vq_backward_path(int64_t n_rows, int K, int D, int flags);
 
 /* -- the consumer of `encodings` as an index gather ------------------------------------ */
 /* LocationModule.fc_1 (location_model.py:10,21) applied to flatten(one_hot(B,T,K)) (train_location.py:74-75):

@@ -1,0 +1,183 @@
+"""GPU tests of the three backward strategies behind vq_backward:
+flat (one red.global.add per element), bucket (code-owner CTAs, no atomics) and private (per-CTA copy of dE in
+shared memory).  All three must give the oracle's gradients (autograd of vector_quantizer.py:46-54, restated in
+oracle/vq_oracle.c) within the north-star tolerance; dz is the same arithmetic in all three and must be BIT-identical.
+Edge cases: ragged N (N % 4 != 0), K below / not a multiple of the 128 owner CTAs, a single hot code that owns every
+row (list flushes, window overflow), accumulate-vs-overwrite semantics of VQ_FLAG_ZERO_DE, dz == NULL, frozen codebook.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+BETA = 0.25
+TRAIN, ZERO_DE, FLAT, BUCKET, PRIVATE = 1 << 1, 1 << 5, 1 << 12, 1 << 13, 1 << 14
+
+
+def _dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _backward(lib, g, gl, z, E, idx, flags, n_dE=None, dE_init=None, want_dz=True):
+    dev = z.device
+    N, D = z.shape
+    K = E.shape[0]
+    dz = torch.full((N, D), 7.0, device=dev) if want_dz else None
+    dE = torch.zeros(K, D, device=dev) if dE_init is None else dE_init.clone()
+    glt = torch.tensor(gl, dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.vq_backward(None if g is None else g.data_ptr(), glt.data_ptr(), z.data_ptr(), E.data_ptr(), idx.data_ptr(), N, N,
+                         N if n_dE is None else n_dE, K, D, BETA, flags, None if dz is None else dz.data_ptr(), dE.data_ptr(), st)
+    assert rc == 0, lib.vq_last_error()
+    torch.cuda.synchronize()
+    return dz, dE
+
+
+def _oracle(g, gl, z, E, idx):
+    from oracle import c_oracle
+    return c_oracle.backward(g.cpu().numpy(), gl, z.cpu().numpy(), E.cpu().numpy(), idx.cpu().numpy().astype(np.int32), BETA, True)
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def _make(N, D, K, seed, hot=None):
+    dev = _dev()
+    g0 = torch.Generator(device="cpu").manual_seed(seed)
+    E = torch.randn(K, D, generator=g0).to(dev)
+    z = torch.randn(N, D, generator=g0).to(dev)
+    g = torch.randn(N, D, generator=g0).to(dev)
+    if hot is None:
+        # a skewed but realistic assignment: nearest code under the reference's distance (cheap torch ops; the index
+        # source does not matter for the backward, any idx in [0, K) is a valid input)
+        d = (z * z).sum(1, keepdim=True) + (E * E).sum(1) - 2 * z @ E.t()
+        idx = d.argmin(1).int()
+    else:
+        idx = torch.full((N,), hot, dtype=torch.int32, device=dev)
+    return E, z, g, idx
+
+
+SHAPES = [
+    # N, D, K
+    (51456, 64, 1024),      # BASELINE configs[1]
+    (16000, 128, 1024),     # configs[0]
+    (3216, 64, 1024),       # configs[4] RIR side
+    (4099, 64, 200),        # ragged N, K not a multiple of 128
+    (1003, 32, 37),         # K below the owner count
+    (2051, 96, 384),
+    (6000, 256, 512),
+    (9001, 192, 256),
+]
+
+
+@pytest.mark.parametrize("N,D,K", SHAPES)
+def test_paths_agree_with_oracle(lib, N, D, K):
+    E, z, g, idx = _make(N, D, K, seed=N + D + K)
+    dz_ref, dE_ref = _oracle(g, 0.7, z, E, idx)
+    outs = {}
+    for name, fl in (("flat", FLAT), ("bucket", BUCKET), ("private", PRIVATE)):
+        assert lib.vq_backward_path(N, K, D, fl) in (0, 1, 2)
+        dz, dE = _backward(lib, g, 0.7, z, E, idx, TRAIN | ZERO_DE | fl)
+        outs[name] = (dz, dE, lib.vq_backward_path(N, K, D, fl))
+        assert _rel(dz.cpu().numpy(), dz_ref) <= 1e-5, name
+        assert _rel(dE.cpu().numpy(), dE_ref) <= 1e-5, name
+    # the forced paths really ran where the shape allows them (all of SHAPES do for bucket; private needs D % 32 == 0 and K * 128 B of smem)
+    assert outs["bucket"][2] == 1
+    assert outs["private"][2] == 2
+    assert torch.equal(outs["flat"][0], outs["bucket"][0]) and torch.equal(outs["flat"][0], outs["private"][0])
+    # the default choice is one of them and agrees as well
+    dz, dE = _backward(lib, g, 0.7, z, E, idx, TRAIN | ZERO_DE)
+    assert torch.equal(dz, outs["flat"][0]) and _rel(dE.cpu().numpy(), dE_ref) <= 1e-5
+
+
+def test_default_path_choice(lib):
+    assert lib.vq_backward_path(51456, 1024, 64, 0) == 1          # bench workload: bucket
+    assert lib.vq_backward_path(1 << 20, 512, 64, 0) == 2         # sweep, K*D small: private
+    assert lib.vq_backward_path(1 << 20, 1024, 64, 0) == 2
+    assert lib.vq_backward_path(1 << 20, 8192, 256, 0) == 0       # dE does not fit shared memory: flat
+    assert lib.vq_backward_path(1000, 1000, 5, 0) == 0            # odd D: flat
+
+
+@pytest.mark.parametrize("path", [BUCKET, PRIVATE])
+def test_hot_code_owns_every_row(lib, path):
+    # one code takes all rows: the owner's list is flushed many times (bucket) / one warp owns every row (private)
+    N, D, K = 20000, 64, 512
+    E, z, g, idx = _make(N, D, K, seed=5, hot=130)
+    dz_ref, dE_ref = _oracle(g, 1.0, z, E, idx)
+    dz, dE = _backward(lib, g, 1.0, z, E, idx, TRAIN | ZERO_DE | path)
+    assert _rel(dz.cpu().numpy(), dz_ref) <= 1e-5
+    assert _rel(dE.cpu().numpy(), dE_ref) <= 2e-5        # 20 000 addends in one fp32 sum
+    assert float(dE[:130].abs().max()) == 0.0 and float(dE[131:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("path", [FLAT, BUCKET, PRIVATE])
+def test_accumulate_and_overwrite(lib, path):
+    N, D, K = 5000, 64, 256
+    E, z, g, idx = _make(N, D, K, seed=9)
+    _, dE_ref = _oracle(g, 1.0, z, E, idx)
+    init = torch.randn(K, D, device=z.device)
+    _, dE_over = _backward(lib, g, 1.0, z, E, idx, TRAIN | ZERO_DE | path, dE_init=init)       # dE = gradient
+    _, dE_acc = _backward(lib, g, 1.0, z, E, idx, TRAIN | path, dE_init=init)                  # dE += gradient
+    assert _rel(dE_over.cpu().numpy(), dE_ref) <= 1e-5
+    np.testing.assert_allclose((dE_acc - init).cpu().numpy(), dE_ref, rtol=0, atol=2e-7 + 1e-5 * np.abs(dE_ref).max())
+
+
+@pytest.mark.parametrize("path", [BUCKET, PRIVATE])
+def test_codebook_gradient_only(lib, path):
+    N, D, K = 7001, 64, 512
+    E, z, g, idx = _make(N, D, K, seed=11)
+    _, dE_ref = _oracle(g, 1.0, z, E, idx)
+    dz, dE = _backward(lib, None, 1.0, z, E, idx, TRAIN | ZERO_DE | path, want_dz=False)
+    assert dz is None and _rel(dE.cpu().numpy(), dE_ref) <= 1e-5
+
+
+def test_global_row_count_scales_dE_only(lib):
+    # data parallel: dE carries the GLOBAL row count in its scale, dz the local one
+    N, D, K = 6432, 64, 1024
+    E, z, g, idx = _make(N, D, K, seed=13)
+    dz1, dE1 = _backward(lib, g, 1.0, z, E, idx, TRAIN | ZERO_DE | BUCKET)
+    dz8, dE8 = _backward(lib, g, 1.0, z, E, idx, TRAIN | ZERO_DE | BUCKET, n_dE=8 * N)
+    assert torch.equal(dz1, dz8)
+    np.testing.assert_allclose(dE8.cpu().numpy() * 8, dE1.cpu().numpy(), rtol=1e-6, atol=1e-12)
+
+
+def test_out_of_range_codes_are_ignored(lib):
+    # indices outside [0, K) never come out of vq_forward; a caller-supplied one must not touch memory outside dE
+    N, D, K = 4096, 64, 256
+    E, z, g, idx = _make(N, D, K, seed=17)
+    bad = idx.clone()
+    bad[::97] = K + 5
+    good_rows = (bad < K)
+    for path in (BUCKET, PRIVATE):
+        guard = torch.zeros(K + 64, D, device=z.device)
+        glt = torch.ones((), device=z.device)
+        dz = torch.empty(N, D, device=z.device)
+        st = torch.cuda.current_stream().cuda_stream
+        rc = lib.vq_backward(g.data_ptr(), glt.data_ptr(), z.data_ptr(), E.data_ptr(), bad.data_ptr(), N, N, N, K, D, BETA,
+                             TRAIN | ZERO_DE | path, dz.data_ptr(), guard.data_ptr(), st)
+        assert rc == 0, lib.vq_last_error()
+        torch.cuda.synchronize()
+        assert float(guard[K:].abs().max()) == 0.0
+        assert torch.equal(dz[~good_rows], g[~good_rows])       # no code, no commitment term
+        ref = torch.zeros(K, D, device=z.device, dtype=torch.float64)
+        ref.index_add_(0, bad[good_rows].long(), (E[bad[good_rows].long()] - z[good_rows]).double())
+        ref *= 2.0 / (N * D)
+        assert _rel(guard[:K].cpu().numpy(), ref.cpu().numpy()) <= 1e-5
+
+
+def test_prepare_fast_matches_oracle_norms(lib):
+    from oracle import c_oracle
+    dev = _dev()
+    for K, D in ((1024, 64), (1000, 128), (37, 32), (8192, 256), (129, 100)):
+        E = torch.randn(K, D, device=dev)
+        e2 = torch.empty(K, device=dev); ehi = torch.empty_like(E); elo = torch.empty_like(E)
+        st = torch.cuda.current_stream().cuda_stream
+        assert lib.vq_prepare_codebook(E.data_ptr(), K, D, e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(), st) == 0
+        torch.cuda.synchronize()
+        assert np.array_equal(e2.cpu().numpy(), c_oracle.code_norms(E.cpu().numpy())), (K, D)
+        # hi is E rounded to tf32 (10 explicit mantissa bits), lo the rounded remainder: hi + lo reproduces E to 2^-21
+        hi = ehi.cpu().numpy(); lo = elo.cpu().numpy()
+        assert np.all((hi.view(np.uint32) & 0x1FFF) == 0) and np.all((lo.view(np.uint32) & 0x1FFF) == 0)
+        assert np.abs(hi + lo - E.cpu().numpy()).max() <= 2.0 ** -21 * np.abs(E.cpu().numpy()).max()
