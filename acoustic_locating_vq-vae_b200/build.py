@@ -11,7 +11,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SO_PATH = os.path.join(CSRC, "libb200vq.so")
+SO_PATH = os.environ.get("B200VQ_SO") or os.path.join(CSRC, "libb200vq.so")   # B200VQ_SO: an experiment build (tools/)
 SOURCES = ["b200vq.cu"]
 HEADERS = ["common.cuh", "kernels_simt.cuh", "kernels_tc.cuh", "kernels_screen.cuh", "kernels_bwd.cuh", os.path.join("..", "..", "include", "b200vq.h")]
 

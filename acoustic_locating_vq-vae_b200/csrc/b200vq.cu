@@ -19,6 +19,7 @@
 #include "kernels_tc.cuh"
 #include "kernels_screen.cuh"
 #include "kernels_bwd.cuh"
+#include "kernels_dp.cuh"
 
 using namespace b200vq;
 
@@ -154,7 +155,22 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 // (rows, D) fp32 row-major matrix; box = 32 floats (128 B) x 128 rows, 128-byte swizzle.
+// A descriptor depends on (address, rows, D) only and encoding one costs about a microsecond of host time, so the
+// last few are kept per thread (training loops present the same codebook and the same few activation buffers).
+struct TmapSlot { const float* base; long long rows; int D; unsigned long long stamp; CUtensorMap map; };
 int make_tmap(CUtensorMap* out, const float* base, long long rows, int D) {
+    constexpr int NSLOT = 16;
+    static thread_local TmapSlot cache[NSLOT] = {};
+    static thread_local unsigned long long tick = 0;
+    int victim = 0;
+    for (int i = 0; i < NSLOT; ++i) {
+        if (cache[i].stamp != 0 && cache[i].base == base && cache[i].rows == rows && cache[i].D == D) {
+            cache[i].stamp = ++tick;
+            *out = cache[i].map;
+            return VQ_OK;
+        }
+        if (cache[i].stamp < cache[victim].stamp) victim = i;
+    }
     auto fn = get_encode_fn();
     if (fn == nullptr) return fail(VQ_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(rows)};
@@ -165,6 +181,7 @@ int make_tmap(CUtensorMap* out, const float* base, long long rows, int D) {
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(VQ_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    cache[victim] = TmapSlot{base, rows, D, ++tick, *out};
     return VQ_OK;
 }
 
@@ -181,6 +198,16 @@ bool tensor_path_ok(long long N, int K, int D, int flags, const float* z = nullp
     if (D > 128 && !screen_shape) return false;
     if (check_ptrs && (ehi == nullptr || elo == nullptr || !aligned16(z) || !aligned16(ehi) || !aligned16(elo))) return false;
     return true;
+}
+
+// shapes / alignments the screen + refine kernel takes (E_hi is not needed in self-prepared mode)
+bool screen_path_ok(long long N, int K, int D, int flags, const float* z, const float* E, const float* q_out, const float* onehot) {
+    if (flags & (VQ_FLAG_EXACT | VQ_FLAG_NO_SCREEN | VQ_FLAG_NO_FUSE | VQ_FLAG_TC_1CTA)) return false;
+    if (N < 1 || N >= (1ll << 31) - TC_ROWS) return false;
+    if (!(D == 32 || D == 64 || D == 96 || D == 128 || D == 192 || D == 256)) return false;
+    if (K % TC2_CODES != 0 || K < TC2_CODES || K > (1 << 20)) return false;   // (row, code) pairs pack the code into 20 bits
+    const bool quant = (flags & VQ_FLAG_NO_QUANT) == 0, want_onehot = (flags & VQ_FLAG_ONEHOT) != 0;
+    return aligned16(z) && aligned16(E) && (!quant || aligned16(q_out)) && (!want_onehot || aligned16(onehot));
 }
 
 // number of codebook splits per row tile: fill the 148 SMs when there are few row tiles.
@@ -202,7 +229,7 @@ int choose_splits(long long row_tiles, int code_tiles, int max_splits, int slots
 }
 
 struct WsLayout {
-    size_t partials_off, counter_off, keys_off, total;
+    size_t partials_off, counter_off, keys_off, hist_off, sums_off, total;
     int rows_grid;
 };
 
@@ -224,7 +251,7 @@ int rows_grid_for(long long N, int R) {
     return static_cast<int>(g);
 }
 
-WsLayout ws_layout(long long N) {
+WsLayout ws_layout(long long N, int K = 0, int D = 0) {
     WsLayout w;
     w.rows_grid = 0;
     w.partials_off = 0;
@@ -233,7 +260,9 @@ WsLayout ws_layout(long long N) {
     // the per-row key buffer (unfused paths) and the screen kernel's spill lists (fused path) share the tail
     const size_t keys_bytes = static_cast<size_t>(N) * sizeof(unsigned long long);
     const size_t spill_bytes = static_cast<size_t>(kNumSMs) * 4 * SC_SPILL * sizeof(int4);
-    w.total = w.keys_off + (keys_bytes > spill_bytes ? keys_bytes : spill_bytes);
+    w.hist_off = (w.keys_off + (keys_bytes > spill_bytes ? keys_bytes : spill_bytes) + 255) / 256 * 256;
+    w.sums_off = (w.hist_off + 2 * sizeof(float) * static_cast<size_t>(K) + 255) / 256 * 256;   // [2][K] usage accumulators (vq_step_forward)
+    w.total = w.sums_off + 2 * sizeof(float) * static_cast<size_t>(K) * static_cast<size_t>(D);      // [2][K*D] code sums (VQ_FLAG_CODE_SUMS)
     return w;
 }
 
@@ -358,9 +387,9 @@ int vq_forward_uses_tensor_path(int64_t n_rows, int K, int D, int flags) {
 }
 
 size_t vq_workspace_bytes(int64_t n_rows, int K, int D, int flags) {
-    (void)K; (void)D; (void)flags;
+    (void)flags;
     if (n_rows < 0) n_rows = 0;
-    return ws_layout(n_rows).total;
+    return ws_layout(n_rows, K < 0 ? 0 : K, D < 0 ? 0 : D).total;
 }
 
 static int prepare_impl(const float* E, int K, int D, float* e_norm2, float* E_hi, float* E_lo, float* hist,
@@ -410,7 +439,7 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
     if (quant && q_out == nullptr) return fail(VQ_ERR_ARG, "vq_forward: q_out is NULL without VQ_FLAG_NO_QUANT");
     if (want_onehot && onehot == nullptr) return fail(VQ_ERR_ARG, "vq_forward: VQ_FLAG_ONEHOT with onehot == NULL");
     if (!defer && (perplexity == nullptr || (quant && loss == nullptr))) return fail(VQ_ERR_ARG, "vq_forward: loss/perplexity NULL without VQ_FLAG_DEFER_STATS");
-    const WsLayout w = ws_layout(N);
+    const WsLayout w = ws_layout(N, K, D);
     if (workspace == nullptr || workspace_bytes < w.total)
         return fail(VQ_ERR_WORKSPACE, "vq_forward: workspace %zu B < required %zu B", workspace_bytes, w.total);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -427,39 +456,43 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
 
     // ---- 1. argmin ----------------------------------------------------------------------------------------
     unsigned long long* keys = nullptr;
+    const bool self = (flags & VQ_FLAG_SELF_PREPARE) != 0;
+    // ---- screen + refine (one TF32 pass, exact fp32 refine of the candidates): the default fused forward ----
+    // Indices are bit-identical to the fp32 oracle, and it is the faster kernel everywhere on B200 (RIR-256 with the
+    // dense one-hot: 69.0 vs 69.6 us per step; 1.5x at D = 64 and 2x at D = 128 without the one-hot); D > 128 only
+    // fits this kernel.  VQ_FLAG_NO_SCREEN / B200VQ_SCREEN=0 select the 3xTF32 kernel, VQ_FLAG_SCREEN forces this one.
+    const bool screen = screen_path_ok(N, K, D, flags, z, E, q_out, onehot) && (self || (E_hi != nullptr && aligned16(E_hi))) &&
+                        ((flags & VQ_FLAG_SCREEN) || self || screen_enabled());
+    if (self && !screen) return fail(VQ_ERR_ARG, "vq_forward: VQ_FLAG_SELF_PREPARE needs the screen + refine path (call vq_step_forward)");
+    if (screen) {
+        FusedRowArgs fr{};
+        fr.z = z; fr.E = E; fr.q_out = quant ? q_out : nullptr; fr.onehot = want_onehot ? onehot : nullptr; fr.hist = hist;
+        fr.partials = partials; fr.counter = counter; fr.sse_out = sse; fr.loss = loss; fr.perplexity = perplexity;
+        fr.beta = beta; fr.finalize = defer ? 0 : 1; fr.trace = g_trace_buf;
+        fr.spill = reinterpret_cast<int4*>(keys_buf);   // 16-byte aligned: keys_off is a multiple of 256
+        static const int evict_first = [] { const char* e = getenv("B200VQ_ONEHOT_EVICT_FIRST"); return e != nullptr && e[0] == '0' ? 0 : 1; }();
+        fr.onehot_evict_first = evict_first;
+        if (self) {     // no prepare launch: norms in-kernel, raw codebook under the tensor map, usage counts ping-pong in the workspace
+            fr.e_norm2_w = const_cast<float*>(e_norm2);
+            fr.hist_ws = reinterpret_cast<float*>(ws + w.hist_off);
+            if ((flags & VQ_FLAG_CODE_SUMS) && quant) fr.sums_ws = reinterpret_cast<float*>(ws + w.sums_off);
+        }
+        CUtensorMap tz, thi;
+        if (int rc = make_tmap(&tz, z, N, D)) return rc;
+        if (int rc = make_tmap(&thi, self ? E : E_hi, K, D)) return rc;
+        const bool ready = self || (flags & VQ_FLAG_STATE_READY) != 0;
+        switch (D / TC_SLAB_FLOATS) {
+            case 1: return launch_screen<1, 8, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
+            case 2: return launch_screen<2, 8, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
+            case 3: return launch_screen<3, 6, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
+            case 4: return launch_screen<4, 4, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
+            case 6: return launch_screen<6, 6, 1>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
+            case 8: return launch_screen<8, 4, 1>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
+            default: break;
+        }
+    }
     if (tensor_path_ok(N, K, D, flags, z, E_hi, E_lo, true)) {
         const long long row_tiles = (N + TC_ROWS - 1) / TC_ROWS;
-        // ---- screen + refine (one TF32 pass, exact fp32 refine of the candidates): the default fused forward ----
-        // Indices are bit-identical to the fp32 oracle, and it is the faster kernel everywhere on B200 (RIR-256 with the
-        // dense one-hot: 69.0 vs 69.6 us per step; 1.5x at D = 64 and 2x at D = 128 without the one-hot); D > 128 only
-        // fits this kernel.  VQ_FLAG_NO_SCREEN / B200VQ_SCREEN=0 select the 3xTF32 kernel, VQ_FLAG_SCREEN forces this one.
-        const bool screen_shape = (K % TC2_CODES == 0) && K <= (1 << 20) /* (row, code) pairs pack the code into 20 bits */ &&
-                                  (D <= 128 || D == 192 || D == 256) && aligned16(E) &&
-                                  (!quant || aligned16(q_out)) && (!want_onehot || aligned16(onehot)) &&
-                                  !(flags & (VQ_FLAG_NO_SCREEN | VQ_FLAG_NO_FUSE | VQ_FLAG_TC_1CTA));
-        const bool screen = screen_shape && ((flags & VQ_FLAG_SCREEN) || screen_enabled());
-        if (screen) {
-            FusedRowArgs fr{};
-            fr.z = z; fr.E = E; fr.q_out = quant ? q_out : nullptr; fr.onehot = want_onehot ? onehot : nullptr; fr.hist = hist;
-            fr.partials = partials; fr.counter = counter; fr.sse_out = sse; fr.loss = loss; fr.perplexity = perplexity;
-            fr.beta = beta; fr.finalize = defer ? 0 : 1; fr.trace = g_trace_buf;
-            fr.spill = reinterpret_cast<int4*>(keys_buf);   // 16-byte aligned: keys_off is a multiple of 256
-            static const int evict_first = [] { const char* e = getenv("B200VQ_ONEHOT_EVICT_FIRST"); return e != nullptr && e[0] == '0' ? 0 : 1; }();
-            fr.onehot_evict_first = evict_first;
-            CUtensorMap tz, thi;
-            if (int rc = make_tmap(&tz, z, N, D)) return rc;
-            if (int rc = make_tmap(&thi, E_hi, K, D)) return rc;
-            const bool ready = (flags & VQ_FLAG_STATE_READY) != 0;
-            switch (D / TC_SLAB_FLOATS) {
-                case 1: return launch_screen<1, 8, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
-                case 2: return launch_screen<2, 8, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
-                case 3: return launch_screen<3, 6, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
-                case 4: return launch_screen<4, 4, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
-                case 6: return launch_screen<6, 6, 1>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
-                case 8: return launch_screen<8, 4, 1>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
-                default: break;
-            }
-        }
         const bool pair = (K % TC2_CODES == 0) && !(flags & VQ_FLAG_TC_1CTA);
         // CTA pairs: a wave is 74 pairs, each covering 256 rows x 256 codes per tile
         const int code_tiles = pair ? K / TC2_CODES : K / TC_CODES;
@@ -559,6 +592,36 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
     return VQ_OK;
 }
 
+int vq_workspace_init(void* workspace, size_t workspace_bytes, vq_stream_t stream) {
+    if (workspace == nullptr) return fail(VQ_ERR_ARG, "vq_workspace_init: workspace is NULL");
+    CUDA_TRY(cudaMemsetAsync(workspace, 0, workspace_bytes, static_cast<cudaStream_t>(stream)));
+    return VQ_OK;
+}
+
+// prepare + forward behind ONE entry.  On the screen + refine path this is a single launch: the kernel computes
+// |E_k|^2 itself, reads the raw codebook through the tensor map and keeps its per-call state (usage accumulators,
+// call counter) in the workspace, which must have been zeroed ONCE with vq_workspace_init.  Other shapes run the
+// prepare launch followed by vq_forward.
+int vq_step_forward(const float* z, const float* E, int64_t n_rows, int K, int D, float beta, int flags, float* e_norm2,
+                    float* E_hi, float* E_lo, float* q_out, int32_t* idx, float* onehot, float* hist, float* sse, float* loss,
+                    float* perplexity, void* workspace, size_t workspace_bytes, vq_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    if (z == nullptr || E == nullptr || e_norm2 == nullptr || hist == nullptr || K < 1 || D < 1 || n_rows < 0)
+        return fail(VQ_ERR_ARG, "vq_step_forward: bad argument");
+    const int fl = flags & ~(VQ_FLAG_STATE_READY | VQ_FLAG_SELF_PREPARE);
+    static const bool self_on = [] { const char* e = getenv("B200VQ_SELF_PREPARE"); return !(e != nullptr && e[0] == '0'); }();   // tuning knob
+    if (self_on && n_rows > 0 && screen_path_ok(n_rows, K, D, fl, z, E, q_out, onehot) && ((fl & VQ_FLAG_SCREEN) || screen_enabled()))
+        return vq_forward(z, E, e_norm2, nullptr, nullptr, n_rows, K, D, beta, fl | VQ_FLAG_SELF_PREPARE, q_out, idx, onehot, hist, sse,
+                          loss, perplexity, workspace, workspace_bytes, stream);
+    const bool tensor = tensor_path_ok(n_rows, K, D, fl);
+    if (tensor && (E_hi == nullptr || E_lo == nullptr)) return fail(VQ_ERR_ARG, "vq_step_forward: E_hi / E_lo scratch is NULL but this shape runs the 3xTF32 kernels");
+    if (int rc = vq_prepare_step(E, K, D, e_norm2, tensor ? E_hi : nullptr, tensor ? E_lo : nullptr, hist, workspace, workspace_bytes, nullptr,
+                                 stream))
+        return rc;
+    return vq_forward(z, E, e_norm2, E_hi, E_lo, n_rows, K, D, beta, fl | VQ_FLAG_STATE_READY, q_out, idx, onehot, hist, sse, loss, perplexity,
+                      workspace, workspace_bytes, stream);
+}
+
 int vq_finalize_stats(const float* hist, const float* sse, int64_t n_rows_global, int K, int D, float beta,
                       float* loss, float* perplexity, vq_stream_t stream) {
     if (int rc = check_device()) return rc;
@@ -586,7 +649,7 @@ int vq_onehot(const int32_t* idx, int64_t n_rows, int K, float* onehot, vq_strea
 namespace {
 
 // ---- backward strategy ------------------------------------------------------------
-enum BwdPath { BWD_FLAT = 0, BWD_BUCKET = 1, BWD_PRIVATE = 2 };
+enum BwdPath { BWD_FLAT = 0, BWD_PRIVATE = 2 };
 
 // columns per lane of the private kernel (0: does not apply) -- the CTA's share of dE must fit shared memory
 int private_nc(int K, int D) {
@@ -595,56 +658,22 @@ int private_nc(int K, int D) {
     return 0;
 }
 
-int choose_bwd_path(long long N, int K, int D, int flags, bool vec, bool idx_aligned) {
+int choose_bwd_path(long long N, int K, int D, int flags, bool vec) {
     if (flags & VQ_FLAG_BWD_FLAT) return BWD_FLAT;
-    const bool bucket_ok = vec && idx_aligned && D % 32 == 0 && D <= 256 && (D / 32 <= 4 || D / 32 == 6 || D / 32 == 8) &&
-                           K <= BK_NB * BK_MAXLC && static_cast<long long>((K + BK_NB - 1) / BK_NB) * D <= BK_TABLE && N < (1ll << 24);
     const bool private_ok = vec && private_nc(K, D) != 0 && N < (1ll << 40);
-    if (flags & VQ_FLAG_BWD_BUCKET) return bucket_ok ? BWD_BUCKET : BWD_FLAT;
     if (flags & VQ_FLAG_BWD_PRIVATE) return private_ok ? BWD_PRIVATE : BWD_FLAT;
-    // every owner CTA scans all of idx (4 N bytes from L2): fine up to a few 100 k rows
-    if (bucket_ok && N <= 196608) return BWD_BUCKET;
-    // the private tables are flushed with (row chunks) * K * D atomics: worth it once a chunk holds several rows per code
-    if (private_ok && N >= 64ll * K) return BWD_PRIVATE;
+    // the private tables are flushed with (row chunks) * K * D atomics, and the kernel only beats the flat one where
+    // the flat one is bound by its atomics (few addresses): measured 196 vs 252 us at K = 512, D = 64, N = 1M
+    if (private_ok && N >= 256ll * K && static_cast<long long>(K) * D <= 32768) return BWD_PRIVATE;
     return BWD_FLAT;
-}
-
-template <bool HAS_GQ, typename Sink>
-cudaError_t launch_bucket(int ni, dim3 grid, cudaStream_t st, const float* g_q, const float* g_loss, const float* z, const float* E,
-                          const int* idx, long long N, float denom_dz, float denom_dE, int K, int D, float beta, float* dz,
-                          const Sink& sink) {
-#define BK_CASE(NI_)                                                                                                   \
-    case NI_:                                                                                                         \
-        return launch_pdl(backward_bucket_kernel<HAS_GQ, NI_, Sink>, grid, dim3(BK_THREADS), 0, st, g_q, g_loss, z, E, idx, N, \
-                          denom_dz, denom_dE, K, D, beta, dz, sink);
-    switch (ni) {
-        BK_CASE(1) BK_CASE(2) BK_CASE(3) BK_CASE(4) BK_CASE(6) BK_CASE(8)
-        default: return cudaErrorInvalidValue;
-    }
-#undef BK_CASE
-}
-
-template <typename Sink>
-int run_bucket(const float* g_q, const float* g_loss, const float* z, const float* E, const int* idx, long long N, float denom_dz,
-               float denom_dE, int K, int D, float beta, float* dz, const Sink& sink, cudaStream_t st) {
-    const long long n_el = N * (D / 4);
-    long long dz_ctas = dz != nullptr ? (n_el + BK_THREADS * BK_DZ_EPT - 1) / (BK_THREADS * BK_DZ_EPT) : 0;
-    if (dz_ctas > 65535) dz_ctas = 65535;
-    const dim3 grid(static_cast<unsigned>(BK_NB + dz_ctas));
-    ProfScope prof(KID_BACKWARD, st);
-    const cudaError_t e = g_q != nullptr ? launch_bucket<true>(D / 32, grid, st, g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, K, D, beta, dz, sink)
-                                         : launch_bucket<false>(D / 32, grid, st, g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, K, D, beta, dz, sink);
-    if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of backward_bucket_kernel failed: %s", cudaGetErrorString(e));
-    LAUNCH_CHECK("backward_bucket_kernel");
-    return VQ_OK;
 }
 
 template <bool HAS_GQ, int NC>
 int run_private(const float* g_q, const float* g_loss, const float* z, const float* E, const int* idx, long long N, float denom_dz,
                 float denom_dE, int K, int D, float beta, float* dz, float* dE, cudaStream_t st) {
     const int smem = pv_smem_bytes(K, NC);
-    static DeviceOnce once;
-    CUDA_TRY(once.max_smem(backward_private_kernel<HAS_GQ, NC>, smem));
+    static DeviceOnce once;                               // the table size depends on K: opt in to the maximum once
+    CUDA_TRY(once.max_smem(backward_private_kernel<HAS_GQ, NC>, 227 * 1024));
     const int slices = D / (32 * NC);
     int chunks = sm_count() / slices;                     // one CTA per SM (the table fills its shared memory)
     if (chunks < 1) chunks = 1;
@@ -664,7 +693,7 @@ int run_private(const float* g_q, const float* g_loss, const float* z, const flo
 extern "C" {
 
 int vq_backward_path(int64_t n_rows, int K, int D, int flags) {
-    return choose_bwd_path(n_rows, K, D, flags, D % 4 == 0, true);
+    return choose_bwd_path(n_rows, K, D, flags, D % 4 == 0);
 }
 
 int vq_backward(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx,
@@ -686,12 +715,7 @@ int vq_backward(const float* g_q, const float* g_loss, const float* z, const flo
     const float denom_dE = static_cast<float>(static_cast<double>(n_rows_dE) * static_cast<double>(D));
     const bool vec = (D % 4 == 0) && aligned16(z) && aligned16(E) && (dz == nullptr || aligned16(dz)) && (g_q == nullptr || aligned16(g_q)) &&
                      (!train || aligned16(dE));
-    const int path = train ? choose_bwd_path(N, K, D, flags, vec, aligned16(idx)) : BWD_FLAT;
-    if (path == BWD_BUCKET) {
-        // every dE element has one writer: VQ_FLAG_ZERO_DE becomes "overwrite" (no memset), otherwise dE += ...
-        const StoreDE sink{dE, D, !zero_dE};
-        return run_bucket(g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, K, D, beta, dz, sink, st);
-    }
+    const int path = train ? choose_bwd_path(N, K, D, flags, vec) : BWD_FLAT;
     if (zero_dE) CUDA_TRY(cudaMemsetAsync(dE, 0, sizeof(float) * static_cast<size_t>(K) * D, st));
     if (path == BWD_PRIVATE) {
         const int nc = private_nc(K, D);
@@ -701,7 +725,7 @@ int vq_backward(const float* g_q, const float* g_loss, const float* z, const flo
         return nc == 2 ? run_private<false, 2>(g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, K, D, beta, dz, dE, st)
                        : run_private<false, 1>(g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, K, D, beta, dz, dE, st);
     }
-    if (dz == nullptr) return fail(VQ_ERR_ARG, "vq_backward: dz == NULL needs the bucket or private path (shape / alignment rules them out here)");
+    if (dz == nullptr) return fail(VQ_ERR_ARG, "vq_backward: dz == NULL needs the private path (shape / alignment rule it out here)");
     const long long n_el = N * (vec ? D / 4 : D);
     long long g = (n_el + 255) / 256;
     if (g > kNumSMs * 32) g = kNumSMs * 32;
@@ -725,119 +749,221 @@ int vq_backward(const float* g_q, const float* g_loss, const float* z, const flo
     return VQ_OK;
 }
 
-// One-shot all-reduce over NVLink peer memory (see allreduce_oneshot_kernel).  peer_buffers: host array of `world`
-// device pointers, entry p = rank p's symmetric buffer as mapped into THIS process (entry `rank` = our own).
-int vq_allreduce_sum(const void* const* peer_buffers, int world, int rank, int64_t flag_offset_floats, int64_t n_floats,
-                     uint32_t seq, float* out, vq_stream_t stream) {
-    if (int rc = check_device()) return rc;
-    if (peer_buffers == nullptr || out == nullptr || world < 1 || world > AR_MAX_RANKS || rank < 0 || rank >= world ||
-        n_floats < 0 || flag_offset_floats < n_floats)
-        return fail(VQ_ERR_ARG, "vq_allreduce_sum: bad argument (world=%d rank=%d)", world, rank);
-    PeerBuffers pb{};
-    for (int p = 0; p < world; ++p) {
-        if (peer_buffers[p] == nullptr || !aligned16(peer_buffers[p])) return fail(VQ_ERR_ARG, "vq_allreduce_sum: peer buffer %d is NULL or misaligned", p);
-        pb.buf[p] = static_cast<float*>(const_cast<void*>(peer_buffers[p]));
-    }
-    if (!aligned16(out)) return fail(VQ_ERR_ARG, "vq_allreduce_sum: out is misaligned");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    long long blocks = (n_floats / 4 + 255) / 256;
-    if (blocks < 1) blocks = 1;
-    if (blocks > 64) blocks = 64;
-    ProfScope prof(KID_ALLREDUCE, st);
-    cudaError_t e = launch_pdl(allreduce_oneshot_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, pb, world, rank,
-                               static_cast<long long>(flag_offset_floats), static_cast<long long>(n_floats), seq, out);
-    if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of allreduce_oneshot_kernel failed: %s", cudaGetErrorString(e));
-    LAUNCH_CHECK("allreduce_oneshot_kernel");
-    return VQ_OK;
+// =========================================================================================================
+// step backward: the backward that pairs with vq_step_forward
+// =========================================================================================================
+int vq_step_uses_code_sums(int64_t n_rows, int K, int D, int flags) {
+    const int fl = flags & ~(VQ_FLAG_STATE_READY | VQ_FLAG_SELF_PREPARE);
+    static const bool self_on = [] { const char* e = getenv("B200VQ_SELF_PREPARE"); return !(e != nullptr && e[0] == '0'); }();
+    return (self_on && n_rows > 0 && (fl & VQ_FLAG_CODE_SUMS) && !(fl & VQ_FLAG_NO_QUANT) && screen_path_ok(n_rows, K, D, fl, nullptr, nullptr, nullptr, nullptr) &&
+            ((fl & VQ_FLAG_SCREEN) || screen_enabled())) ? 1 : 0;
 }
 
-// Push ("low-latency") all-reduce: see allreduce_push_kernel.  recv_buffers[p] = rank p's symmetric RECEIVE buffer
-// (world slots of lines_per_slot 16-byte lines, zero-initialised) as mapped into this process.
-int vq_allreduce_push(const void* const* recv_buffers, void* multicast_or_null, int world, int rank, const float* payload,
-                      int64_t n_floats, uint32_t seq, float* out, vq_stream_t stream) {
-    if (int rc = check_device()) return rc;
-    if (recv_buffers == nullptr || payload == nullptr || out == nullptr || world < 1 || world > AR_MAX_RANKS || rank < 0 ||
-        rank >= world || n_floats < 1 || seq == 0)
-        return fail(VQ_ERR_ARG, "vq_allreduce_push: bad argument (world=%d rank=%d seq=%u)", world, rank, seq);
-    PeerBuffers pb{};
-    for (int p = 0; p < world; ++p) {
-        if (recv_buffers[p] == nullptr || !aligned16(recv_buffers[p])) return fail(VQ_ERR_ARG, "vq_allreduce_push: receive buffer %d is NULL or misaligned", p);
-        pb.buf[p] = static_cast<float*>(const_cast<void*>(recv_buffers[p]));
-    }
-    const long long lines = (n_floats + 1) / 2;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    long long blocks = (lines + 255) / 256;
-    if (blocks > kNumSMs) blocks = kNumSMs;
-    ProfScope prof(KID_ALLREDUCE, st);
-    // one step (every payload to every rank) below 8 ranks; reduce-scatter + all-gather from 8 ranks on, where the
-    // world x payload that one step lands in every rank costs more than a second NVLink latency (11.9 vs 14.8 us back
-    // to back at 8 GPUs; inside the training step the two are within run-to-run noise at 4 GPUs)
-    // (B200VQ_AR_ALGO=1|2 forces either; both fit the same world x (lines + 2) receive buffers)
-    static const int forced = [] { const char* e = getenv("B200VQ_AR_ALGO"); return e == nullptr ? 0 : atoi(e); }();
-    const long long S = (lines + world - 1) / world;
-    const bool two_step = world >= 2 && 2 * S <= lines + 2 && (forced == 2 || (forced != 1 && world >= 8));   // always true: see the header
-    cudaError_t e;
-    if (two_step)
-        e = launch_pdl(allreduce_push2_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, pb,
-                       static_cast<float*>(multicast_or_null), world, rank, lines, S, payload, static_cast<long long>(n_floats), seq, out);
-    else
-        e = launch_pdl(allreduce_push_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, pb,
-                       static_cast<float*>(multicast_or_null), world, rank, lines, payload, static_cast<long long>(n_floats), seq, out);
-    if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of allreduce_push_kernel failed: %s", cudaGetErrorString(e));
-    LAUNCH_CHECK("allreduce_push_kernel");
-    return VQ_OK;
-}
-
-// backward + all-reduce fused (see backward_allreduce_kernel): the transfer overlaps the dz pass.
-int vq_backward_allreduce(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx,
-                          int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags, float* dz,
-                          float* payload, int64_t n_floats, const void* const* recv_buffers, void* multicast_or_null,
-                          int world, int rank, uint32_t seq, uint32_t* grid_sync, float* out, vq_stream_t stream) {
+int vq_step_backward(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx, int64_t n_rows,
+                     int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags, float* dz, float* dE,
+                     const void* workspace, size_t workspace_bytes, const float* reduced_sums, vq_stream_t stream) {
     if (int rc = check_device()) return rc;
     const long long N = n_rows;
-    if (z == nullptr || E == nullptr || idx == nullptr || dz == nullptr || payload == nullptr || out == nullptr ||
-        grid_sync == nullptr || recv_buffers == nullptr || K < 1 || D < 4 || D % 4 != 0 || N < 1 || n_rows_dz < 1 || n_rows_dE < 1 ||
-        world < 2 || world > AR_MAX_RANKS || rank < 0 || rank >= world || seq == 0 ||
-        n_floats < static_cast<int64_t>(K) * D || !(flags & VQ_FLAG_TRAIN_VQ))
-        return fail(VQ_ERR_ARG, "vq_backward_allreduce: bad argument (N=%lld K=%d D=%d world=%d rank=%d seq=%u flags=%d)", N, K, D, world,
-                    rank, seq, flags);
-    if (!aligned16(z) || !aligned16(dz) || !aligned16(payload) || !aligned16(E) || (g_q != nullptr && !aligned16(g_q)))
-        return fail(VQ_ERR_ARG, "vq_backward_allreduce: z / g_q / dz / E / payload must be 16-byte aligned");
-    PeerBuffers pb{};
-    for (int p = 0; p < world; ++p) {
-        if (recv_buffers[p] == nullptr || !aligned16(recv_buffers[p])) return fail(VQ_ERR_ARG, "vq_backward_allreduce: receive buffer %d is NULL or misaligned", p);
-        pb.buf[p] = static_cast<float*>(const_cast<void*>(recv_buffers[p]));
+    const bool train = (flags & VQ_FLAG_TRAIN_VQ) != 0 && dE != nullptr;
+    if (!(flags & VQ_FLAG_CODE_SUMS) || !train) {
+        if (reduced_sums != nullptr) return fail(VQ_ERR_ARG, "vq_step_backward: reduced_sums needs VQ_FLAG_CODE_SUMS | VQ_FLAG_TRAIN_VQ and dE");
+        return vq_backward(g_q, g_loss, z, E, idx, n_rows, n_rows_dz, n_rows_dE, K, D, beta, flags, dz, dE, stream);
     }
-    const long long lines = (n_floats + 1) / 2;
-    const long long S = (lines + world - 1) / world;
-    if (2 * S > lines + 2) return fail(VQ_ERR_ARG, "vq_backward_allreduce: payload too small for the two-step exchange");
+    if (z == nullptr || E == nullptr || idx == nullptr || K < 1 || D < 4 || D % 4 != 0 || N < 1 || n_rows_dz < 1 || n_rows_dE < 1 ||
+        workspace == nullptr)
+        return fail(VQ_ERR_ARG, "vq_step_backward: bad argument");
+    if (!aligned16(z) || !aligned16(E) || !aligned16(dE) || (dz != nullptr && !aligned16(dz)) || (g_q != nullptr && !aligned16(g_q)) ||
+        (reduced_sums != nullptr && !aligned16(reduced_sums)))
+        return fail(VQ_ERR_ARG, "vq_step_backward: z / g_q / dz / E / dE / reduced_sums must be 16-byte aligned");
+    const WsLayout w = ws_layout(N, K, D);
+    if (workspace_bytes < w.total) return fail(VQ_ERR_WORKSPACE, "vq_step_backward: workspace %zu B < %zu B", workspace_bytes, w.total);
+    const uint8_t* ws = static_cast<const uint8_t*>(workspace);
+    const float* sums_ws = reinterpret_cast<const float*>(ws + w.sums_off);
+    const unsigned int* counter = reinterpret_cast<const unsigned int*>(ws + w.counter_off);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float denom_dz = static_cast<float>(static_cast<double>(n_rows_dz) * static_cast<double>(D));
     const float denom_dE = static_cast<float>(static_cast<double>(n_rows_dE) * static_cast<double>(D));
-    const long long n_el = N * (D / 4);
-    // persistent and fully resident: the kernel has a grid barrier (and the all-reduce must not wait on unscheduled CTAs)
-    static const int occ = [] {
-        int a = 0, b = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, backward_allreduce_kernel<true>, 256, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, backward_allreduce_kernel<false>, 256, 0);
-        const int o = a < b ? a : b;
-        return o < 1 ? 1 : (o > 4 ? 4 : o);
-    }();
-    long long g = (n_el + 255) / 256;
-    if (g > static_cast<long long>(kNumSMs) * occ) g = static_cast<long long>(kNumSMs) * occ;
+    const long long n_el = dz != nullptr ? N * (D / 4) : 0;
+    long long g = (n_el + 511) / 512;                       // two 16-byte elements per thread
+    const long long g_min = (static_cast<long long>(K) * D / 4 + 255) / 256;
+    if (g < g_min) g = g_min;
+    if (g > static_cast<long long>(sm_count()) * 32) g = static_cast<long long>(sm_count()) * 32;
+    const int accumulate = (flags & VQ_FLAG_ZERO_DE) ? 0 : 1;
+    // VQ_FLAG_OVERLAP_EXCHANGE: our predecessor in the stream is the exchange, which we overlap (see backward_stream_kernel)
+    const int wait_first = (reduced_sums != nullptr && (flags & VQ_FLAG_OVERLAP_EXCHANGE)) ? 0 : 1;
     ProfScope prof(KID_BACKWARD, st);
-    cudaError_t e;
-    if (g_q != nullptr)
-        e = launch_pdl(backward_allreduce_kernel<true>, dim3(static_cast<unsigned>(g)), dim3(256), 0, st, g_q, g_loss, z, E, idx, N, denom_dz,
-                       denom_dE, D, beta, dz, payload, static_cast<long long>(n_floats), pb, static_cast<float*>(multicast_or_null), world, rank,
-                       lines, S, seq, grid_sync, out);
-    else
-        e = launch_pdl(backward_allreduce_kernel<false>, dim3(static_cast<unsigned>(g)), dim3(256), 0, st, g_q, g_loss, z, E, idx, N, denom_dz,
-                       denom_dE, D, beta, dz, payload, static_cast<long long>(n_floats), pb, static_cast<float*>(multicast_or_null), world, rank,
-                       lines, S, seq, grid_sync, out);
-    if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of backward_allreduce_kernel failed: %s", cudaGetErrorString(e));
-    LAUNCH_CHECK("backward_allreduce_kernel");
+    const cudaError_t e =
+        g_q != nullptr ? launch_pdl(backward_stream_kernel<true>, dim3(static_cast<unsigned>(g)), dim3(256), 0, st, g_q, g_loss, z, E, idx, N, denom_dz,
+                                    denom_dE, K, D, beta, dz, sums_ws, counter, reduced_sums, dE, accumulate, wait_first)
+                       : launch_pdl(backward_stream_kernel<false>, dim3(static_cast<unsigned>(g)), dim3(256), 0, st, g_q, g_loss, z, E, idx, N, denom_dz,
+                                    denom_dE, K, D, beta, dz, sums_ws, counter, reduced_sums, dE, accumulate, wait_first);
+    if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of backward_stream_kernel failed: %s", cudaGetErrorString(e));
+    LAUNCH_CHECK("backward_stream_kernel");
     return VQ_OK;
+}
+
+// =========================================================================================================
+// data parallel: exchange of [code sums | usage histogram | squared error] over NVLink peer memory
+// =========================================================================================================
+struct vq_dp_ctx {
+    DpCtxDev dev;
+    int device;
+};
+
+int vq_dp_create(const void* const* recv0, const void* const* recv1, void* multicast0, void* multicast1, int world, int rank,
+                 int64_t n_floats, uint32_t spin_limit, vq_dp_ctx** out) {
+    if (int rc = check_device()) return rc;
+    if (out == nullptr || recv0 == nullptr || recv1 == nullptr || world < 1 || world > DP_MAX_RANKS || rank < 0 || rank >= world || n_floats < 1)
+        return fail(VQ_ERR_ARG, "vq_dp_create: bad argument (world=%d rank=%d n=%lld)", world, rank, (long long)n_floats);
+    vq_dp_ctx* c = new (std::nothrow) vq_dp_ctx();
+    if (c == nullptr) return fail(VQ_ERR_ARG, "vq_dp_create: out of host memory");
+    memset(c, 0, sizeof(*c));
+    for (int p = 0; p < world; ++p) {
+        if (recv0[p] == nullptr || recv1[p] == nullptr || !aligned16(recv0[p]) || !aligned16(recv1[p])) {
+            delete c;
+            return fail(VQ_ERR_ARG, "vq_dp_create: receive buffer %d is NULL or misaligned", p);
+        }
+        c->dev.recv[0][p] = static_cast<float*>(const_cast<void*>(recv0[p]));
+        c->dev.recv[1][p] = static_cast<float*>(const_cast<void*>(recv1[p]));
+    }
+    const bool mc = multicast0 != nullptr && multicast1 != nullptr;
+    c->dev.mc[0] = mc ? static_cast<float*>(multicast0) : nullptr;
+    c->dev.mc[1] = mc ? static_cast<float*>(multicast1) : nullptr;
+    c->dev.world = world; c->dev.rank = rank;
+    c->dev.n = n_floats;
+    c->dev.L = (n_floats + 1) / 2;
+    c->dev.S = (c->dev.L + world - 1) / world;
+    // one step (every payload to every rank) below 8 ranks; reduce-scatter + all-gather from 8 ranks on, where the
+    // world x payload that one step lands in every rank costs more than a second NVLink latency (11.9 vs 14.8 us at 8 GPUs).
+    // B200VQ_AR_ALGO=1|2 forces either; both fit receive buffers of world x (L + 2) lines.
+    static const int forced = [] { const char* e = getenv("B200VQ_AR_ALGO"); return e == nullptr ? 0 : atoi(e); }();
+    c->dev.two_step = (world >= 2 && 2 * c->dev.S <= c->dev.L + 2 && (forced == 2 || (forced != 1 && world >= 8))) ? 1 : 0;
+    c->dev.spin_limit = spin_limit != 0 ? spin_limit : (1u << 23);     // a few seconds of polling
+    cudaGetDevice(&c->device);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->dev.state), 64);
+    if (e == cudaSuccess) e = cudaMemset(c->dev.state, 0, 64);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(VQ_ERR_CUDA, "vq_dp_create: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return VQ_OK;
+}
+
+void vq_dp_destroy(vq_dp_ctx* c) {
+    if (c == nullptr) return;
+    cudaFree(c->dev.state);
+    delete c;
+}
+
+int64_t vq_dp_recv_lines(int world, int64_t n_floats) { return static_cast<int64_t>(world) * ((n_floats + 1) / 2 + 2); }
+
+// synchronises `stream`; calls completed so far and the error word (bit 0: a wait ran into spin_limit)
+int vq_dp_status(vq_dp_ctx* c, uint32_t* calls_done, uint32_t* error_word, vq_stream_t stream) {
+    if (c == nullptr) return fail(VQ_ERR_ARG, "vq_dp_status: null");
+    unsigned int h[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(h, c->dev.state, sizeof(h), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    if (calls_done) *calls_done = h[0];
+    if (error_word) *error_word = h[1];
+    return VQ_OK;
+}
+
+static int dp_launch(vq_dp_ctx* c, const DpSource& src, float* out, cudaStream_t st) {
+    if (!aligned16(out)) return fail(VQ_ERR_ARG, "vq_dp: out is misaligned");
+    long long blocks = (c->dev.L + DP_THREADS - 1) / DP_THREADS;
+    const int cap = sm_count();
+    if (blocks > cap) blocks = cap;                          // no CTA waits for another CTA of this grid: no residency requirement
+    ProfScope prof(KID_ALLREDUCE, st);
+    const cudaError_t e = launch_pdl(dp_allreduce_kernel<true>, dim3(static_cast<unsigned>(blocks)), dim3(DP_THREADS), 0, st, c->dev, src, out);
+    if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of dp_allreduce_kernel failed: %s", cudaGetErrorString(e));
+    LAUNCH_CHECK("dp_allreduce_kernel");
+    return VQ_OK;
+}
+
+// out[i] = sum over ranks (rank order: bit-identical everywhere) of payload[i]
+int vq_dp_allreduce(vq_dp_ctx* c, const float* payload, float* out, vq_stream_t stream) {
+    if (c == nullptr || payload == nullptr || out == nullptr) return fail(VQ_ERR_ARG, "vq_dp_allreduce: null");
+    const DpSource src{payload, c->dev.n, nullptr, nullptr, 0};
+    return dp_launch(c, src, out, static_cast<cudaStream_t>(stream));
+}
+
+// the step's exchange: [code sums of the last vq_step_forward (in its workspace) | tail] -> out
+int vq_dp_exchange_sums(vq_dp_ctx* c, const void* workspace, size_t workspace_bytes, int64_t n_rows, int K, int D, const float* tail,
+                        int n_tail, float* out, vq_stream_t stream) {
+    if (c == nullptr || workspace == nullptr || out == nullptr || K < 1 || D < 1 || n_tail < 0 || (n_tail > 0 && tail == nullptr))
+        return fail(VQ_ERR_ARG, "vq_dp_exchange_sums: bad argument");
+    const long long kd = static_cast<long long>(K) * D;
+    if (c->dev.n != kd + n_tail) return fail(VQ_ERR_ARG, "vq_dp_exchange_sums: context holds %lld floats, K*D + n_tail = %lld", c->dev.n, kd + n_tail);
+    const WsLayout w = ws_layout(n_rows, K, D);
+    if (workspace_bytes < w.total) return fail(VQ_ERR_WORKSPACE, "vq_dp_exchange_sums: workspace %zu B < %zu B", workspace_bytes, w.total);
+    const uint8_t* ws = static_cast<const uint8_t*>(workspace);
+    const DpSource src{reinterpret_cast<const float*>(ws + w.sums_off), kd, tail, reinterpret_cast<const unsigned int*>(ws + w.counter_off), kd};
+    return dp_launch(c, src, out, static_cast<cudaStream_t>(stream));
+}
+
+// Single-GPU emulation of `world` ranks for the tests: ONE cooperative launch in which blockIdx.y plays the rank, all
+// ranks' receive buffers living on this GPU (plain stores instead of NVLink; no multicast).  payloads / outs: host arrays
+// of `world` device pointers.  Runs `rounds` calls back to back (buffer parity, sequence numbers).
+int vq_dp_emulate(int world, int two_step, int64_t n_floats, const float* const* payloads, float* const* outs, int rounds,
+                  uint32_t spin_limit, uint32_t* error_word, vq_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    if (world < 1 || world > DP_MAX_RANKS || n_floats < 1 || payloads == nullptr || outs == nullptr || rounds < 1)
+        return fail(VQ_ERR_ARG, "vq_dp_emulate: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long L = (n_floats + 1) / 2, S = (L + world - 1) / world;
+    if (two_step && 2 * S > L + 2) return fail(VQ_ERR_ARG, "vq_dp_emulate: payload too small for two steps");
+    const size_t buf_bytes = static_cast<size_t>(world) * (L + 2) * 16;
+    uint8_t* pool = nullptr;
+    const size_t pool_bytes = 2 * world * buf_bytes + world * 64 + world * sizeof(DpCtxDev) + 2 * world * sizeof(void*);
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&pool), pool_bytes));
+    int rc = VQ_OK;
+    do {
+        if (cudaMemsetAsync(pool, 0, pool_bytes, st) != cudaSuccess) { rc = fail(VQ_ERR_CUDA, "vq_dp_emulate: memset failed"); break; }
+        uint8_t* states = pool + 2 * world * buf_bytes;
+        DpCtxDev* d_ctx = reinterpret_cast<DpCtxDev*>(states + world * 64);
+        const float** d_pay = reinterpret_cast<const float**>(d_ctx + world);
+        float** d_out = const_cast<float**>(d_pay + world);
+        std::vector<DpCtxDev> h(world);
+        for (int r = 0; r < world; ++r) {
+            memset(&h[r], 0, sizeof(DpCtxDev));
+            for (int par = 0; par < 2; ++par)
+                for (int p = 0; p < world; ++p) h[r].recv[par][p] = reinterpret_cast<float*>(pool + (static_cast<size_t>(par) * world + p) * buf_bytes);
+            h[r].state = reinterpret_cast<unsigned int*>(states + r * 64);
+            h[r].L = L; h[r].S = S; h[r].n = n_floats; h[r].world = world; h[r].rank = r; h[r].two_step = two_step ? 1 : 0;
+            h[r].spin_limit = spin_limit != 0 ? spin_limit : (1u << 22);
+        }
+        if (cudaMemcpyAsync(d_ctx, h.data(), world * sizeof(DpCtxDev), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(d_pay, payloads, world * sizeof(void*), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(d_out, outs, world * sizeof(void*), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { rc = fail(VQ_ERR_CUDA, "vq_dp_emulate: setup copies failed"); break; }
+        long long blocks = (L + DP_THREADS - 1) / DP_THREADS;
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_emulate_kernel<true>, DP_THREADS, 0);
+        const long long cap = static_cast<long long>(per_sm < 1 ? 1 : per_sm) * sm_count() / world;   // all ranks resident at once
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) { rc = fail(VQ_ERR_ARG, "vq_dp_emulate: world too large for a cooperative launch"); break; }
+        const DpCtxDev* a0 = d_ctx; const float* const* a1 = d_pay; float* const* a2 = d_out;
+        void* args[] = {&a0, &a1, &a2};
+        for (int i = 0; i < rounds && rc == VQ_OK; ++i) {
+            const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(dp_emulate_kernel<true>),
+                                                              dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(world)), dim3(DP_THREADS), args, 0, st);
+            if (e != cudaSuccess) rc = fail(VQ_ERR_CUDA, "vq_dp_emulate: cooperative launch failed: %s", cudaGetErrorString(e));
+            else g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        if (rc != VQ_OK) break;
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc = fail(VQ_ERR_CUDA, "vq_dp_emulate: kernel failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        unsigned int err = 0;
+        for (int r = 0; r < world; ++r) {
+            unsigned int hs[2];
+            if (cudaMemcpy(hs, states + r * 64, sizeof(hs), cudaMemcpyDeviceToHost) != cudaSuccess) { rc = fail(VQ_ERR_CUDA, "vq_dp_emulate: readback failed"); break; }
+            err |= hs[1];
+            if (hs[0] != static_cast<unsigned int>(rounds)) err |= 0x100u;      // the call counter did not advance once per round
+        }
+        if (error_word) *error_word = err;
+    } while (false);
+    cudaFree(pool);
+    return rc;
 }
 
 // fc_1(one_hot) as an index gather (location_model.py:10,21; train_location.py:74-75).
@@ -943,6 +1069,7 @@ int vq_host_ctx_create(int64_t max_rows, int K, int D, vq_host_ctx** out) {
         A(reinterpret_cast<void**>(&l.idx), sizeof(int32_t) * max_rows);
         l.ws_bytes = vq_workspace_bytes(max_rows, K, D, 0);
         A(&l.ws, l.ws_bytes);
+        if (e == cudaSuccess) e = cudaMemsetAsync(l.ws, 0, l.ws_bytes, l.st);      // vq_workspace_init
     }
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_start);
     if (e != cudaSuccess) {
@@ -959,8 +1086,7 @@ int vq_host_set_codebook(vq_host_ctx* c, const float* E_host) {
     if (c == nullptr || E_host == nullptr) return fail(VQ_ERR_ARG, "vq_host_set_codebook: null");
     cudaStream_t st = c->lane[0].st;
     CUDA_TRY(cudaMemcpyAsync(c->E, E_host, sizeof(float) * c->K * c->D, cudaMemcpyHostToDevice, st));
-    if (int rc = vq_prepare_codebook(c->E, c->K, c->D, c->e_norm2, c->E_hi, c->E_lo, st)) return rc;
-    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaStreamSynchronize(st));      // every step prepares the codebook itself (vq_step_forward)
     return VQ_OK;
 }
 
@@ -981,13 +1107,20 @@ int vq_host_step_async(vq_host_ctx* c, int lane, const float* z_host, const floa
         LAUNCH_CHECK("fill_kernel");
         l.gq_is_ones = true;
     }
-    if (int rc = vq_forward(l.z, c->E, c->e_norm2, c->E_hi, c->E_lo, n_rows, c->K, c->D, beta, flags & ~(VQ_FLAG_ONEHOT | VQ_FLAG_DEFER_STATS | VQ_FLAG_NO_QUANT),
-                            l.q, l.idx, nullptr, l.hist, l.scal + 0, l.scal + 1, l.scal + 2, l.ws, l.ws_bytes, l.st))
+    // prepare + forward in one entry (one launch on the screen path); with a training codebook the forward also
+    // accumulates the code sums and the backward is the streaming pass.  Both lanes share the codebook scratch: a lane's
+    // forward rewrites e_norm2 / E_hi / E_lo with the values the other lane's kernels may be reading -- identical bits.
+    const int sums = train ? VQ_FLAG_CODE_SUMS : 0;
+    const int keep = VQ_FLAG_EXACT | VQ_FLAG_NO_SCREEN | VQ_FLAG_SCREEN | VQ_FLAG_NO_FUSE | VQ_FLAG_TC_1CTA;
+    if (int rc = vq_step_forward(l.z, c->E, n_rows, c->K, c->D, beta, (flags & keep) | sums, c->e_norm2, c->E_hi, c->E_lo, l.q, l.idx, nullptr, l.hist,
+                                 l.scal + 0, l.scal + 1, l.scal + 2, l.ws, l.ws_bytes, l.st))
         return rc;
     // gq_host == NULL: the lane's g_q buffer still holds the ones written at context creation, i.e. the
     // `(loss + quantized.sum()).backward()` workload; the kernel reads it like any upstream gradient.
-    if (int rc = vq_backward(l.gq, nullptr, l.z, c->E, l.idx, n_rows, n_rows, n_rows_dE > 0 ? n_rows_dE : n_rows, c->K, c->D, beta, flags | VQ_FLAG_ZERO_DE, l.dz,
-                             train ? l.dE : nullptr, l.st))
+    const int use_sums = vq_step_uses_code_sums(n_rows, c->K, c->D, (flags & keep) | sums) ? VQ_FLAG_CODE_SUMS : 0;
+    if (int rc = vq_step_backward(l.gq, nullptr, l.z, c->E, l.idx, n_rows, n_rows, n_rows_dE > 0 ? n_rows_dE : n_rows, c->K, c->D, beta,
+                                  (flags & (VQ_FLAG_TRAIN_VQ | VQ_FLAG_BWD_FLAT | VQ_FLAG_BWD_PRIVATE)) | VQ_FLAG_ZERO_DE | use_sums, l.dz,
+                                  train ? l.dE : nullptr, l.ws, l.ws_bytes, nullptr, l.st))
         return rc;
     if (loss_host) CUDA_TRY(cudaMemcpyAsync(loss_host, l.scal + 1, sizeof(float), cudaMemcpyDeviceToHost, l.st));
     if (perplexity_host) CUDA_TRY(cudaMemcpyAsync(perplexity_host, l.scal + 2, sizeof(float), cudaMemcpyDeviceToHost, l.st));

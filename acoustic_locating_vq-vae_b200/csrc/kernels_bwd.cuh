@@ -1,53 +1,26 @@
-// kernels_bwd.cuh -- backward of the VQ hot path (autograd of vector_quantizer.py:46-54) without one global
-// atomic per element.
+// kernels_bwd.cuh -- backward of the VQ hot path (autograd of vector_quantizer.py:46-54).
 //
 //   dz[n,:]  = g_q[n,:] - cz * (E[idx[n]] - z[n])          cz = g_loss * beta * 2 / (n_rows_dz * D)
 //   dE[k,:]  = ce * sum_{n : idx[n] == k} (E[k] - z[n])     ce = g_loss * 2 / (n_rows_dE * D)
 //
-// The flat kernel in kernels_simt.cuh issues one 16-byte red.global.add per 16-byte element of z: at the RIR-256
-// shape that is 823 k atomics on 16 k addresses and the LSU's atomic issue rate (not HBM) sets the time.  Two
-// kernels replace it, chosen by the launcher:
-//
-//   backward_bucket_kernel   N up to a few 100 k rows.  The grid has two roles that share nothing but inputs:
-//       * code owners (the first BK_NB CTAs): CTA j owns the codes k with k % BK_NB == j.  It scans idx once
-//         (L2-resident, 4 bytes per row), collects the rows of its codes in shared memory, sorts them by code
-//         (counting sort) and sums (E[k] - z[n]) per code with warp-wide coalesced row reads from L2 into
-//         REGISTERS; every dE element has exactly one writer -> plain stores, no zeroing, no global atomics, and
-//         under data parallelism the owner can send its rows straight to the peers (kernels_dp.cuh).
-//       * dz streamers (the other CTAs): the HBM-bound pass over z / g_q / dz, no atomics.
-//   backward_private_kernel  N >> K.  Persistent CTAs keep a PRIVATE copy of (a column slice of) dE in shared
-//       memory; rows are bucketed by code inside a chunk so that every table row has one owning warp (plain
-//       shared-memory read-modify-write, no atomics) and the table is flushed once per CTA with 16-byte reds.
+// Where the scatter-add into dE happens decides the cost: the flat kernel in kernels_simt.cuh issues one 16-byte
+// red.global.add per 16-byte element of z (823 k atomics on 16 k addresses at the RIR-256 shape: 11.0 us against
+// 7.7 us for the dz pass alone).
+//   backward_stream_kernel   the step path: the FORWARD accumulated the code sums S_k = sum (E_k - z_n) in its row
+//       epilogue (E[idx] - z is in registers there and the kernel is bound by the one-hot write), so the backward is
+//       the pure streaming dz pass plus dE = ce * S.  Under data parallelism S is exchanged right after the forward
+//       and the exchange runs concurrently with this kernel.
+//   backward_private_kernel  N >> K without code sums (e.g. the indices-only sweep): persistent CTAs keep a PRIVATE
+//       copy of (a column slice of) dE in shared memory; rows are bucketed by code inside a window so that every
+//       table row has one owning warp (plain shared-memory read-modify-write, no atomics) and the table is flushed
+//       once per CTA with 16-byte reds.
+// Measured and dropped (round 2): code-owner CTAs that scan idx, sort their rows and sum them in registers next to
+// the dz streamers in one grid (no atomics, single writer per dE element).  The owners' latency-bound chains (idx
+// scan, sort, row batches) stall while the streamers saturate the memory system: 45 - 65 us against 11 us flat.
 #pragma once
 #include "common.cuh"
 
 namespace b200vq {
-
-constexpr int BK_THREADS = 512;
-constexpr int BK_WARPS = BK_THREADS / 32;
-constexpr int BK_NB = 128;        // code-owner CTAs; code k belongs to CTA (k & 127), local code = k >> 7
-constexpr int BK_NB_LOG2 = 7;
-constexpr int BK_LIST = 4096;     // rows collected before a flush (a scan pass adds at most BK_THREADS * 4)
-constexpr int BK_TABLE = 2048;    // floats: ceil(K / BK_NB) * D must fit
-constexpr int BK_MAXLC = 64;      // local codes per owner CTA (K <= 8192)
-constexpr int BK_DZ_EPT = 4;      // 16-byte elements per dz-streamer thread
-
-// what an owner does with a finished dE row: `vals[i]` is element d = lane + 32 * i of row `code`
-struct StoreDE {
-    float* dE;
-    int D;
-    bool accumulate;              // false: dE is overwritten (VQ_FLAG_ZERO_DE semantics without a memset)
-    template <int NI>
-    __device__ __forceinline__ void row(int code, int lane, const float (&vals)[NI]) const {
-        float* dst = dE + static_cast<size_t>(code) * D;
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-            const int d = lane + 32 * i;
-            if (d < D) dst[d] = accumulate ? dst[d] + vals[i] : vals[i];
-        }
-    }
-    __device__ __forceinline__ void finish(int /*owner*/, int /*tid*/) const {}
-};
 
 // ---------------------------------------------------------------------------------------------
 // dz pass over elements [e_begin, e_end) with a stride: two independent 16-byte elements in flight per thread
@@ -89,178 +62,48 @@ __device__ __forceinline__ void dz_stream(const float* __restrict__ g_q, const f
 
 // ---------------------------------------------------------------------------------------------
 // code owner: see the header.  NI = ceil(D / 32) floats per lane and row (lane l holds d = l + 32 i).
+// The owner code runs once per CTA, so its size is what it costs (instruction fetch): the rare paths are kept
+// out of line and there is a single flush site.
 // ---------------------------------------------------------------------------------------------
-template <int NI, typename Sink>
-__device__ __forceinline__ void bucket_owner(const float* __restrict__ z, const float* __restrict__ E, const int* __restrict__ idx,
-                                             long long N, int K, int D, float ce, int owner, const Sink& sink) {
-    __shared__ int s_list[BK_LIST];        // row | local code << 24, in arrival order
-    __shared__ int s_sorted[BK_LIST];      // rows, grouped by local code
-    __shared__ float s_table[BK_TABLE];    // [local code][D] running sums
-    __shared__ int s_cnt[BK_MAXLC];        // entries per local code in s_list
-    __shared__ int s_off[BK_MAXLC + 1];    // exclusive prefix of s_cnt
-    __shared__ int s_fill[BK_MAXLC];
-    __shared__ int s_n;
-    __shared__ int s_flush;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ncl = (K + BK_NB - 1) >> BK_NB_LOG2;
-    for (int i = tid; i < ncl * D; i += BK_THREADS) s_table[i] = 0.0f;
-    if (tid < BK_MAXLC) s_cnt[tid] = 0;
-    if (tid == 0) s_n = 0;
-    __syncthreads();
-
-    auto append = [&](int code, long long row) {
-        if ((code & (BK_NB - 1)) == owner && static_cast<unsigned>(code) < static_cast<unsigned>(K)) {
-            const int lc = code >> BK_NB_LOG2;
-            const int pos = atomicAdd(&s_n, 1);
-            s_list[pos] = static_cast<int>(row) | (lc << 24);
-            atomicAdd(&s_cnt[lc], 1);
-        }
-    };
-
-    // sums the rows collected so far into s_table and empties the list; called by the whole CTA
-    auto flush = [&]() {
-        const int n = s_n;
-        if (warp == 0) {                                    // exclusive scan over <= 64 local codes
-            int a = lane < ncl ? s_cnt[lane] : 0;
-            int b = lane + 32 < ncl ? s_cnt[lane + 32] : 0;
-            int ia = a, ib = b;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
-                if (lane >= o) { ia += ta; ib += tb; }
-            }
-            const int tot_a = __shfl_sync(0xffffffffu, ia, 31);
-            s_off[lane] = ia - a;
-            s_off[lane + 32] = tot_a + ib - b;
-            s_fill[lane] = 0;
-            s_fill[lane + 32] = 0;
-            if (lane == 0) s_off[BK_MAXLC] = n;
-        }
-        __syncthreads();
-        for (int i = tid; i < n; i += BK_THREADS) {         // counting sort: scatter by local code
-            const int en = s_list[i];
-            const int lc = en >> 24;
-            s_sorted[s_off[lc] + atomicAdd(&s_fill[lc], 1)] = en;
-        }
-        __syncthreads();
-        // every warp takes an equal share of the sorted rows; a run of one code accumulates in registers
-        const int lo = static_cast<int>(static_cast<long long>(n) * warp / BK_WARPS);
-        const int hi = static_cast<int>(static_cast<long long>(n) * (warp + 1) / BK_WARPS);
-        constexpr int RB = NI <= 2 ? 8 : (NI <= 4 ? 4 : 2);   // rows in flight per warp
-        float acc[NI], er[NI];
-        int cur = -1;
-#pragma unroll
-        for (int i = 0; i < NI; ++i) acc[i] = er[i] = 0.0f;
-        auto spill = [&]() {
-            if (cur >= 0) {
-#pragma unroll
-                for (int i = 0; i < NI; ++i) {
-                    const int d = lane + 32 * i;
-                    if (d < D) atomicAdd(&s_table[cur * D + d], acc[i]);
-                }
-            }
-        };
-        for (int p0 = lo; p0 < hi; p0 += RB) {
-            float zv[RB][NI];
-            int ent[RB];
-#pragma unroll
-            for (int u = 0; u < RB; ++u) {
-                ent[u] = p0 + u < hi ? s_sorted[p0 + u] : -1;
-                if (ent[u] >= 0) {
-                    const float* zr = z + static_cast<long long>(ent[u] & 0xffffff) * D;
-#pragma unroll
-                    for (int i = 0; i < NI; ++i) {
-                        const int d = lane + 32 * i;
-                        zv[u][i] = d < D ? __ldg(zr + d) : 0.0f;
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < RB; ++u) {
-                if (ent[u] >= 0) {
-                    const int lc = ent[u] >> 24;
-                    if (lc != cur) {                        // warp-uniform: a new run starts
-                        spill();
-                        cur = lc;
-                        const float* erow = E + static_cast<size_t>((lc << BK_NB_LOG2) + owner) * D;
-#pragma unroll
-                        for (int i = 0; i < NI; ++i) {
-                            const int d = lane + 32 * i;
-                            er[i] = d < D ? __ldg(erow + d) : 0.0f;
-                            acc[i] = 0.0f;
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < NI; ++i) acc[i] += er[i] - zv[u][i];
-                }
-            }
-        }
-        spill();
-        __syncthreads();
-        if (tid < BK_MAXLC) s_cnt[tid] = 0;
-        if (tid == 0) s_n = 0;
-        __syncthreads();
-    };
-
-    // ---- scan idx: 4 rows per thread and pass, the next pass's load in flight while this one is filed ----
-    const long long n4 = N >> 2;
-    const int4* idx4 = reinterpret_cast<const int4*>(idx);
-    long long p = tid;
-    int4 nxt = p < n4 ? __ldg(idx4 + p) : make_int4(-1, -1, -1, -1);
-    for (long long base = 0; base < n4; base += BK_THREADS) {
-        const int4 cur4 = nxt;
-        const long long pn = base + BK_THREADS + tid;
-        nxt = pn < n4 ? __ldg(idx4 + pn) : make_int4(-1, -1, -1, -1);
-        const long long r0 = (base + tid) << 2;
-        if (base + tid < n4) {
-            append(cur4.x, r0);
-            append(cur4.y, r0 + 1);
-            append(cur4.z, r0 + 2);
-            append(cur4.w, r0 + 3);
-        }
-        __syncthreads();
-        if (tid == 0) s_flush = s_n > BK_LIST - 4 * BK_THREADS ? 1 : 0;   // the next pass could overflow the list
-        __syncthreads();
-        if (s_flush) flush();                               // uniform: written once between two barriers
-    }
-    {
-        const long long r = (n4 << 2) + tid;                // the N % 4 tail rows
-        if (r < N) append(__ldg(idx + r), r);
-        __syncthreads();
-    }
-    flush();
-
-    // ---- hand the owned rows over (every element exactly once) ----
-    for (int lc = warp; lc < ncl; lc += BK_WARPS) {
-        const int code = (lc << BK_NB_LOG2) + owner;
-        if (code < K) {
-            float vals[NI];
-#pragma unroll
-            for (int i = 0; i < NI; ++i) {
-                const int d = lane + 32 * i;
-                vals[i] = d < D ? ce * s_table[lc * D + d] : 0.0f;
-            }
-            sink.template row<NI>(code, lane, vals);
-        }
-    }
-    sink.finish(owner, tid);
-}
-
-template <bool HAS_GQ, int NI, typename Sink>
-__global__ void __launch_bounds__(BK_THREADS, 2)
-backward_bucket_kernel(const float* __restrict__ g_q, const float* __restrict__ g_loss, const float* __restrict__ z,
-                       const float* __restrict__ E, const int* __restrict__ idx, long long N, float denom_dz, float denom_dE, int K,
-                       int D, float beta, float* __restrict__ dz, const Sink sink) {
+// ---------------------------------------------------------------------------------------------
+// backward_stream_kernel: the backward when the forward already accumulated the code sums
+//   S_k = sum_{n : idx_n = k} (E_k - z_n)                       (vq_step_forward with VQ_FLAG_CODE_SUMS)
+// in its row epilogue, where E[idx] - z sits in registers anyway.  What is left is a pure streaming pass
+//   dz = g_q - cz * (E[idx] - z)
+// and dE = ce * S over K*D elements.  Under data parallelism S (with the usage histogram and the squared error) is
+// exchanged right after the FORWARD (none of it depends on upstream gradients), so the exchange kernel is this
+// kernel's predecessor in the stream and runs concurrently with the dz pass: with wait_first == 0 the pass starts
+// without waiting for it (the exchange triggers this launch only after it has itself seen the forward complete) and
+// the kernel orders itself behind the exchange just before it reads the reduced sums.
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_GQ>
+__global__ void __launch_bounds__(256) backward_stream_kernel(const float* __restrict__ g_q, const float* __restrict__ g_loss,
+                                                              const float* __restrict__ z, const float* __restrict__ E,
+                                                              const int* __restrict__ idx, long long N, float denom_dz, float denom_dE,
+                                                              int K, int D, float beta, float* __restrict__ dz,
+                                                              const float* sums_ws, const unsigned int* counter, const float* reduced,
+                                                              float* __restrict__ dE, int accumulate, int wait_first) {
+    if (wait_first) pdl_wait_prior_grids();
     pdl_launch_dependents();
-    pdl_wait_prior_grids();
     const float gl = g_loss != nullptr ? __ldg(g_loss) : 1.0f;
-    if (blockIdx.x < BK_NB) {
-        bucket_owner<NI>(z, E, idx, N, K, D, gl * 2.0f / denom_dE, static_cast<int>(blockIdx.x), sink);
-    } else if (dz != nullptr) {
-        const long long n_el = N * (D >> 2);
-        const long long nthreads = static_cast<long long>(gridDim.x - BK_NB) * BK_THREADS;
-        dz_stream<HAS_GQ>(g_q, z, E, idx, dz, K, D, gl * beta * 2.0f / denom_dz,
-                          static_cast<long long>(blockIdx.x - BK_NB) * BK_THREADS + threadIdx.x, n_el, nthreads);
+    const long long nthreads = static_cast<long long>(gridDim.x) * 256;
+    const long long first = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (dz != nullptr) dz_stream<HAS_GQ>(g_q, z, E, idx, dz, K, D, gl * beta * 2.0f / denom_dz, first, N * (D >> 2), nthreads);
+    if (!wait_first) pdl_wait_prior_grids();
+    if (dE != nullptr) {
+        const float ce = gl * 2.0f / denom_dE;
+        const size_t kd = static_cast<size_t>(K) * D;
+        // single GPU: the buffer the last forward call filled (the call counter has been advanced past it)
+        const float* S = reduced != nullptr ? reduced : sums_ws + ((__ldcg(counter + 1) - 1u) & 1u) * kd;
+        for (size_t i = first; i < kd / 4; i += nthreads) {
+            float4 v = __ldcg(reinterpret_cast<const float4*>(S) + i);
+            v.x *= ce; v.y *= ce; v.z *= ce; v.w *= ce;
+            if (accumulate) {
+                const float4 o = reinterpret_cast<const float4*>(dE)[i];
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            reinterpret_cast<float4*>(dE)[i] = v;
+        }
     }
 }
 

@@ -1,0 +1,272 @@
+// kernels_dp.cuh -- data-parallel exchange of the packed step buffer [dE (K*D) | usage histogram (K) | sse (1)]
+// over NVLink peer memory (the one collective of the path; the reference has none -- DDP
+// would all-reduce `_embedding.weight.grad` after backward).
+//
+// Every rank owns two symmetric RECEIVE buffers (alternating between calls).  Data travels as 16-byte lines
+// {d0, seq, d1, seq}: payload and the call's sequence number in the same store, so a line whose two flag words
+// carry `seq` is complete (16-byte stores may tear only at 8-byte granularity) -- no barrier, no second message.
+//   one step  (world < 8): every rank stores line i into slot [rank] of EVERY rank's buffer (one multimem.st when
+//             the NVLS multicast mapping exists), then sums its own `world` slots in rank order.
+//   two steps (world >= 8): rank j owns slice j; (1) line i goes to slot [rank] of region A of its owner,
+//             (2) the owner sums its slots in rank order and stores the result into region B of every rank,
+//             (3) everybody collects region B.  2 x payload instead of world x payload lands in each rank.
+// Sums run in rank order, so the result is bit-identical on every rank.
+//
+// The sequence number lives in DEVICE memory (state[0] = calls completed): the kernels derive buffer parity and
+// `seq` from it and the last CTA of the finishing kernel advances it, so a captured CUDA graph can be replayed
+// and no host state has to stay in step with the device.  Every wait is bounded: after `spin_limit` polls a
+// thread raises state[1] and the kernel drains without waiting any further (results are then garbage, the host
+// reads the error word with vq_dp_status).
+//
+// Everything the exchange carries -- code sums S (the codebook gradient up to a scalar), usage histogram, squared
+// error -- is produced by the FORWARD, so the exchange is launched right behind it and runs concurrently with the
+// backward's dz pass (backward_stream_kernel waits for it only before it reads the reduced sums).
+#pragma once
+#include "common.cuh"
+
+namespace b200vq {
+
+constexpr int DP_MAX_RANKS = 16;
+constexpr int DP_THREADS = 256;
+
+struct DpCtxDev {
+    float* recv[2][DP_MAX_RANKS];   // [parity][rank]: that rank's receive buffer as mapped into this process
+    float* mc[2];                   // NVLS multicast mapping of the same buffers, or nullptr
+    unsigned int* state;            // [0] calls completed, [1] error word, [2] finishing-CTA counter
+    long long L;                    // 16-byte lines per payload = ceil(n / 2)
+    long long S;                    // two steps: lines per owner slice = ceil(L / world)
+    long long n;                    // payload floats
+    int world, rank;
+    int two_step;
+    unsigned int spin_limit;
+};
+
+// where the local contribution comes from: `n_main` floats at `main` (optionally one of two buffers `stride` floats
+// apart, chosen by the forward's call counter: the code sums in its workspace), then the rest of the payload at `tail`
+struct DpSource {
+    const float* main;
+    long long n_main;
+    const float* tail;
+    const unsigned int* counter;     // not NULL: main += ((counter[1] - 1) & 1) * stride
+    long long stride;
+    __device__ __forceinline__ const float* resolve() const {
+        return counter != nullptr ? main + ((__ldcg(counter + 1) - 1u) & 1u) * stride : main;
+    }
+    __device__ __forceinline__ float at(const float* m, long long f) const { return f < n_main ? __ldcg(m + f) : __ldcg(tail + (f - n_main)); }
+};
+
+struct DpCall {
+    int which;                      // receive-buffer parity of this call
+    unsigned int seq;               // per-buffer sequence number (never 0)
+};
+
+__device__ __forceinline__ DpCall dp_begin(const DpCtxDev& c) {
+    const unsigned int s = __ldcg(c.state) + 1u;      // L2: the previous call's last CTA advanced it with an atomic
+    DpCall k;
+    k.which = static_cast<int>((s - 1u) & 1u);
+    k.seq = (s + 1u) >> 1;
+    return k;
+}
+
+__device__ __forceinline__ void st_volatile_v4(uint4* p, uint4 v) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// one store, delivered by the NVSwitch to the same offset of EVERY rank's buffer (NVLS multicast mapping)
+__device__ __forceinline__ void multimem_st_v4(void* mc_addr, uint4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
+}
+
+// store a line at line offset `off` of every rank's receive buffer
+__device__ __forceinline__ void dp_store_all(const DpCtxDev& c, int which, long long off, uint4 line) {
+    if (c.mc[which] != nullptr) {
+        multimem_st_v4(reinterpret_cast<uint4*>(c.mc[which]) + off, line);
+    } else {
+        for (int p = 0; p < c.world; ++p) {
+            const int dst = (c.rank + p) % c.world;     // spread the ranks' first targets over the links
+            st_volatile_v4(reinterpret_cast<uint4*>(c.recv[which][dst]) + off, line);
+        }
+    }
+}
+
+// first hop of line i of the local payload
+__device__ __forceinline__ void dp_push_line(const DpCtxDev& c, const DpCall& k, long long i, float d0, float d1) {
+    const uint4 line = make_uint4(__float_as_uint(d0), k.seq, __float_as_uint(d1), k.seq);
+    if (c.two_step) {
+        const long long j = i / c.S, l = i - j * c.S;
+        st_volatile_v4(reinterpret_cast<uint4*>(c.recv[k.which][j]) + static_cast<long long>(c.rank) * c.S + l, line);
+    } else {
+        dp_store_all(c, k.which, static_cast<long long>(c.rank) * c.L + i, line);
+    }
+}
+
+// bounded wait for a line: false (and the error word raised) when it did not arrive within spin_limit polls
+struct DpWaiter {
+    const DpCtxDev& c;
+    int* s_abort;                    // shared: some thread of this CTA gave up
+    __device__ __forceinline__ bool wait(const uint4* p, unsigned int seq, uint4& v) const {
+        unsigned int polls = 0;
+        while (v.y != seq || v.w != seq) {
+            if (++polls > c.spin_limit || *reinterpret_cast<volatile int*>(s_abort) != 0) {
+                if (*reinterpret_cast<volatile int*>(s_abort) == 0) {
+                    *reinterpret_cast<volatile int*>(s_abort) = 1;
+                    atomicOr(c.state + 1, 1u);
+                }
+                return false;
+            }
+            v = ld_volatile_v4(p);
+        }
+        return true;
+    }
+};
+
+// one step: sum our `world` slots in rank order as the lines arrive
+__device__ __forceinline__ void dp_collect_one_step(const DpCtxDev& c, const DpCall& k, const DpWaiter& w, float* __restrict__ out,
+                                                    long long first, long long stride) {
+    const uint4* mine = reinterpret_cast<const uint4*>(c.recv[k.which][c.rank]);
+    for (long long i = first; i < c.L; i += stride) {
+        uint4 v[DP_MAX_RANKS];
+#pragma unroll
+        for (int p = 0; p < DP_MAX_RANKS; ++p)
+            if (p < c.world) v[p] = ld_volatile_v4(mine + static_cast<long long>(p) * c.L + i);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int p = 0; p < DP_MAX_RANKS; ++p) {
+            if (p < c.world) {
+                w.wait(mine + static_cast<long long>(p) * c.L + i, k.seq, v[p]);
+                a0 += __uint_as_float(v[p].x);
+                a1 += __uint_as_float(v[p].z);
+            }
+        }
+        out[2 * i] = a0;
+        if (2 * i + 1 < c.n) out[2 * i + 1] = a1;
+    }
+}
+
+// two steps, (2): reduce our own slice in rank order and broadcast it into region B of every rank
+__device__ __forceinline__ void dp_reduce_bcast(const DpCtxDev& c, const DpCall& k, const DpWaiter& w, long long first, long long stride) {
+    const uint4* mine = reinterpret_cast<const uint4*>(c.recv[k.which][c.rank]);
+    const long long own = min(c.S, c.L - static_cast<long long>(c.rank) * c.S);
+    const long long b_off = static_cast<long long>(c.world) * c.S + static_cast<long long>(c.rank) * c.S;
+    for (long long l = first; l < own; l += stride) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int p0 = 0; p0 < c.world; p0 += 8) {           // 8 slots requested together, summed in rank order
+            uint4 v[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p)
+                if (p0 + p < c.world) v[p] = ld_volatile_v4(mine + static_cast<long long>(p0 + p) * c.S + l);
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                if (p0 + p < c.world) {
+                    w.wait(mine + static_cast<long long>(p0 + p) * c.S + l, k.seq, v[p]);
+                    a0 += __uint_as_float(v[p].x);
+                    a1 += __uint_as_float(v[p].z);
+                }
+            }
+        }
+        dp_store_all(c, k.which, b_off + l, make_uint4(__float_as_uint(a0), k.seq, __float_as_uint(a1), k.seq));
+    }
+}
+
+// two steps, (3): region B is owner-major with S lines per owner, so reduced line i sits at offset i
+__device__ __forceinline__ void dp_gather(const DpCtxDev& c, const DpCall& k, const DpWaiter& w, float* __restrict__ out, long long first,
+                                          long long stride) {
+    const uint4* gathered = reinterpret_cast<const uint4*>(c.recv[k.which][c.rank]) + static_cast<long long>(c.world) * c.S;
+    for (long long i0 = first; i0 < c.L; i0 += 4 * stride) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < c.L) v[u] = ld_volatile_v4(gathered + i);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < c.L) {
+                w.wait(gathered + i, k.seq, v[u]);
+                out[2 * i] = __uint_as_float(v[u].x);
+                if (2 * i + 1 < c.n) out[2 * i + 1] = __uint_as_float(v[u].z);
+            }
+        }
+    }
+}
+
+// body shared by the production kernel (one rank per launch) and the single-GPU emulation (one rank per blockIdx.y)
+template <bool PUSH>
+__device__ __forceinline__ void dp_allreduce_body(const DpCtxDev& c, const DpSource& src, float* __restrict__ out, int* s_abort) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long first = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (threadIdx.x == 0) *s_abort = 0;
+    __syncthreads();
+    const DpCall k = dp_begin(c);
+    const DpWaiter w{c, s_abort};
+    if (PUSH) {
+        const float* m = src.resolve();
+        for (long long i = first; i < c.L; i += stride) {
+            const float d0 = src.at(m, 2 * i);
+            const float d1 = (2 * i + 1 < c.n) ? src.at(m, 2 * i + 1) : 0.0f;
+            dp_push_line(c, k, i, d0, d1);
+        }
+    }
+    if (c.two_step) {
+        dp_reduce_bcast(c, k, w, first, stride);
+        dp_gather(c, k, w, out, first, stride);
+    } else {
+        dp_collect_one_step(c, k, w, out, first, stride);
+    }
+}
+
+// the last CTA to finish advances the call counter (the next call -- or graph replay -- uses the other buffer)
+__device__ __forceinline__ void dp_end(const DpCtxDev& c) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(c.state + 2, 1u) == gridDim.x - 1) {
+            c.state[2] = 0u;
+            __threadfence();
+            atomicAdd(c.state, 1u);
+        }
+    }
+}
+
+// PUSH = true : complete all-reduce of the local contribution (written by the previous kernel of the stream)
+// PUSH = false: the first hop was done by the producer; this kernel may start polling while the producer still runs
+//               and only orders itself behind it at its very end, which keeps "previous kernel complete" transitive
+//               along the stream for whatever follows.
+template <bool PUSH>
+__global__ void __launch_bounds__(DP_THREADS) dp_allreduce_kernel(const __grid_constant__ DpCtxDev c, const DpSource src,
+                                                                  float* __restrict__ out) {
+    __shared__ int s_abort;
+    if (PUSH) {
+        pdl_wait_prior_grids();      // the local contribution is complete ...
+        pdl_launch_dependents();     // ... and whoever is launched behind us may rely on that without waiting for US
+    }
+    dp_allreduce_body<PUSH>(c, src, out, &s_abort);
+    if (!PUSH) {
+        pdl_wait_prior_grids();
+        pdl_launch_dependents();
+    }
+    dp_end(c);
+}
+
+// single-GPU emulation of `world` ranks (tests): blockIdx.y is the rank, launched cooperatively so that all ranks'
+// CTAs are resident at once -- the ranks wait for each other's lines exactly as they do across GPUs.
+template <bool PUSH>
+__global__ void __launch_bounds__(DP_THREADS) dp_emulate_kernel(const DpCtxDev* __restrict__ ctxs, const float* const* __restrict__ payloads,
+                                                                float* const* __restrict__ outs) {
+    __shared__ int s_abort;
+    __shared__ DpCtxDev c;
+    if (threadIdx.x == 0) c = ctxs[blockIdx.y];
+    __syncthreads();
+    const DpSource src{payloads != nullptr ? payloads[blockIdx.y] : nullptr, c.n, nullptr, nullptr, 0};
+    dp_allreduce_body<PUSH>(c, src, outs[blockIdx.y], &s_abort);
+    dp_end(c);
+}
+
+}  // namespace b200vq

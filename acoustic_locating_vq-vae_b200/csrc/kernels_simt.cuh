@@ -5,7 +5,7 @@
 //                          loss / perplexity                             (vector_quantizer.py:39-56)
 //   finalize_stats_kernel  loss / perplexity from all-reduced statistics (data parallel)
 //   onehot_kernel          dense one-hot from indices                    (vector_quantizer.py:39-40)
-//   backward_kernel        dz and the scatter-add into dE                (autograd of :46-54)
+//   backward_kernel        dz and the scatter-add into dE, one red per element (autograd of :46-54; see kernels_bwd.cuh)
 // Arithmetic order is the one oracle/vq_oracle.c documents.
 #pragma once
 #include "common.cuh"
@@ -417,362 +417,6 @@ __global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__
             if (TRAIN_VQ) atomicAdd(dE + static_cast<size_t>(code) * D + c, ce * df);
         }
     }
-}
-
-// codebook gradient only (VQ_FLAG_NO_DZ): dE[idx] += ce*(E[idx] - z).  Data parallel splits the backward in two so that
-// the all-reduce of dE (side stream) overlaps the dz pass: this kernel reads a third of the backward's bytes.
-template <int VEC>
-__global__ void __launch_bounds__(256) backward_dE_kernel(const float* __restrict__ g_loss, const float* __restrict__ z,
-                                                          const float* __restrict__ E, const int* __restrict__ idx, long long N,
-                                                          float denom_dE, int D, float* __restrict__ dE) {
-    pdl_launch_dependents();
-    pdl_wait_prior_grids();
-    const float gl = g_loss != nullptr ? __ldg(g_loss) : 1.0f;
-    const float ce = gl * 2.0f / denom_dE;
-    const int DV = D / VEC;
-    const long long n_el = N * DV;
-    const long long stride = static_cast<long long>(gridDim.x) * 256;
-    for (long long e = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; e < n_el; e += stride) {
-        const long long r = e / DV;
-        const int c = static_cast<int>(e - r * DV);
-        const int code = __ldg(idx + r);
-        if (VEC == 4) {
-            const float4 zv = __ldg(reinterpret_cast<const float4*>(z) + e);      // kept in L2 for the dz pass that follows
-            const float4 ev = __ldg(reinterpret_cast<const float4*>(E + static_cast<size_t>(code) * D) + c);
-            float4 a;
-            a.x = ce * (ev.x - zv.x); a.y = ce * (ev.y - zv.y); a.z = ce * (ev.z - zv.z); a.w = ce * (ev.w - zv.w);
-            atomicAdd(reinterpret_cast<float4*>(dE + static_cast<size_t>(code) * D) + c, a);
-        } else {
-            atomicAdd(dE + static_cast<size_t>(code) * D + c, ce * (__ldg(E + static_cast<size_t>(code) * D + c) - z[e]));
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// one-shot all-reduce over NVLink peer memory (data parallel: the packed [dE | hist | sse] buffer).
-// Every rank owns a symmetric buffer [payload | flags]; `peers.buf[p]` is rank p's buffer mapped into this
-// process (torch symmetric memory / CUDA IPC).  Protocol per call (sequence number `seq`, strictly increasing):
-//   1. block 0 publishes "my payload for `seq` is complete" into every peer's flag slot [rank];
-//   2. every block waits until all peers have published `seq` into OUR flags;
-//   3. out[i] = sum over ranks p = 0..W-1 (fixed order => bit-identical on every rank) of peer p's payload[i],
-//      read with system-scope loads that bypass the local L1 (peer lines are never cached in local L2).
-// The caller alternates between two symmetric buffers, so a buffer is rewritten only after every peer has
-// passed the barrier of the following call, i.e. finished reading it: no second barrier is needed.
-// ---------------------------------------------------------------------------------------------
-constexpr int AR_MAX_RANKS = 16;
-struct PeerBuffers {
-    float* buf[AR_MAX_RANKS];
-};
-
-__device__ __forceinline__ float4 ld_sys_f4(const float4* p) {
-    float4 v;
-    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ float ld_sys_f1(const float* p) {
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__global__ void __launch_bounds__(256) allreduce_oneshot_kernel(PeerBuffers peers, int world, int rank,
-                                                                long long flag_off_floats, long long n, unsigned int seq,
-                                                                float* __restrict__ out) {
-    pdl_launch_dependents();
-    pdl_wait_prior_grids();            // our own payload (written by the backward kernel) is complete
-    if (blockIdx.x == 0 && threadIdx.x < world) {
-        __threadfence_system();
-        unsigned int* peer_flags = reinterpret_cast<unsigned int*>(peers.buf[threadIdx.x] + flag_off_floats);
-        st_release_sys_u32(peer_flags + rank, seq);
-    }
-    if (threadIdx.x < world) {
-        const unsigned int* my_flags = reinterpret_cast<const unsigned int*>(peers.buf[rank] + flag_off_floats);
-        // sequence numbers only grow; "seq - flag" wraps negative (as int) once the peer has caught up
-        while (static_cast<int>(seq - ld_acquire_sys_u32(my_flags + threadIdx.x)) > 0) {
-        }
-    }
-    __syncthreads();
-    const long long n4 = n >> 2;
-    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int p = 0; p < world; ++p) {
-            const float4 v = ld_sys_f4(reinterpret_cast<const float4*>(peers.buf[p]) + i);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
-        reinterpret_cast<float4*>(out)[i] = acc;
-    }
-    for (long long i = (n4 << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-        float acc = 0.f;
-        for (int p = 0; p < world; ++p) acc += ld_sys_f1(peers.buf[p] + i);
-        out[i] = acc;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// push ("low-latency") all-reduce: ONE NVLink one-way latency, no barrier.
-// Every rank owns a symmetric RECEIVE buffer of `world` slots; slot s holds rank s's contribution as 16-byte
-// lines {d0, seq, d1, seq}: the data and the sequence number of the call travel in the same store, so a line
-// whose two flag words equal `seq` is complete (16-byte stores may tear only at 8-byte granularity).
-//   1. every thread reads its part of the LOCAL payload and stores the lines into slot [rank] of every rank's
-//      receive buffer (remote stores over NVLink; the local one included);
-//   2. the same thread then polls ITS lines in all `world` local slots and sums them in rank order
-//      (bit-identical on every rank), writing `out`.
-// Two receive buffers alternate between calls: a peer can overwrite a slot for call c+2 only after it has
-// finished call c+1, which needed OUR contribution to c+1, which we send after having finished reading call c.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_volatile_v4(uint4* p, uint4 v) {
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
-    uint4 v;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
-
-// one store, delivered by the NVSwitch to the same offset of EVERY rank's buffer (NVLS multicast mapping)
-__device__ __forceinline__ void multimem_st_v4(void* mc_addr, uint4 v) {
-    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(__uint_as_float(v.x)),
-                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
-                 : "memory");
-}
-
-__global__ void __launch_bounds__(256) allreduce_push_kernel(PeerBuffers recv, float* multicast, int world, int rank,
-                                                             long long lines_per_slot, const float* __restrict__ payload,
-                                                             long long n, unsigned int seq, float* __restrict__ out) {
-    pdl_launch_dependents();
-    pdl_wait_prior_grids();            // the local payload (written by the backward kernel) is complete
-    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    const long long first = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    // 1. push: line i carries payload[2i], payload[2i+1]
-    for (long long i = first; i < lines_per_slot; i += stride) {
-        const float d0 = payload[2 * i];
-        const float d1 = (2 * i + 1 < n) ? payload[2 * i + 1] : 0.0f;
-        const uint4 line = make_uint4(__float_as_uint(d0), seq, __float_as_uint(d1), seq);
-        if (multicast != nullptr) {
-            // NVLS: the switch replicates this single store into slot [rank] of every rank's receive buffer
-            multimem_st_v4(reinterpret_cast<uint4*>(multicast) + static_cast<long long>(rank) * lines_per_slot + i, line);
-        } else {
-            for (int p = 0; p < world; ++p) {
-                const int dst = (rank + p) % world;    // spread the ranks' first targets over the links
-                st_volatile_v4(reinterpret_cast<uint4*>(recv.buf[dst]) + static_cast<long long>(rank) * lines_per_slot + i, line);
-            }
-        }
-    }
-    // 2. poll our own receive slots and reduce in rank order.  All slots of a line are requested together
-    //    (independent loads in flight), then only the ones that have not arrived yet are re-polled.
-    const uint4* mine = reinterpret_cast<const uint4*>(recv.buf[rank]);
-    for (long long i = first; i < lines_per_slot; i += stride) {
-        uint4 v[AR_MAX_RANKS];
-#pragma unroll
-        for (int p = 0; p < AR_MAX_RANKS; ++p)
-            if (p < world) v[p] = ld_volatile_v4(mine + static_cast<long long>(p) * lines_per_slot + i);
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-        for (int p = 0; p < AR_MAX_RANKS; ++p) {
-            if (p < world) {
-                while (v[p].y != seq || v[p].w != seq) v[p] = ld_volatile_v4(mine + static_cast<long long>(p) * lines_per_slot + i);
-                a0 += __uint_as_float(v[p].x);
-                a1 += __uint_as_float(v[p].z);
-            }
-        }
-        out[2 * i] = a0;
-        if (2 * i + 1 < n) out[2 * i + 1] = a1;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Two-step variant for larger worlds (reduce-scatter, then all-gather; same receive buffers, same line format).
-// The one-step kernel delivers world x payload into every rank (3.7 MB at 8 ranks for the 266 KB step buffer);
-// here rank j OWNS slice j (1/world of the lines):
-//   1. every rank stores slice j of its payload into slot [rank] of region A of rank j's receive buffer;
-//   2. the owner polls its `world` slots, sums them in rank order and stores the reduced lines into slot [rank] of
-//      region B of every rank's receive buffer (ONE multimem.st per line with NVLS);
-//   3. every rank polls region B and writes `out`.
-// Two NVLink one-way latencies instead of one, but only 2 x payload lands in each rank; every slice is reduced once,
-// by its owner, in rank order, so the result is bit-identical on all ranks (and equal to the one-step result).
-// No thread waits for anything but remote stores whose producers wait for nothing themselves (step 1) or only for
-// step-1 stores (step 2): with the whole grid resident (<= one CTA per SM) there is no circular wait.  The
-// alternating-buffer argument of the one-step kernel carries over unchanged.
-// Receive buffer: region A = lines [0, world*S), region B = lines [world*S, 2*world*S), S = ceil(L / world).
-// ---------------------------------------------------------------------------------------------
-// step 1: line i of the local payload goes to its owner j = i / S (slot [rank] of region A of rank j's buffer)
-__device__ __forceinline__ void ar2_push(const PeerBuffers& recv, int rank, long long L, long long S, const float* payload,
-                                         long long n, unsigned int seq, long long first, long long stride) {
-    for (long long i = first; i < L; i += stride) {
-        const long long j = i / S, l = i - j * S;
-        const float d0 = __ldcg(payload + 2 * i);
-        const float d1 = (2 * i + 1 < n) ? __ldcg(payload + 2 * i + 1) : 0.0f;
-        st_volatile_v4(reinterpret_cast<uint4*>(recv.buf[j]) + static_cast<long long>(rank) * S + l,
-                       make_uint4(__float_as_uint(d0), seq, __float_as_uint(d1), seq));
-    }
-}
-
-// step 2: reduce our own slice in rank order and broadcast it
-__device__ __forceinline__ void ar2_reduce_bcast(const PeerBuffers& recv, float* multicast, int world, int rank, long long L,
-                                                 long long S, unsigned int seq, long long first, long long stride) {
-    const uint4* mine = reinterpret_cast<const uint4*>(recv.buf[rank]);
-    const long long own = min(S, L - static_cast<long long>(rank) * S);
-    const long long b_off = static_cast<long long>(world) * S + static_cast<long long>(rank) * S;
-    for (long long l = first; l < own; l += stride) {
-        float a0 = 0.f, a1 = 0.f;
-        for (int p0 = 0; p0 < world; p0 += 8) {           // 8 slots requested together, summed in rank order
-            uint4 v[8];
-#pragma unroll
-            for (int p = 0; p < 8; ++p)
-                if (p0 + p < world) v[p] = ld_volatile_v4(mine + static_cast<long long>(p0 + p) * S + l);
-#pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                if (p0 + p < world) {
-                    while (v[p].y != seq || v[p].w != seq) v[p] = ld_volatile_v4(mine + static_cast<long long>(p0 + p) * S + l);
-                    a0 += __uint_as_float(v[p].x);
-                    a1 += __uint_as_float(v[p].z);
-                }
-            }
-        }
-        const uint4 line = make_uint4(__float_as_uint(a0), seq, __float_as_uint(a1), seq);
-        if (multicast != nullptr) {
-            multimem_st_v4(reinterpret_cast<uint4*>(multicast) + b_off + l, line);
-        } else {
-            for (int p = 0; p < world; ++p)
-                st_volatile_v4(reinterpret_cast<uint4*>(recv.buf[(rank + p) % world]) + b_off + l, line);
-        }
-    }
-}
-
-// step 3: collect every owner's reduced slice.  Region B is laid out owner-major with S lines per owner and owner j's
-// slice starts at line j*S, so reduced line i sits at offset i; 4 polls in flight per thread
-__device__ __forceinline__ void ar2_gather(const PeerBuffers& recv, int world, int rank, long long L, long long S, long long n,
-                                           unsigned int seq, float* __restrict__ out, long long first, long long stride) {
-    const uint4* gathered = reinterpret_cast<const uint4*>(recv.buf[rank]) + static_cast<long long>(world) * S;
-    for (long long i0 = first; i0 < L; i0 += 4 * stride) {
-        uint4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const long long i = i0 + u * stride;
-            if (i < L) v[u] = ld_volatile_v4(gathered + i);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const long long i = i0 + u * stride;
-            if (i < L) {
-                while (v[u].y != seq || v[u].w != seq) v[u] = ld_volatile_v4(gathered + i);
-                out[2 * i] = __uint_as_float(v[u].x);
-                if (2 * i + 1 < n) out[2 * i + 1] = __uint_as_float(v[u].z);
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256) allreduce_push2_kernel(PeerBuffers recv, float* multicast, int world, int rank, long long L,
-                                                              long long S, const float* __restrict__ payload, long long n,
-                                                              unsigned int seq, float* __restrict__ out) {
-    pdl_launch_dependents();
-    pdl_wait_prior_grids();            // the local payload (written by the backward kernel) is complete
-    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    const long long first = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    ar2_push(recv, rank, L, S, payload, n, seq, first, stride);
-    ar2_reduce_bcast(recv, multicast, world, rank, L, S, seq, first, stride);
-    ar2_gather(recv, world, rank, L, S, n, seq, out, first, stride);
-}
-
-// ---------------------------------------------------------------------------------------------
-// backward + all-reduce in ONE persistent kernel (data parallel): the NVLink transfer of the packed
-// [dE | hist | sse] buffer overlaps the dz pass instead of following the backward kernel.
-//   A1  dE[idx] += ce*(E[idx] - z)                  (reads z, idx, E: a third of the backward's traffic)
-//   --  grid barrier (sense reversal on two words owned by the caller): every dE atomic has landed
-//   B   step 1 of the two-step all-reduce: push the slices to their owners (stores only, nothing waits)
-//   A2  dz = g_q - cz*(E[idx] - z), first half      (z comes from L2 this time) -- the pushes are in flight meanwhile
-//   C   step 2: reduce our slice (its inputs have arrived by now) and broadcast it
-//   A2  second half                                 -- the broadcasts are in flight meanwhile
-//   D   step 3: collect every owner's reduced slice
-// The grid is persistent and fully resident (<= 4 CTAs of 256 threads per SM), which both the grid barrier and the
-// all-reduce's no-circular-wait argument need.  Arithmetic is backward_kernel's, so dz is bit-identical to it.
-// ---------------------------------------------------------------------------------------------
-template <bool HAS_GQ>
-__global__ void __launch_bounds__(256, 4) backward_allreduce_kernel(const float* __restrict__ g_q, const float* __restrict__ g_loss,
-                                                                 const float* __restrict__ z, const float* __restrict__ E,
-                                                                 const int* __restrict__ idx, long long N, float denom_dz,
-                                                                 float denom_dE, int D, float beta, float* __restrict__ dz,
-                                                                 float* payload, long long n, PeerBuffers recv, float* multicast,
-                                                                 int world, int rank, long long L, long long S, unsigned int seq,
-                                                                 unsigned int* grid_sync, float* __restrict__ out) {
-    pdl_launch_dependents();
-    pdl_wait_prior_grids();
-    const float gl = g_loss != nullptr ? __ldg(g_loss) : 1.0f;
-    const float cz = gl * beta * 2.0f / denom_dz;
-    const float ce = gl * 2.0f / denom_dE;
-    const int DV = D / 4;
-    const long long n_el = N * DV;
-    const long long stride = static_cast<long long>(gridDim.x) * 256;
-    const long long first = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-    float* dE = payload;
-    for (long long e = first; e < n_el; e += stride) {                      // A1
-        const long long r = e / DV;
-        const int c = static_cast<int>(e - r * DV);
-        const int code = __ldg(idx + r);
-        const float4 zv = __ldg(reinterpret_cast<const float4*>(z) + e);
-        const float4 ev = __ldg(reinterpret_cast<const float4*>(E + static_cast<size_t>(code) * D) + c);
-        float4 a;
-        a.x = ce * (ev.x - zv.x); a.y = ce * (ev.y - zv.y); a.z = ce * (ev.z - zv.z); a.w = ce * (ev.w - zv.w);
-        atomicAdd(reinterpret_cast<float4*>(dE + static_cast<size_t>(code) * D) + c, a);
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {                                                  // grid barrier
-        const unsigned int gen = ld_acquire_gpu_u32(grid_sync + 1);
-        if (atomicAdd(grid_sync, 1u) == gridDim.x - 1) {
-            grid_sync[0] = 0u;
-            __threadfence();
-            atomicAdd(grid_sync + 1, 1u);
-        } else {
-            while (ld_acquire_gpu_u32(grid_sync + 1) == gen) {
-            }
-        }
-    }
-    __syncthreads();
-    ar2_push(recv, rank, L, S, payload, n, seq, first, stride);              // B
-    auto dz_pass = [&](long long e_begin, long long e_end) {                 // A2 over elements [e_begin, e_end)
-        for (long long e0 = e_begin + first; e0 < e_end; e0 += 2 * stride) {    // two elements in flight per thread
-            float4 zv[2], ev[2], gv[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const long long e = e0 + u * stride;
-                if (e < e_end) {
-                    const long long r = e / DV;
-                    const int c = static_cast<int>(e - r * DV);
-                    const int code = __ldg(idx + r);
-                    zv[u] = __ldcs(reinterpret_cast<const float4*>(z) + e);
-                    ev[u] = __ldg(reinterpret_cast<const float4*>(E + static_cast<size_t>(code) * D) + c);
-                    gv[u] = HAS_GQ ? __ldcs(reinterpret_cast<const float4*>(g_q) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const long long e = e0 + u * stride;
-                if (e < e_end) {
-                    float4 df, o;
-                    df.x = ev[u].x - zv[u].x; df.y = ev[u].y - zv[u].y; df.z = ev[u].z - zv[u].z; df.w = ev[u].w - zv[u].w;
-                    o.x = fmaf(-cz, df.x, gv[u].x); o.y = fmaf(-cz, df.y, gv[u].y);
-                    o.z = fmaf(-cz, df.z, gv[u].z); o.w = fmaf(-cz, df.w, gv[u].w);
-                    __stcs(reinterpret_cast<float4*>(dz) + e, o);
-                }
-            }
-        }
-    };
-    const long long half = (n_el / 2 / stride) * stride;                     // whole grid strides: every thread does both halves
-    dz_pass(0, half);                                                         // A2, first half: the pushes are in flight
-    ar2_reduce_bcast(recv, multicast, world, rank, L, S, seq, first, stride); // C: our slice's inputs have arrived
-    dz_pass(half, n_el);                                                      // A2, second half: the broadcasts are in flight
-    ar2_gather(recv, world, rank, L, S, n, seq, out, first, stride);          // D
 }
 
 // ---------------------------------------------------------------------------------------------

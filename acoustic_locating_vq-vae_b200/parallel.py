@@ -68,66 +68,17 @@ def global_row_count(n_rows_local: int, group=None, equal_shards: bool = True) -
     return int(t.item())
 
 
-class SymmetricAllReduce:
-    """One-shot sum all-reduce of the packed step buffer over NVLink peer memory (vq_allreduce_sum).
+class PeerExchange:
+    """Sum all-reduce of the packed step buffer over NVLink peer memory (include/b200vq.h: vq_dp_*).
 
-    Two symmetric buffers ([payload | flags], torch symmetric memory) alternate between calls; the kernel does a
-    flag barrier and sums the peers' payloads in rank order, so every rank gets bit-identical results.  The
-    backward kernel accumulates dE straight into `payload()`; `reduce()` returns the reduced packed buffer.
-    Falls back to NCCL (`all_reduce_packed`) when symmetric memory cannot be set up.
+    Each rank owns two symmetric RECEIVE buffers (torch symmetric memory; alternating between calls).  A call stores
+    the local contribution as 16-byte lines {d0, seq, d1, seq} -- data and sequence number in the same store -- into
+    the peers and sums what arrives in rank order: no barrier, bit-identical results on every rank.  The sequence
+    number lives in device memory and is advanced by the kernel, so calls can be captured in a CUDA graph and replayed
+    (nothing on the host has to stay in step with the device).
     """
 
-    def __init__(self, n_floats: int, device, group=None):
-        import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm_mem
-        from . import _lib
-        self.lib = _lib.load()
-        self.check = _lib.check
-        self.group = group if group is not None else dist.group.WORLD
-        self.world = dist.get_world_size(self.group)
-        self.rank = dist.get_rank(self.group)
-        self.n = n_floats
-        self.flag_off = (n_floats + 63) // 64 * 64                   # flags start on a 256-byte boundary
-        total = self.flag_off + 64
-        self.bufs, self.ptr_arrays = [], []
-        for _ in range(2):
-            t = symm_mem.empty(total, dtype=torch.float32, device=device)
-            t.zero_()
-            hdl = symm_mem.rendezvous(t, self.group)
-            ptrs = list(hdl.buffer_ptrs)
-            import ctypes
-            arr = (ctypes.c_void_p * self.world)(*ptrs)
-            self.bufs.append(t)
-            self.ptr_arrays.append(arr)
-        torch.cuda.synchronize(device)
-        dist.barrier(self.group)                                     # zero-initialised flags are in place everywhere
-        self.out = torch.zeros(n_floats, dtype=torch.float32, device=device)
-        self.seq = 0
-
-    def payload(self) -> torch.Tensor:
-        """The buffer the NEXT reduce() will contribute (write the local partial result here)."""
-        return self.bufs[self.seq & 1][:self.n]
-
-    def reduce(self, stream_ptr: int) -> torch.Tensor:
-        which = self.seq & 1
-        self.seq += 1
-        seq_no = (self.seq + 1) // 2                                 # 1, 1, 2, 2, ...: per-buffer sequence number
-        self.check(self.lib.vq_allreduce_sum(self.ptr_arrays[which], self.world, self.rank, self.flag_off, self.n,
-                                             seq_no, self.out.data_ptr(), stream_ptr))
-        return self.out
-
-
-class PushAllReduce:
-    """Low-latency push all-reduce of the packed step buffer over NVLink peer memory (vq_allreduce_push).
-
-    Each rank owns two symmetric RECEIVE buffers (alternating between calls) of `world` slots; a call stores the
-    local payload -- data and sequence number in the same 16-byte line -- into slot [rank] of every rank's
-    receive buffer and then sums its own slots in rank order as the lines arrive: one NVLink one-way latency,
-    no barrier, bit-identical results on every rank.  `payload` is ordinary device memory (the backward kernel
-    accumulates dE straight into it).
-    """
-
-    def __init__(self, n_floats: int, device, group=None):
+    def __init__(self, n_floats: int, device, group=None, spin_limit: int = 0):
         import ctypes
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -137,50 +88,64 @@ class PushAllReduce:
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
-        self.n = n_floats
-        lines = (n_floats + 1) // 2
-        self.bufs, self.ptr_arrays, self.mc_ptrs = [], [], []
+        self.n = int(n_floats)
+        self.device = torch.device(device)
+        lines = int(self.lib.vq_dp_recv_lines(self.world, self.n))
+        self.bufs, arrays, mcs = [], [], []
         use_mc = os.environ.get("B200VQ_NVLS", "1") != "0"
         for _ in range(2):
-            t = symm_mem.empty(self.world * (lines + 2) * 4, dtype=torch.float32, device=device)   # include/b200vq.h: world x (lines + 2) lines
+            t = symm_mem.empty(lines * 4, dtype=torch.float32, device=self.device)
             t.zero_()
             hdl = symm_mem.rendezvous(t, self.group)
             self.bufs.append(t)
-            self.ptr_arrays.append((ctypes.c_void_p * self.world)(*list(hdl.buffer_ptrs)))
-            mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if use_mc else 0
-            self.mc_ptrs.append(mc if mc != 0 else None)
-        self.nvls = all(m is not None for m in self.mc_ptrs)
-        if not self.nvls:
-            self.mc_ptrs = [None, None]
-        torch.cuda.synchronize(device)
+            arrays.append((ctypes.c_void_p * self.world)(*list(hdl.buffer_ptrs)))
+            mcs.append(int(getattr(hdl, "multicast_ptr", 0) or 0) if use_mc else 0)
+        self.nvls = all(m != 0 for m in mcs)
+        torch.cuda.synchronize(self.device)
         dist.barrier(self.group)                      # zero-initialised receive buffers are in place everywhere
-        self.payload_buf = torch.zeros(n_floats, dtype=torch.float32, device=device)
-        self.out = torch.zeros(n_floats, dtype=torch.float32, device=device)
-        self.grid_sync = torch.zeros(2, dtype=torch.int32, device=device)     # grid barrier of the fused backward kernel
-        self.seq = 0
+        ctx = ctypes.c_void_p()
+        self.check(self.lib.vq_dp_create(arrays[0], arrays[1], mcs[0] if self.nvls else None, mcs[1] if self.nvls else None,
+                                         self.world, self.rank, self.n, spin_limit, ctypes.byref(ctx)))
+        self.ctx = ctx
 
-    def payload(self) -> torch.Tensor:
-        return self.payload_buf
+    def allreduce(self, payload: torch.Tensor, out: torch.Tensor, stream_ptr: int) -> torch.Tensor:
+        """out = sum over ranks of payload (n_floats each)."""
+        assert payload.numel() == self.n and out.numel() == self.n
+        self.check(self.lib.vq_dp_allreduce(self.ctx, payload.data_ptr(), out.data_ptr(), stream_ptr))
+        return out
 
-    def _next(self):
-        which = self.seq & 1
-        self.seq += 1
-        return which, (self.seq + 1) // 2             # 1, 1, 2, 2, ...: per-buffer sequence number (never 0)
+    def exchange_sums(self, workspace: torch.Tensor, n_rows: int, K: int, D: int, tail: torch.Tensor, out: torch.Tensor,
+                      stream_ptr: int) -> torch.Tensor:
+        """out = sum over ranks of [code sums of the last vq_step_forward on `workspace` | tail]."""
+        assert K * D + tail.numel() == self.n and out.numel() == self.n
+        self.check(self.lib.vq_dp_exchange_sums(self.ctx, workspace.data_ptr(), workspace.numel(), n_rows, K, D, tail.data_ptr(),
+                                                tail.numel(), out.data_ptr(), stream_ptr))
+        return out
 
-    def backward_reduce(self, g_q_ptr, g_loss_ptr, z_ptr, E_ptr, idx_ptr, n_rows: int, n_rows_dE: int, K: int, D: int,
-                        beta: float, flags: int, dz_ptr: int, stream_ptr: int) -> torch.Tensor:
-        """vq_backward + all-reduce in one kernel (vq_backward_allreduce): dE accumulates into payload()[:K*D] (which the
-        caller has zeroed, with the histogram / squared error already behind it) and the NVLink exchange overlaps the
-        dz pass.  Returns the reduced buffer, like reduce()."""
-        which, seq_no = self._next()
-        self.check(self.lib.vq_backward_allreduce(g_q_ptr, g_loss_ptr, z_ptr, E_ptr, idx_ptr, n_rows, max(n_rows, 1), n_rows_dE,
-                                                  K, D, beta, flags, dz_ptr, self.payload_buf.data_ptr(), self.n,
-                                                  self.ptr_arrays[which], self.mc_ptrs[which], self.world, self.rank, seq_no,
-                                                  self.grid_sync.data_ptr(), self.out.data_ptr(), stream_ptr))
-        return self.out
+    def status(self, stream_ptr: int = 0):
+        """(calls completed, error word) -- synchronises the stream; error bit 0 = a bounded wait expired."""
+        import ctypes
+        calls, err = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        self.check(self.lib.vq_dp_status(self.ctx, ctypes.byref(calls), ctypes.byref(err), stream_ptr))
+        return calls.value, err.value
 
-    def reduce(self, stream_ptr: int) -> torch.Tensor:
-        which, seq_no = self._next()
-        self.check(self.lib.vq_allreduce_push(self.ptr_arrays[which], self.mc_ptrs[which], self.world, self.rank,
-                                              self.payload_buf.data_ptr(), self.n, seq_no, self.out.data_ptr(), stream_ptr))
-        return self.out
+    def close(self):
+        if getattr(self, "ctx", None) is not None:
+            self.lib.vq_dp_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def agree(ok: bool, group=None) -> bool:
+    """True only if `ok` holds on EVERY rank (one small all-reduce): ranks must not pick different collectives."""
+    import torch.distributed as dist
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32)
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t.item()) == 1)

@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, parallel
-from ._lib import (FLAG_DEFER_STATS, FLAG_EXACT, FLAG_NO_QUANT, FLAG_ONEHOT, FLAG_STATE_READY, FLAG_TRAIN_VQ, FLAG_ZERO_DE, check)
+from ._lib import (FLAG_CODE_SUMS, FLAG_EXACT, FLAG_ONEHOT, FLAG_TRAIN_VQ, FLAG_ZERO_DE, check)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -37,13 +37,15 @@ class _Buffers:
     """Per-module device scratch, grown on demand and reused (stream-ordered, one stream per module)."""
 
     def __init__(self):
-        self.ws = None
+        self.ws = None       # workspace of vq_step_forward: carries the call counter / accumulators from call to call
         self.code = None     # (e_norm2, E_hi, E_lo)
-        self.ws_bytes = {}   # (N, K, D, flags) -> vq_workspace_bytes
+        self.ws_bytes = {}   # (N, K, D) -> vq_workspace_bytes
+        self.sums = {}       # (N, K, D) -> vq_step_uses_code_sums
 
-    def workspace(self, nbytes: int, device) -> torch.Tensor:
+    def workspace(self, lib, nbytes: int, device, stream: int) -> torch.Tensor:
         if self.ws is None or self.ws.numel() < nbytes or self.ws.device != device:
             self.ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+            check(lib.vq_workspace_init(self.ws.data_ptr(), self.ws.numel(), stream))     # once per allocation
         return self.ws
 
     def codebook(self, K: int, D: int, device):
@@ -56,7 +58,12 @@ class _Buffers:
 
 
 class _VQFunction(torch.autograd.Function):
-    """forward = vq_prepare_codebook + vq_forward; backward = vq_backward (+ optional all-reduce)."""
+    """forward = vq_step_forward (ONE launch on the screen + refine path); backward = vq_step_backward.
+
+    When the codebook trains, the forward also accumulates the code sums S_k = sum (E_k - z_n) (VQ_FLAG_CODE_SUMS) and
+    the backward is a pure streaming pass; under data parallelism [S | usage histogram | squared error] is exchanged
+    right behind the forward (nothing in it depends on upstream gradients), so the collective overlaps whatever the
+    model does between the quantizer's forward and backward."""
 
     @staticmethod
     def forward(ctx, inputs, weight, module, flags, want_onehot):
@@ -73,35 +80,43 @@ class _VQFunction(torch.autograd.Function):
         e_norm2, e_hi, e_lo = bufs.codebook(K, D, dev)
         q_out = torch.empty_like(inputs)
         idx = torch.empty(N, dtype=torch.int32, device=dev)
-        stats = torch.empty(K + 1, dtype=torch.float32, device=dev)    # [hist(K) | sse]
-        loss = torch.empty((), dtype=torch.float32, device=dev)
-        perplexity = torch.empty((), dtype=torch.float32, device=dev)
+        scal = torch.empty(K + 3, dtype=torch.float32, device=dev)     # [hist (K) | sse | loss | perplexity]
         onehot = torch.empty(N, K, dtype=torch.float32, device=dev) if want_onehot else None
-        fl = flags | (FLAG_ONEHOT if want_onehot else 0)
-        key = (N, K, D, fl)
+        train_vq = bool(module._train_vq)
+        wants_dE = train_vq and weight.requires_grad and torch.is_grad_enabled()
+        key = (N, K, D)
         nbytes = bufs.ws_bytes.get(key)
         if nbytes is None:
-            nbytes = bufs.ws_bytes[key] = lib.vq_workspace_bytes(N, K, D, fl)
-        ws = bufs.workspace(nbytes, dev)
-        sp = stats.data_ptr()
-        # codebook norms, tf32 hi/lo split and the reset of hist / completion counter in ONE launch
-        check(lib.vq_prepare_step(_ptr(w), K, D, _ptr(e_norm2), _ptr(e_hi), _ptr(e_lo), sp, _ptr(ws), ws.numel(), None, st))
-        fl |= FLAG_STATE_READY
-        check(lib.vq_forward(_ptr(flat), _ptr(w), _ptr(e_norm2), _ptr(e_hi), _ptr(e_lo), N, K, D,
-                             float(module._commitment_cost), fl, _ptr(q_out), _ptr(idx), _ptr(onehot),
-                             sp, sp + 4 * K, _ptr(loss), _ptr(perplexity), _ptr(ws), ws.numel(), st))
-        if N == 0:   # mean over nothing: the reference yields NaN
-            loss.fill_(float("nan"))
-            perplexity.fill_(1.0)
+            nbytes = bufs.ws_bytes[key] = lib.vq_workspace_bytes(N, K, D, 0)
+            bufs.sums[key] = bool(lib.vq_step_uses_code_sums(N, K, D, flags | FLAG_CODE_SUMS))
+        sums = wants_dE and bufs.sums[key]
+        fl = flags | (FLAG_ONEHOT if want_onehot else 0) | (FLAG_CODE_SUMS if sums else 0)
+        ws = bufs.workspace(lib, nbytes, dev, st)
+        sp = scal.data_ptr()
+        check(lib.vq_step_forward(_ptr(flat), _ptr(w), N, K, D, float(module._commitment_cost), fl,
+                                  _ptr(e_norm2), _ptr(e_hi), _ptr(e_lo), _ptr(q_out), _ptr(idx), _ptr(onehot),
+                                  sp, sp + 4 * K, sp + 4 * (K + 1), sp + 4 * (K + 2), _ptr(ws), ws.numel(), st))
+        loss = scal[K + 1]
+        perplexity = scal[K + 2]
+        reduced = None
+        if sums and (module.process_group is not None or module.data_parallel):
+            # data parallel: everything the exchange carries exists now -- launch it right behind the forward
+            ex = module._peer_exchange(K, D, dev, module.process_group)
+            if ex is not None:
+                reduced = torch.empty(K * D + K + 1, dtype=torch.float32, device=dev)
+                ex.exchange_sums(ws, N, K, D, scal[:K + 1], reduced, st)
         ctx.save_for_backward(inputs, weight, idx)
         ctx.module = module
-        ctx.stats = stats
-        ctx.train_vq = bool(module._train_vq)
+        ctx.stats = scal
+        ctx.train_vq = train_vq
+        ctx.sums = sums
+        ctx.reduced = reduced
+        ctx.ws = ws
         if onehot is not None:
             ctx.mark_non_differentiable(perplexity, idx, onehot)
         else:
             ctx.mark_non_differentiable(perplexity, idx)
-        module.__dict__["_last_stats"] = stats      # plain attribute: skip nn.Module.__setattr__ on the eager path
+        module.__dict__["_last_stats"] = scal       # plain attribute: skip nn.Module.__setattr__ on the eager path
         return loss, q_out, perplexity, onehot, idx
 
     @staticmethod
@@ -128,37 +143,45 @@ class _VQFunction(torch.autograd.Function):
         if pg is not None or module.data_parallel:
             import torch.distributed as dist
             world = dist.get_world_size(pg)
-        packed = None
-        dE = None
-        push = None
-        if need_dE:
-            if world > 1:
-                # one all-reduce per step over [dE | hist | sse]  (SURVEY.md section 8e): our own low-latency push
-                # kernel over NVLink peer memory when symmetric memory is available, NCCL otherwise
-                push = module._push_allreduce(K, D, dev, pg)
-                packed = push.payload() if push is not None else parallel.new_packed(K, D, dev)
-                if push is not None:
-                    packed.zero_()
-                dE = parallel.packed_views(packed, K, D)[0]
-            else:
-                dE = torch.empty(K, D, dtype=torch.float32, device=dev)     # zeroed inside vq_backward (VQ_FLAG_ZERO_DE)
-        dz = torch.empty_like(inputs)
+        dz = torch.empty_like(inputs) if need_dz else None
         w = weight.detach()
         if not w.is_contiguous():
             w = w.contiguous()
-        flags = (FLAG_TRAIN_VQ | (FLAG_ZERO_DE if packed is None else 0)) if need_dE else 0
-        check(lib.vq_backward(_ptr(g_q), _ptr(g_loss), _ptr(inputs), _ptr(w), _ptr(idx), N, max(N, 1),
-                              max(N, 1) * world, K, D, float(module._commitment_cost), flags, _ptr(dz), _ptr(dE), st))
-        if packed is not None:
-            packed[K * D:] = ctx.stats[:K + 1]
-            if push is not None:
-                reduced = push.reduce(st)
-                dE = reduced[:K * D].view(K, D).clone()       # `reduced` is reused by the next step
-                module.__dict__["_global_stats"] = (reduced[K * D:].clone(), N * world)
-            else:
-                parallel.all_reduce_packed(packed, pg)
-                module.__dict__["_global_stats"] = (packed[K * D:], N * world)
-        return (dz if need_dz else None), dE, None, None, None
+        beta = float(module._commitment_cost)
+        n_dz, n_dE = max(N, 1), max(N, 1) * world
+        if not need_dE:
+            if need_dz:
+                check(lib.vq_backward(_ptr(g_q), _ptr(g_loss), _ptr(inputs), _ptr(w), _ptr(idx), N, n_dz, n_dE, K, D, beta, 0,
+                                      _ptr(dz), None, st))
+            return dz, None, None, None, None
+        dE = torch.empty(K, D, dtype=torch.float32, device=dev)
+        if ctx.sums and (world == 1 or ctx.reduced is not None):
+            # the forward accumulated the code sums: stream dz, scale S (all-reduced at forward time under data parallelism)
+            red = ctx.reduced
+            check(lib.vq_step_backward(_ptr(g_q), _ptr(g_loss), _ptr(inputs), _ptr(w), _ptr(idx), N, n_dz, n_dE, K, D, beta,
+                                       FLAG_TRAIN_VQ | FLAG_ZERO_DE | FLAG_CODE_SUMS, _ptr(dz), _ptr(dE), _ptr(ctx.ws), ctx.ws.numel(),
+                                       _ptr(red), st))
+            if red is not None:
+                module.__dict__["_global_stats"] = (red[K * D:], N * world)
+            return dz, dE, None, None, None
+        if world == 1:
+            check(lib.vq_backward(_ptr(g_q), _ptr(g_loss), _ptr(inputs), _ptr(w), _ptr(idx), N, n_dz, n_dE, K, D, beta,
+                                  FLAG_TRAIN_VQ | FLAG_ZERO_DE, _ptr(dz), _ptr(dE), st))
+            return dz, dE, None, None, None
+        # data parallel without code sums (shapes outside the screen path): one all-reduce of [dE | hist | sse] after the backward
+        packed = parallel.new_packed(K, D, dev)
+        dEp = parallel.packed_views(packed, K, D)[0]
+        check(lib.vq_backward(_ptr(g_q), _ptr(g_loss), _ptr(inputs), _ptr(w), _ptr(idx), N, n_dz, n_dE, K, D, beta, FLAG_TRAIN_VQ,
+                              _ptr(dz), _ptr(dEp), st))
+        packed[K * D:] = ctx.stats[:K + 1]
+        ex = module._peer_exchange(K, D, dev, pg)
+        if ex is not None:
+            reduced = torch.empty_like(packed)
+            ex.allreduce(packed, reduced, st)
+        else:
+            reduced = parallel.all_reduce_packed(packed, pg)
+        module.__dict__["_global_stats"] = (reduced[K * D:], N * world)
+        return dz, reduced[:K * D].view(K, D), None, None, None
 
 
 class VectorQuantizer(nn.Module):
@@ -194,7 +217,7 @@ class VectorQuantizer(nn.Module):
         self._bufs = _Buffers()
         self._last_stats = None
         self._global_stats = None
-        self._push_ar = None
+        self._peer_ex = None
         self.last_indices = None
 
     # -- reference accessors (vector_quantizer.py:23-27) ------------------------------------------
@@ -212,7 +235,7 @@ class VectorQuantizer(nn.Module):
         s["_global_stats"] = None
         s["last_indices"] = None
         s["process_group"] = None
-        s["_push_ar"] = None
+        s["_peer_ex"] = None
         return s
 
     def __setstate__(self, s):
@@ -246,20 +269,30 @@ class VectorQuantizer(nn.Module):
         self.__dict__["last_indices"] = idx
         return loss, quantized, perplexity, encodings
 
-    def _push_allreduce(self, K, D, dev, pg):
-        """Lazily set up the NVLink push all-reduce (parallel.PushAllReduce); None -> use NCCL."""
-        if self._push_ar is False:
+    def _peer_exchange(self, K, D, dev, pg):
+        """Lazily set up the NVLink exchange (parallel.PeerExchange); None -> NCCL.  The ranks AGREE on the outcome (one
+        small all-reduce), so a rank whose setup failed cannot end up in a different collective from its peers."""
+        if self._peer_ex is False:
             return None
-        if self._push_ar is None:
+        if self._peer_ex is None:
+            import warnings
+            import torch.distributed as dist
+            ex, why = None, None
             try:
-                import torch.distributed as dist
                 if dist.get_backend(pg) != "nccl":
                     raise RuntimeError("not an NCCL group")
-                self._push_ar = parallel.PushAllReduce(parallel.packed_size(K, D), dev, pg)
-            except Exception:
-                self._push_ar = False
+                ex = parallel.PeerExchange(parallel.packed_size(K, D), dev, pg)
+            except Exception as e:          # symmetric memory unavailable, out of memory, ...
+                why = f"{type(e).__name__}: {e}"
+            if not parallel.agree(ex is not None, pg):
+                if ex is not None:
+                    ex.close()
+                warnings.warn("b200vq: NVLink peer exchange unavailable on at least one rank"
+                              + (f" (here: {why})" if why else "") + "; using NCCL all_reduce for the codebook statistics")
+                self._peer_ex = False
                 return None
-        return self._push_ar
+            self._peer_ex = ex
+        return self._peer_ex
 
     # -- extras ------------------------------------------------------------------------------------
     @torch.no_grad()

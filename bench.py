@@ -3,19 +3,28 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
 
-One "step" = one pass of the hot path (vq_prepare_codebook + vq_forward + vq_backward, i.e.
-vector_quantizer.py:29-58 and its autograd) over one batch of synthetic latents of the shape
-`_pre_vq_conv` hands to the quantizer.  Default workload = BASELINE.json configs[1]:
-RIR VQ-VAE quantizer from train_rir.py defaults at batch 256 -> z (256, 64, 201), N = 51 456 rows,
-K = 1024, D = 64, beta = 0.25, dense one-hot `encodings` emitted (the reference always returns it).
+One "step" = one pass of the hot path (vector_quantizer.py:29-58 and its autograd) over one batch of synthetic
+latents of the shape `_pre_vq_conv` hands to the quantizer:
+    vq_step_forward   codebook norms + distances + argmin + one-hot + gather + losses + perplexity (+ code sums)
+    vq_step_backward  dz and dE
+Default workload = BASELINE.json configs[1]: RIR VQ-VAE quantizer from train_rir.py defaults at batch 256 ->
+z (256, 64, 201), N = 51 456 rows, K = 1024, D = 64, beta = 0.25, dense one-hot `encodings` emitted (the reference
+always returns it).  The step is captured once per input buffer in a CUDA graph and replayed (--no-graph: eager).
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline      dominant kernel: algorithmic bytes|flops per launch / CUDA-event time per launch
-  cpu_baseline  the oracle port (same aten ops as the reference module) timed on this box's host cores
-  e2e           same metric through the host-buffer C ABI (pinned host z in, loss/perplexity/indices out)
-  kernels       per-kernel share of the step (CUDA events on the launching stream)
-Under torchrun (N > 1) every rank runs the same per-rank workload on its own rows (weak scaling) and
-all-reduces the packed [dE | hist | sse] buffer once per step (own one-shot NVLink kernel; --nccl for NCCL).
+  roofline          dominant kernel: algorithmic bytes|flops per launch / CUDA-event time per launch
+  cpu_baseline      the reference's CPU implementation timed on this box's host cores (bounded sample)
+  e2e               same metric through the host-buffer C ABI with the reference's full deliverable copied back
+                    (quantized, dz, dE, indices, loss, perplexity); e2e_lean = indices + loss + perplexity only
+  kernels           per-kernel share of the step (CUDA events on the launching stream, eager launches)
+  sweep             configs[3] corner points (N = 1M rows, indices only): fwd / bwd time, fraction of the roofline
+  peaks             HBM and tensor peaks used (TF32 measured here with cuBLAS: burst and sustained)
+  module            the drop-in nn.Module on the same workload (eager and inside a CUDA graph)
+  collective_check  N > 1: the NVLink exchange against NCCL on the same payload, and the step's dE against an
+                    NCCL all-reduce of the local gradients
+Under torchrun (N > 1) every rank runs the same per-rank workload on its own rows (weak scaling); the only exchange
+is ONE sum all-reduce per step of [code sums | usage histogram | squared error], launched right behind the forward
+(nothing in it depends on upstream gradients) so that it runs concurrently with the backward's dz pass.
 """
 from __future__ import annotations
 
@@ -37,16 +46,20 @@ WORKLOADS = {
     "rir256": (256, 64, 201, 1024, "configs[1]: RIR VQ-VAE quantizer (train_rir.py defaults), batch 256"),
     "speech32": (32, 128, 500, 1024, "configs[0]: speech VQ-VAE quantizer (train_speech.py defaults), batch 32"),
     "echoed64": (64, 128, 500, 1024, "configs[2] speech side: echoed-speech step, batch 64"),
-    "sweep_k1024_d64": (1024, 64, 1024, 1024, "configs[3]: N=1M rows, K=1024, D=64"),
-    "sweep_k4096_d128": (1024, 128, 1024, 4096, "configs[3]: N=1M rows, K=4096, D=128"),
-    "sweep_k8192_d128": (1024, 128, 1024, 8192, "configs[3]: N=1M rows, K=8192, D=128"),
-    "sweep_k512_d64": (1024, 64, 1024, 512, "configs[3]: N=1M rows, K=512, D=64"),
-    "sweep_k2048_d256": (1024, 256, 1024, 2048, "configs[3]: N=1M rows, K=2048, D=256"),
-    "sweep_k8192_d256": (512, 256, 1024, 8192, "configs[3]: N=512k rows, K=8192, D=256"),
+    "loc16": (16, 64, 201, 1024, "configs[4] RIR side: train_location.py quantizer, batch 16"),
 }
+SWEEP_K = (512, 1024, 2048, 4096, 8192)
+SWEEP_D = (64, 128, 256)
+SWEEP_N = 1 << 20
+for _k in SWEEP_K:
+    for _d in SWEEP_D:
+        WORKLOADS[f"sweep_k{_k}_d{_d}"] = (1024, _d, 1024, _k, f"configs[3]: N=1M rows, K={_k}, D={_d}")
+SWEEP_CORNERS = ((512, 64), (1024, 64), (4096, 128), (8192, 256))
 BETA = 0.25
 L2_BYTES = 126 * 1024 * 1024
-KERNEL_NAMES = ["prepare_codebook", "argmin_tc", "argmin_exact", "rows", "backward", "finalize", "onehot", "allreduce"]
+KERNEL_NAMES = ["prepare_codebook", "forward", "argmin_exact", "rows", "backward", "finalize", "onehot", "exchange"]
+METRIC = "quantized vectors/sec (VQ fwd+bwd)"
+REFERENCE_ROOTS = ("/root/reference", os.path.join(ROOT, "baseline", "_ref"))
 
 
 def load_peaks():
@@ -60,12 +73,20 @@ def load_peaks():
 
 
 def load_traffic():
-    """dram bytes per launch of each kernel from the committed ncu --set full capture (or None)."""
+    """DRAM bytes per launch of each kernel from the committed `ncu --set full` capture (profiles/traffic.json)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f)
     return {}
+
+
+def make_config(name, world):
+    """The workload description both arms print (identical dictionaries, so the driver can pair them)."""
+    B, D, T, K, desc = WORKLOADS[name]
+    return {"workload": f"{name}: {desc}", "B": B, "D": D, "T": T, "K": K, "rows_per_gpu": B * T, "beta": BETA,
+            "encodings": "dense one-hot" if B * T * K * 4 <= (8 << 30) else "indices only",
+            "parallelism": f"dp{world}" if world > 1 else "single GPU"}
 
 
 class ClockSampler:
@@ -128,36 +149,100 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU implementation of the path.  The reference is a Python module
-# that cannot travel to the GPU box, so this times the oracle port (oracle/vq_oracle.py: the same aten
-# calls as vector_quantizer.py:29-58, bit-identical to it on CPU) with all host threads.
+# reference arm: the reference's own CPU implementation of the path.  Where the reference tree is present
+# (/root/reference in the authoring container, or baseline/_ref) the UNMODIFIED class
+# acoustic_locating_vq_vae.vq_vae.vector_quantizer.VectorQuantizer is imported and timed (kind "reference");
+# it is a Python module and does not travel to the GPU box, so there the oracle port is timed instead
+# (oracle/vq_oracle.py: the same aten calls as vector_quantizer.py:29-58, asserted bit-identical to the class
+# by tests/test_oracle.py) -- kind "port".
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_run(B, D, T, K, steps, warmup, budget_s=150.0):
+def import_reference_class():
+    for root in REFERENCE_ROOTS:
+        if os.path.isdir(os.path.join(root, "src", "acoustic_locating_vq_vae")):
+            for p in (root, os.path.join(root, "src")):
+                if p not in sys.path:
+                    sys.path.insert(0, p)
+            try:
+                from acoustic_locating_vq_vae.vq_vae.vector_quantizer import VectorQuantizer
+                return VectorQuantizer, root
+            except Exception:
+                continue
+    return None, None
+
+
+def cpu_reference_run(name, steps, warmup, budget_s=150.0):
+    """`steps` timed steps of forward + `(loss + quantized.sum()).backward()` on all host threads.  The batch is only cut
+    (from the front) when the whole run would exceed budget_s; the sample string and rows_per_step say what ran."""
     import torch
-    from oracle import vq_oracle
+    B, D, T, K, _ = WORKLOADS[name]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     E = torch.randn(K, D)
     z = torch.randn(B, D, T)
+    cls, root = import_reference_class()
+    if cls is not None:
+        vq = cls(K, D, BETA)
+        vq._embedding.weight.data.copy_(E)
+        kind = "reference"
+
+        def run(zz):
+            vq._embedding.weight.grad = None
+            zz = zz.detach().requires_grad_(True)
+            loss, q, perp, enc = vq(zz)
+            (loss + q.sum()).backward()
+            return float(loss)
+    else:
+        from oracle import vq_oracle
+        kind = "port"
+
+        def run(zz):
+            return float(vq_oracle.forward_backward_dense(zz, E, BETA).loss)
     t0 = time.perf_counter()
-    vq_oracle.forward_backward_dense(z, E, BETA)
-    t_probe = time.perf_counter() - t0
+    run(z[:max(1, B // 8)].contiguous())
+    t_probe = (time.perf_counter() - t0) * 8
     b_eff = B
-    total = (steps + warmup) * t_probe
-    if total > budget_s:
-        b_eff = max(1, int(B * budget_s / total))
+    if (steps + warmup) * t_probe > budget_s:
+        b_eff = max(1, int(B * budget_s / ((steps + warmup) * t_probe)))
     zs = z[:b_eff].contiguous()
     for _ in range(warmup):
-        vq_oracle.forward_backward_dense(zs, E, BETA)
+        run(zs)
     t0 = time.perf_counter()
     for _ in range(steps):
-        vq_oracle.forward_backward_dense(zs, E, BETA)
+        loss = run(zs)
     dt = time.perf_counter() - t0
     rows = b_eff * T
-    return dict(value=rows * steps / dt, ms_per_step=1e3 * dt / steps, cores=cores, rows_per_step=rows,
-                sample=f"{b_eff} of {B} batch items per step ({rows} rows), {steps} timed steps, "
+    what = f"unmodified reference class from {root}" if kind == "reference" else "oracle port of the reference class (reference tree absent)"
+    return dict(value=rows * steps / dt, ms_per_step=1e3 * dt / steps, cores=cores, rows_per_step=rows, kind=kind, loss=loss,
+                sample=f"{what}; {b_eff} of {B} batch items per step ({rows} rows), {steps} timed steps, "
                        f"torch {torch.__version__} CPU, {cores} threads")
+
+
+def measure_tf32_peak(torch, dev):
+    """cuBLAS TF32 GEMM 8192^3 (the yardstick for the tensor-bound sweep points): best of 10, and back to back for ~1.5 s."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev); b = torch.randn(n, n, device=dev); c = torch.empty(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        best = 1e9
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(10):
+            e0.record(); torch.matmul(a, b, out=c); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(20, int(1500.0 / best))
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record(); torch.cuda.synchronize()
+        sus = e0.elapsed_time(e1) / reps
+        fl = 2.0 * n ** 3
+        return {"tf32_tflops_burst": round(fl / (best * 1e-3) / 1e12, 1), "tf32_tflops_sustained": round(fl / (sus * 1e-3) / 1e12, 1),
+                "how": "torch.matmul fp32 with allow_tf32=True (cuBLAS), 8192^3, best of 10 / back to back for ~1.5 s"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 def main():
@@ -170,14 +255,16 @@ def main():
     ap.add_argument("--no-onehot", action="store_true", help="indices-only mode (encodings not materialised)")
     ap.add_argument("--exact", action="store_true", help="CUDA-core exact path instead of tcgen05")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
-    ap.add_argument("--no-fuse", action="store_true", help="argmin and row epilogue as two kernels (VQ_FLAG_NO_FUSE)")
     ap.add_argument("--no-screen", action="store_true", help="3xTF32 tensor kernels instead of screen + exact refine (VQ_FLAG_NO_SCREEN)")
-    ap.add_argument("--screen", action="store_true", help="force screen + exact refine (VQ_FLAG_SCREEN)")
-    ap.add_argument("--split-backward", action="store_true", help="N > 1: dE-only backward, all-reduce on a side stream while the dz pass runs (measured slower than the serial default: cross-stream events cost more than the overlap gains)")
-    ap.add_argument("--fused-allreduce", action="store_true", help="N > 1: vq_backward_allreduce (one kernel, exchange overlaps the dz pass; measured slower) instead of vq_backward + vq_allreduce_push")
-    ap.add_argument("--nccl", action="store_true", help="N > 1: use NCCL for the per-step all-reduce instead of vq_allreduce_sum")
+    ap.add_argument("--no-sums", action="store_true", help="scatter-add dE in the backward (flat / private kernel) instead of code sums in the forward")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per input buffer")
+    ap.add_argument("--nccl", action="store_true", help="N > 1: NCCL all_reduce of [dE|hist|sse] after the backward instead of the NVLink exchange")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: the backward waits for the exchange before it starts (no overlap with the dz pass)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the configs[3] corner points")
+    ap.add_argument("--sweep-all", action="store_true", help="all 15 (K, D) sweep points instead of the 4 corners")
+    ap.add_argument("--no-module", action="store_true", help="skip the nn.Module timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -187,22 +274,24 @@ def main():
     B, D, T, K, desc = WORKLOADS[args.workload]
     N = B * T
     emit_onehot = not args.no_onehot and N * K * 4 <= (8 << 30)
+    config = make_config(args.workload, max(world, args.gpus))
+    if args.no_onehot:
+        config["encodings"] = "indices only"
 
     # -------------------------------------------------------------------------------- reference arm
     if args.impl == "reference":
         if rank != 0:
             return 0
-        r = cpu_reference_run(B, D, T, K, args.steps, args.warmup)
+        r = cpu_reference_run(args.workload, args.steps, args.warmup)
+        if r["rows_per_step"] != N:
+            config["rows_per_gpu"] = r["rows_per_step"]      # the budget forced a smaller batch: say so where the driver looks
         line = {
-            "impl": "reference", "metric": "quantized vectors/sec (VQ fwd+bwd)", "value": r["value"],
-            "unit": "vectors/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "B": B, "D": D, "T": T, "K": K, "rows_per_step": r["rows_per_step"],
-                       "beta": BETA, "encodings": "dense one-hot (as the reference)"},
-            "cpu_baseline": {"value": r["value"], "unit": "vectors/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "vectors/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": r["value"], "unit": "vectors/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
+            "gpu_launches": 0, "loss": r["loss"],
         }
         print(json.dumps(line))
         return 0
@@ -224,179 +313,252 @@ def main():
     lib = b200vq.load_library()
     L.check(lib.vq_device_check())
     peaks = load_peaks()
-
-    torch.manual_seed(1000 + rank)
-    g = torch.Generator(device=dev)
-    g.manual_seed(1000 + rank)
-    torch.manual_seed(0)
-    E = torch.randn(K, D).to(dev)                                     # same codebook on every rank
-    nbuf = max(3, int(1.25 * L2_BYTES / (N * D * 4)) + 1)             # rotating inputs: set larger than L2
-    zs = [torch.randn(N, D, device=dev, generator=g) for _ in range(nbuf)]
-    gs = [torch.randn(N, D, device=dev, generator=g) for _ in range(nbuf)]
-    e2 = torch.empty(K, device=dev); ehi = torch.empty(K, D, device=dev); elo = torch.empty(K, D, device=dev)
-    q = torch.empty(N, D, device=dev); idx = torch.empty(N, dtype=torch.int32, device=dev)
-    onehot = torch.empty(N, K, device=dev) if emit_onehot else None
-    # [dE | hist | sse] -> one all-reduce per step.  With N > 1 the buffer lives in symmetric (peer-mapped) memory and
-    # is reduced by our own one-shot NVLink kernel (vq_allreduce_sum); NCCL is the fallback.
-    n_packed = K * D + K + 1
-    sym = None
-    collective = "none"
-    if world > 1 and not args.nccl:
-        try:
-            par = import_module("acoustic_locating_vq-vae_b200.parallel")
-            sym = par.PushAllReduce(n_packed, dev)
-            collective = "low-latency push all-reduce over NVLink peer memory (vq_allreduce_push, " + ("NVLS multimem.st" if sym.nvls else "P2P stores") + ")"
-        except Exception as e:      # symmetric memory unavailable: keep going with NCCL
-            sym = None
-            collective = f"NCCL all_reduce (symmetric memory unavailable: {type(e).__name__})"
-    elif world > 1:
-        collective = "NCCL all_reduce"
-    fused_ar = sym is not None and D % 4 == 0 and args.fused_allreduce
-    split_bwd = sym is not None and not fused_ar and args.split_backward
-    main_stream = torch.cuda.current_stream()
-    side_stream = torch.cuda.Stream(device=dev) if split_bwd else None
-    ev_dE, ev_ar = torch.cuda.Event(), torch.cuda.Event()
-    if split_bwd:
-        collective = ("backward split in two (dE, then dz) so that the push all-reduce of [dE|hist|sse] over NVLink peer memory "
-                      "(vq_allreduce_push, " + ("NVLS multimem.st" if sym.nvls else "P2P stores") + ") runs on a side stream while dz is computed")
-    if fused_ar:
-        collective = "backward + two-step push all-reduce fused in one kernel (vq_backward_allreduce, " + ("NVLS multimem.st" if sym.nvls else "P2P stores") + ")"
-    packs = [sym.payload()] if sym is not None else [torch.zeros(n_packed, device=dev)]
-    views = [(pk[:K * D], pk[K * D:K * D + K], pk[K * D + K:]) for pk in packs]
-    scal = torch.empty(2, device=dev)                                 # loss, perplexity
-    dz = torch.empty(N, D, device=dev)
-    g_loss = torch.ones((), device=dev)
-    fwd_flags = ((L.FLAG_ONEHOT if emit_onehot else 0) | (L.FLAG_EXACT if args.exact else 0) |
-                 (L.FLAG_NO_FUSE if args.no_fuse else 0) | (L.FLAG_NO_SCREEN if args.no_screen else 0) | (L.FLAG_SCREEN if args.screen else 0) | L.FLAG_STATE_READY)
-    bwd_flags = L.FLAG_TRAIN_VQ
-    # the bucket backward writes every dE element exactly once (VQ_FLAG_ZERO_DE = plain stores); the other paths
-    # accumulate with atomics into a buffer that the prepare launch zeroes
-    zero_in_prepare = lib.vq_backward_path(N, K, D, 0) != 1
-    if not zero_in_prepare:
-        bwd_flags |= L.FLAG_ZERO_DE
-    wsb = lib.vq_workspace_bytes(N, K, D, fwd_flags)
-    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-    st = torch.cuda.current_stream().cuda_stream
-    n_dE = N * world
     P = lambda t: None if t is None else t.data_ptr()
 
-    def step(i):
-        z = zs[i % nbuf]
-        dE, hist, sse = views[0]
-        # one launch: codebook norms + tf32 split + reset of hist / completion counter / dE accumulator
-        L.check(lib.vq_prepare_step(P(E), K, D, P(e2), P(ehi), P(elo), P(hist), P(ws), wsb, P(dE) if zero_in_prepare else None, st))
-        L.check(lib.vq_forward(P(z), P(E), P(e2), P(ehi), P(elo), N, K, D, BETA, fwd_flags, P(q), P(idx), P(onehot),
-                               P(hist), P(sse), scal.data_ptr(), scal.data_ptr() + 4, P(ws), wsb, st))
-        if split_bwd:
-            # data parallel: codebook gradient first, then its all-reduce on a side stream WHILE the dz pass runs
-            L.check(lib.vq_backward(None, P(g_loss), P(z), P(E), P(idx), N, N, n_dE, K, D, BETA, bwd_flags | L.FLAG_NO_DZ,
-                                    None, P(dE), st))
-            ev_dE.record(main_stream)
-            side_stream.wait_event(ev_dE)
-            sym.reduce(side_stream.cuda_stream)          # reduced [dE | hist | sse] lands in sym.out
-            ev_ar.record(side_stream)
-            L.check(lib.vq_backward(P(gs[i % nbuf]), P(g_loss), P(z), P(E), P(idx), N, N, n_dE, K, D, BETA, 0, P(dz), None, st))
-            main_stream.wait_event(ev_ar)                # the step ends when both are done
+    def make_state(N, K, D, onehot_on, nbuf, seed):
+        """device buffers of one workload; inputs rotate over `nbuf` z / g_q buffers"""
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+        s = dict(N=N, K=K, D=D, nbuf=nbuf)
+        torch.manual_seed(0)
+        s["E"] = torch.randn(K, D).to(dev)                              # same codebook on every rank
+        s["zs"] = [torch.randn(N, D, device=dev, generator=g) for _ in range(nbuf)]
+        s["gs"] = [torch.randn(N, D, device=dev, generator=g) for _ in range(nbuf)]
+        s["e2"] = torch.empty(K, device=dev); s["ehi"] = torch.empty(K, D, device=dev); s["elo"] = torch.empty(K, D, device=dev)
+        s["q"] = torch.empty(N, D, device=dev); s["idx"] = torch.empty(N, dtype=torch.int32, device=dev)
+        s["onehot"] = torch.empty(N, K, device=dev) if onehot_on else None
+        s["stats"] = torch.zeros(K + 3, device=dev)                     # [hist (K) | sse | loss | perplexity]
+        s["dz"] = torch.empty(N, D, device=dev); s["dE"] = torch.zeros(K, D, device=dev)
+        s["g_loss"] = torch.ones((), device=dev)
+        s["reduced"] = torch.zeros(K * D + K + 1, device=dev)           # data parallel: all-reduced [S | hist | sse]
+        s["packed"] = torch.zeros(K * D + K + 1, device=dev)            # data parallel without code sums: [dE | hist | sse]
+        s["wsb"] = lib.vq_workspace_bytes(N, K, D, 0)
+        s["ws"] = torch.empty(s["wsb"], dtype=torch.uint8, device=dev)
+        L.check(lib.vq_workspace_init(P(s["ws"]), s["wsb"], torch.cuda.current_stream().cuda_stream))
+        fwd = (L.FLAG_ONEHOT if onehot_on else 0) | (L.FLAG_EXACT if args.exact else 0) | (L.FLAG_NO_SCREEN if args.no_screen else 0)
+        s["sums"] = (not args.no_sums) and not args.nccl and bool(lib.vq_step_uses_code_sums(N, K, D, fwd | L.FLAG_CODE_SUMS))
+        s["fwd_flags"] = fwd | (L.FLAG_CODE_SUMS if s["sums"] else 0)
+        return s
+
+    nbuf = max(3, int(1.25 * L2_BYTES / (N * D * 4)) + 1)                # rotating inputs: set larger than L2
+    S0 = make_state(N, K, D, emit_onehot, nbuf, 1000 + rank)
+    n_packed = K * D + K + 1
+    exch = None
+    collective = "none"
+    if world > 1 and not args.nccl:
+        par = import_module("acoustic_locating_vq-vae_b200.parallel")
+        ok, why = True, ""
+        try:
+            exch = par.PeerExchange(n_packed, dev)
+        except Exception as e:          # symmetric memory unavailable on this rank
+            ok, why = False, f"{type(e).__name__}"
+        if not par.agree(ok):           # every rank takes the same collective
+            if exch is not None:
+                exch.close()
+            exch = None
+            collective = f"NCCL all_reduce (NVLink exchange unavailable on some rank{': ' + why if why else ''})"
+        else:
+            collective = ("[code sums | hist | sse] over NVLink peer memory (vq_dp_exchange_sums, " + ("NVLS multimem.st" if exch.nvls else "P2P stores") + ", "
+                          + ("reduce-scatter + all-gather" if world >= 8 else "one step") + "), launched behind the forward, "
+                          + ("serialised before" if args.no_overlap else "concurrent with") + " the backward's dz pass")
+    elif world > 1:
+        collective = "NCCL all_reduce of [dE | hist | sse] after the backward"
+    n_dE_scale = world
+
+    def step(s, i, st):
+        """one step of the hot path on input buffer i, enqueued on raw stream `st`"""
+        N_, K_, D_ = s["N"], s["K"], s["D"]
+        z, gq = s["zs"][i % s["nbuf"]], s["gs"][i % s["nbuf"]]
+        sp = P(s["stats"])
+        L.check(lib.vq_step_forward(P(z), P(s["E"]), N_, K_, D_, BETA, s["fwd_flags"], P(s["e2"]), P(s["ehi"]), P(s["elo"]), P(s["q"]), P(s["idx"]),
+                                    P(s["onehot"]), sp, sp + 4 * K_, sp + 4 * (K_ + 1), sp + 4 * (K_ + 2), P(s["ws"]), s["wsb"], st))
+        n_dE = N_ * n_dE_scale
+        if s["sums"]:
+            red = None
+            bfl = L.FLAG_TRAIN_VQ | L.FLAG_ZERO_DE | L.FLAG_CODE_SUMS
+            if exch is not None:
+                exch.exchange_sums(s["ws"], N_, K_, D_, s["stats"][:K_ + 1], s["reduced"], st)
+                red = s["reduced"]
+                if not args.no_overlap:
+                    bfl |= L.FLAG_OVERLAP_EXCHANGE
+            L.check(lib.vq_step_backward(P(gq), P(s["g_loss"]), P(z), P(s["E"]), P(s["idx"]), N_, N_, n_dE, K_, D_, BETA, bfl, P(s["dz"]), P(s["dE"]),
+                                         P(s["ws"]), s["wsb"], P(red), st))
             return
-        if fused_ar:
-            # backward + all-reduce in ONE kernel: the NVLink exchange overlaps the dz pass; result in sym.out
-            sym.backward_reduce(P(gs[i % nbuf]), P(g_loss), P(z), P(E), P(idx), N, n_dE, K, D, BETA, bwd_flags, P(dz), st)
+        if world == 1:
+            L.check(lib.vq_backward(P(gq), P(s["g_loss"]), P(z), P(s["E"]), P(s["idx"]), N_, N_, n_dE, K_, D_, BETA, L.FLAG_TRAIN_VQ | L.FLAG_ZERO_DE,
+                                    P(s["dz"]), P(s["dE"]), st))
             return
-        L.check(lib.vq_backward(P(gs[i % nbuf]), P(g_loss), P(z), P(E), P(idx), N, N, n_dE, K, D, BETA, bwd_flags,
-                                P(dz), P(dE), st))
-        if sym is not None:
-            sym.reduce(st)                       # reduced [dE | hist | sse] lands in sym.out
-        elif world > 1:
-            dist.all_reduce(packs[0])
+        # data parallel without code sums: backward into the packed buffer, then one all-reduce of [dE | hist | sse]
+        pk = s["packed"]
+        L.check(lib.vq_backward(P(gq), P(s["g_loss"]), P(z), P(s["E"]), P(s["idx"]), N_, N_, n_dE, K_, D_, BETA, L.FLAG_TRAIN_VQ | L.FLAG_ZERO_DE,
+                                P(s["dz"]), P(pk), st))
+        pk[K_ * D_:].copy_(s["stats"][:K_ + 1])
+        if exch is not None:
+            exch.allreduce(pk, s["reduced"], st)
+        else:
+            dist.all_reduce(pk)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    use_graph = not args.no_graph and not (world > 1 and exch is None)   # NCCL stays eager
+    cur = torch.cuda.current_stream()
+
+    def build_runner(s):
+        """returns run(i): replays the captured step for buffer i (or launches it eagerly)"""
+        if not use_graph:
+            return lambda i: step(s, i, cur.cuda_stream), 0
+        for i in range(min(3, s["nbuf"])):          # warm every code path before capture (lazy attribute setting, descriptors)
+            step(s, i, cur.cuda_stream)
+        torch.cuda.synchronize()
+        graphs = []
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for i in range(s["nbuf"]):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    step(s, i, torch.cuda.current_stream().cuda_stream)
+                graphs.append(g)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        return (lambda i: graphs[i % s["nbuf"]].replay()), len(graphs)
+
+    run0, n_graphs = build_runner(S0)
+    l0 = lib.vq_launch_count()
+    step(S0, 0, cur.cuda_stream)
+    launches_per_step = lib.vq_launch_count() - l0
+    barrier()
+
     sampler = ClockSampler(local_rank)
     # ---- device-resident throughput ------------------------------------------------------------------
     for i in range(args.warmup):
-        step(i)
+        run0(i)
     barrier()
     sampler.start()
-    launches0 = lib.vq_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
-        step(args.warmup + i)
+        run0(args.warmup + i)
     ev1.record()
     barrier()
-    launches = lib.vq_launch_count() - launches0
     ms = ev0.elapsed_time(ev1)
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
     value = N * world * args.steps / (ms * 1e-3)
-    loss_val, perp_val = [float(x) for x in scal.tolist()]
+    loss_val, perp_val = [float(x) for x in S0["stats"][K + 1:].tolist()]
+    dp_status = None
+    if exch is not None:
+        calls, err = exch.status(cur.cuda_stream)
+        dp_status = {"calls": calls, "error_word": err}
 
-    # ---- per-kernel timing (CUDA events on the launching stream) for the roofline ---------------------
-    lib.vq_profile_enable(1)
-    for i in range(args.steps):
-        step(i)
-    barrier()
-    kern = {}
-    for kid, name in enumerate(KERNEL_NAMES):
-        tot, cnt = ctypes.c_double(0), ctypes.c_int64(0)
-        L.check(lib.vq_profile_read(kid, ctypes.byref(tot), ctypes.byref(cnt)))
-        if cnt.value:
-            kern[name] = {"launches": cnt.value, "avg_us": 1e3 * tot.value / cnt.value}
-    lib.vq_profile_enable(0)
+    # ---- per-kernel timing (CUDA events on the launching stream, eager launches) for the roofline ---------
+    def profile(s, reps):
+        lib.vq_profile_enable(1)
+        for i in range(reps):
+            step(s, i, cur.cuda_stream)
+        barrier()
+        kern = {}
+        for kid, name in enumerate(KERNEL_NAMES):
+            tot, cnt = ctypes.c_double(0), ctypes.c_int64(0)
+            L.check(lib.vq_profile_read(kid, ctypes.byref(tot), ctypes.byref(cnt)))
+            if cnt.value:
+                kern[name] = {"launches": cnt.value, "avg_us": 1e3 * tot.value / cnt.value}
+        lib.vq_profile_enable(0)
+        return kern
+
+    kern = profile(S0, args.steps)
     tot_us = sum(k["avg_us"] * k["launches"] for k in kern.values()) / max(args.steps, 1)
     for k in kern.values():
         k["share"] = round(k["avg_us"] * k["launches"] / args.steps / tot_us, 4)
         k["avg_us"] = round(k["avg_us"], 3)
     dom = max(kern, key=lambda n: kern[n]["avg_us"] * kern[n]["launches"])
     traffic = load_traffic()
-    fused = "rows" not in kern and "argmin_tc" in kern          # row epilogue ran inside the tensor kernel
-    rows_bytes = 4.0 * (2 * N * D + N + K * D + K + (N * K if emit_onehot else 0))
+    fwd_bytes = lambda N_, K_, D_, oh: 4.0 * (2 * N_ * D_ + N_ + K_ * D_ + K_ + (N_ * K_ if oh else 0))
+    bwd_bytes = lambda N_, K_, D_: 4.0 * (3 * N_ * D_ + N_ + 2 * K_ * D_)
     # algorithmic work per launch: SURVEY.md section 8(d) per-row figures x rows per launch (DESIGN.md section 4)
     alg = {
-        "argmin_tc": {"flops": 2.0 * N * K * D, "bytes": rows_bytes if fused else 4.0 * (N * D + N + 2 * K * D)},
+        "forward": {"flops": 2.0 * N * K * D, "bytes": fwd_bytes(N, K, D, emit_onehot)},
         "argmin_exact": {"flops": 2.0 * N * K * D, "bytes": 4.0 * (N * D + N + K * D)},
-        "rows": {"flops": 0.0, "bytes": rows_bytes},
-        "backward": {"flops": 0.0, "bytes": 4.0 * (3 * N * D + N + 2 * K * D)},
+        "rows": {"flops": 0.0, "bytes": fwd_bytes(N, K, D, emit_onehot)},
+        "backward": {"flops": 0.0, "bytes": bwd_bytes(N, K, D)},
         "prepare_codebook": {"flops": 0.0, "bytes": 4.0 * (3 * K * D + K)},
+        "exchange": {"flops": 0.0, "bytes": 4.0 * 2 * n_packed},
     }
     work = alg.get(dom, {"flops": 0.0, "bytes": 0.0})
     dur_s = kern[dom]["avg_us"] * 1e-6
-    tf32_peak = peaks["bf16_tflops"] / 2.0                        # TF32 pipe = half the measured dense bf16 rate
-    t_tensor = work["flops"] / (tf32_peak * 1e12)
+    tf32 = None
+    if world == 1 and not args.no_sweep:
+        tf32 = measure_tf32_peak(torch, dev)
+    tf32_burst = tf32["tf32_tflops_burst"] if tf32 else peaks["bf16_tflops"] / 2.0
+    tf32_sus = tf32["tf32_tflops_sustained"] if tf32 else peaks["bf16_sustained"] / 2.0
+    tf32_src = "measured here (cuBLAS TF32 8192^3)" if tf32 else peaks["source"] + " bf16 / 2"
+    t_tensor = work["flops"] / (tf32_burst * 1e12)
     t_hbm = work["bytes"] / (peaks["hbm_gbs"] * 1e9)
     if t_tensor >= t_hbm:                                          # whichever roofline binds this launch
-        bound, peak, achieved, unit = "tensor", tf32_peak, work["flops"] / dur_s / 1e12, "TFLOP/s"
-        per_launch = work["flops"]
+        bound, peak, achieved, unit, per_launch = "tensor", tf32_burst, work["flops"] / dur_s / 1e12, "TFLOP/s", work["flops"]
     else:
-        bound, peak, achieved, unit = "hbm", peaks["hbm_gbs"], work["bytes"] / dur_s / 1e9, "GB/s"
-        per_launch = work["bytes"]
-    screen_used = (not args.exact and not args.no_screen and not args.no_fuse and K % 256 == 0 and D in (32, 64, 96, 128, 192, 256)
-                   and os.environ.get("B200VQ_SCREEN", "1")[:1] != "0") or (args.screen and K % 256 == 0)
-    fused_name = ("fused forward (vq_screen_kernel: TF32 screen + exact refine + row epilogue)" if screen_used
-                  else "fused forward (argmin_tc2: 3xTF32 + row epilogue)")
-    roofline = {"kernel": (fused_name if fused and dom == "argmin_tc" else dom), "bound": bound,
-                "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": unit, "frac": round(achieved / peak, 4),
-                "traffic": traffic.get(args.workload, {}).get(dom),
-                "peak_source": peaks["source"] + (" bf16/2 (tf32 pipe)" if bound == "tensor" else " copy bandwidth"),
+        bound, peak, achieved, unit, per_launch = "hbm", peaks["hbm_gbs"], work["bytes"] / dur_s / 1e9, "GB/s", work["bytes"]
+    tensor_path = bool(lib.vq_forward_uses_tensor_path(N, K, D, S0["fwd_flags"]))
+    screen_used = tensor_path and not args.no_screen and K % 256 == 0 and D in (32, 64, 96, 128, 192, 256) and os.environ.get("B200VQ_SCREEN", "1")[:1] != "0"
+    kname = {"forward": ("vq_screen_kernel (fused forward: codebook norms, TF32 screen + exact refine, row epilogue, one-hot"
+                         + (", code sums" if S0["sums"] else "") + ")") if screen_used else "fused forward (argmin_tc2: 3xTF32 + row epilogue)"}.get(dom, dom)
+    tr = traffic.get(args.workload, {})
+    roofline = {"kernel": kname, "bound": bound, "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": unit,
+                "frac": round(achieved / peak, 4), "traffic": tr.get(dom),
+                "traffic_source": tr.get("source", "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one committed ncu --set full capture (not measured in this run)"),
+                "peak_source": (tf32_src if bound == "tensor" else peaks["source"] + " copy bandwidth"),
                 "per_launch": per_launch, "avg_us": kern[dom]["avg_us"],
+                "step": {"bytes": fwd_bytes(N, K, D, emit_onehot) + bwd_bytes(N, K, D), "us": round(1e3 * ms / args.steps, 3),
+                         "frac_of_hbm": round((fwd_bytes(N, K, D, emit_onehot) + bwd_bytes(N, K, D)) / (1e-3 * ms / args.steps) / 1e9 / peaks["hbm_gbs"], 4)},
                 "other_roof": {"tensor_tflops": round(work["flops"] / dur_s / 1e12, 2), "hbm_gbs": round(work["bytes"] / dur_s / 1e9, 1)}}
 
-    # ---- end to end through the host-buffer C ABI: pinned host z in, loss/perplexity/indices out ------
-    e2e = None
-    if not args.skip_e2e:
+    # ---- data parallel: the exchange against NCCL, outside every timed region ---------------------------
+    coll_check = None
+    if world > 1 and exch is not None:
+        torch.manual_seed(77 + rank)
+        pay = torch.randn(n_packed, device=dev)
+        out = torch.empty_like(pay)
+        exch.allreduce(pay, out, cur.cuda_stream)
+        ref = pay.clone()
+        dist.all_reduce(ref)
+        d1 = float((out - ref).abs().max())
+        # the step's gradient: DP step vs NCCL all-reduce of the local gradients (same rows, same scale)
+        step(S0, 0, cur.cuda_stream)
+        torch.cuda.synchronize()
+        dE_dp = S0["dE"].clone()
+        stats_dp = S0["reduced"][K * D:].clone()
+        loc = torch.zeros(K, D, device=dev)
+        L.check(lib.vq_backward(P(S0["gs"][0]), P(S0["g_loss"]), P(S0["zs"][0]), P(S0["E"]), P(S0["idx"]), N, N, N * world, K, D, BETA,
+                                L.FLAG_TRAIN_VQ | L.FLAG_ZERO_DE | L.FLAG_BWD_FLAT, P(S0["dz"]), P(loc), cur.cuda_stream))
+        dist.all_reduce(loc)
+        st_loc = S0["stats"][:K + 1].clone()
+        dist.all_reduce(st_loc)
+        d2 = float((dE_dp - loc).abs().max())
+        d3 = float((stats_dp - st_loc).abs().max())
+        chk = torch.tensor([float(out.double().sum()), float(dE_dp.double().sum())], dtype=torch.float64, device=dev)
+        gathered = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(gathered, chk)
+        same = all(torch.equal(gathered[0], g_) for g_ in gathered)
+        coll_check = {"max_abs_diff": d1, "vs": "dist.all_reduce (NCCL) on the same random payload", "payload_floats": n_packed,
+                      "step_dE_max_abs_diff": d2, "step_dE_scale": float(loc.abs().max()), "step_stats_max_abs_diff": d3,
+                      "checksums_identical_on_all_ranks": bool(same), "status": dp_status}
+
+    # ---- end to end through the host-buffer C ABI ---------------------------------------------------------
+    def run_e2e(full):
         ctx = ctypes.c_void_p()
         L.check(lib.vq_host_ctx_create(N, K, D, ctypes.byref(ctx)))
-        E_host = E.cpu().contiguous()
+        E_host = S0["E"].cpu().contiguous()
         L.check(lib.vq_host_set_codebook(ctx, E_host.data_ptr()))
         nhost = 4
         z_host = [torch.randn(N, D).pin_memory() for _ in range(nhost)]
-        res = [dict(loss=torch.zeros(1).pin_memory(), perp=torch.zeros(1).pin_memory(),
-                    idx=torch.zeros(N, dtype=torch.int32).pin_memory()) for _ in range(2)]
+        res = [dict(loss=torch.zeros(1).pin_memory(), perp=torch.zeros(1).pin_memory(), idx=torch.zeros(N, dtype=torch.int32).pin_memory(),
+                    q=torch.zeros(N, D).pin_memory() if full else None, dz=torch.zeros(N, D).pin_memory() if full else None,
+                    dE=torch.zeros(K, D).pin_memory() if full else None) for _ in range(2)]
         lane_t = []
         if world > 1:
             for lane in range(2):
@@ -413,21 +575,23 @@ def main():
             lane = i & 1
             L.check(lib.vq_host_wait(ctx, lane))          # results of step i-2 are now in res[lane]
             r = res[lane]
-            L.check(lib.vq_host_step_async(ctx, lane, z_host[i % nhost].data_ptr(), None, N, n_dE, BETA,
+            L.check(lib.vq_host_step_async(ctx, lane, z_host[i % nhost].data_ptr(), None, N, N * world, BETA,
                                            L.FLAG_TRAIN_VQ | (L.FLAG_EXACT if args.exact else 0),
-                                           r["loss"].data_ptr(), r["perp"].data_ptr(), r["idx"].data_ptr(), None, None, None))
-            if world > 1:
+                                           r["loss"].data_ptr(), r["perp"].data_ptr(), r["idx"].data_ptr(), P(r["q"]), P(r["dz"]),
+                                           None if (world > 1 or not full) else P(r["dE"])))
+            if world > 1:                                 # dE crosses the ranks before it goes home
                 s_, t_ = lane_t[lane]
                 with torch.cuda.stream(s_):
                     dist.all_reduce(t_)
+                    if full:
+                        r["dE"].view(-1).copy_(t_, non_blocking=True)
 
-        e_steps = args.steps
         for i in range(args.warmup):
             host_step(i)
         L.check(lib.vq_host_wait(ctx, 0)); L.check(lib.vq_host_wait(ctx, 1))
         barrier()
         L.check(lib.vq_host_timer_start(ctx))
-        for i in range(e_steps):
+        for i in range(args.steps):
             host_step(i)
         e_ms = ctypes.c_float(0)
         L.check(lib.vq_host_timer_stop_ms(ctx, ctypes.byref(e_ms)))
@@ -437,38 +601,128 @@ def main():
             t = torch.tensor([e_ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = float(t[0])
-        e2e = {"value": N * world * e_steps / (e_ms * 1e-3), "unit": "vectors/s", "h2d_bytes_per_step": N * D * 4,
-               "d2h_bytes_per_step": N * 4 + 8, "ms_per_step": e_ms / e_steps,
-               "api": "vq_host_step_async (2 lanes; pinned host z -> loss, perplexity, indices on the host)",
-               "loss": float(res[0]["loss"][0])}
+        d2h = N * 4 + 8 + ((2 * N * D + K * D) * 4 if full else 0)
+        out = {"value": N * world * args.steps / (e_ms * 1e-3), "unit": "vectors/s", "h2d_bytes_per_step": N * D * 4, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e_ms / args.steps, "loss": float(res[0]["loss"][0]),
+               "api": "vq_host_step_async (2 lanes; pinned host z in; " + ("quantized, dz, dE, indices, loss, perplexity" if full else "indices, loss, perplexity")
+                      + " back on the host)"}
+        if full:
+            out["encodings"] = "indices (N int32); the dense (N, K) one-hot is rebuilt by the caller (one store per row), not shipped over PCIe"
         lib.vq_host_ctx_destroy(ctx)
+        return out
+
+    e2e = e2e_lean = None
+    if not args.skip_e2e:
+        e2e = run_e2e(True)
+        e2e_lean = run_e2e(False)
     sampler.stop()
+
+    # ---- configs[3]: sweep corner points (N = 1M rows, indices only), single GPU ----------------------------
+    sweep = None
+    if world == 1 and not args.no_sweep and not args.workload.startswith("sweep"):
+        sweep = {"n_rows": SWEEP_N, "encodings": "indices only", "tf32_peak_tflops": {"burst": tf32_burst, "sustained": tf32_sus, "source": tf32_src},
+                 "note": "frac_fwd = algorithmic 2NKD / t_fwd over the sustained TF32 peak; frac = T_roof / (t_fwd + t_bwd), "
+                         "T_roof = max(2NKD / P_tf32, bytes_fwd / BW) + bytes_bwd / BW (SURVEY.md 8d)", "points": []}
+        pts = [(k, d) for k in SWEEP_K for d in SWEEP_D] if args.sweep_all else SWEEP_CORNERS
+        del S0["zs"][1:], S0["gs"][1:]
+        for (k_, d_) in pts:
+            torch.cuda.empty_cache()
+            s = make_state(SWEEP_N, k_, d_, False, 1 if d_ >= 128 else 2, 5)
+            for i in range(2):
+                step(s, i, cur.cuda_stream)
+            torch.cuda.synchronize()
+            reps = 4
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(reps):
+                step(s, i, cur.cuda_stream)
+            b.record(); torch.cuda.synchronize()
+            t_step = a.elapsed_time(b) / reps * 1e3
+            kk = profile(s, reps)
+            t_f = kk.get("forward", kk.get("argmin_exact", {"avg_us": float("nan")}))["avg_us"] + kk.get("prepare_codebook", {"avg_us": 0.0})["avg_us"]
+            t_b = kk["backward"]["avg_us"]
+            fl = 2.0 * SWEEP_N * k_ * d_
+            bf, bb = fwd_bytes(SWEEP_N, k_, d_, False), bwd_bytes(SWEEP_N, k_, d_)
+            t_roof = max(fl / (tf32_sus * 1e12), bf / (peaks["hbm_gbs"] * 1e9)) + bb / (peaks["hbm_gbs"] * 1e9)
+            sweep["points"].append({"K": k_, "D": d_, "fwd_us": round(t_f, 1), "bwd_us": round(t_b, 1), "step_us": round(t_step, 1),
+                                    "fwd_tflops": round(fl / (t_f * 1e-6) / 1e12, 1), "frac_fwd": round(fl / (t_f * 1e-6) / 1e12 / tf32_sus, 3),
+                                    "bwd_frac_hbm": round(bb / (t_b * 1e-6) / 1e9 / peaks["hbm_gbs"], 3),
+                                    "frac": round(t_roof * 1e6 / (t_f + t_b), 3), "vectors_per_s": round(SWEEP_N / (t_step * 1e-6)),
+                                    "code_sums": s["sums"], "backward_path": "streaming (code sums)" if s["sums"] else ["flat", "", "private"][lib.vq_backward_path(SWEEP_N, k_, d_, 0)]})
+            del s
+
+    # ---- the drop-in nn.Module on the same workload (north star: the module is the deliverable) ------------------
+    module = None
+    if world == 1 and not args.no_module:
+        torch.cuda.empty_cache()
+        vq = b200vq.VectorQuantizer(K, D, BETA, return_encodings=emit_onehot).to(dev)
+        vq._embedding.weight.data.copy_(S0["E"])
+        zin = S0["zs"][0].view(B, D, T).clone().requires_grad_(True)      # what _pre_vq_conv hands over: contiguous (B, D, T)
+        gq = torch.ones(B, D, T, device=dev)
+
+        def mstep():
+            vq._embedding.weight.grad = None
+            zin.grad = None
+            loss, q, perp, enc = vq(zin)
+            torch.autograd.backward([loss, q], [None, gq])
+        for _ in range(10):
+            mstep()
+        torch.cuda.synchronize()
+        reps = 50
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            mstep()
+        b.record(); torch.cuda.synchronize()
+        module = {"eager_us_per_step": round(a.elapsed_time(b) / reps * 1e3, 1), "what": "b200vq.VectorQuantizer forward + autograd backward, "
+                  + ("dense one-hot returned" if emit_onehot else "return_encodings=False")}
+        try:
+            gm = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                mstep()
+                with torch.cuda.graph(gm, stream=side):
+                    mstep()
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(reps):
+                gm.replay()
+            b.record(); torch.cuda.synchronize()
+            module["graph_us_per_step"] = round(a.elapsed_time(b) / reps * 1e3, 1)
+        except Exception as e:
+            module["graph_us_per_step"] = None
+            module["graph_error"] = f"{type(e).__name__}: {e}"[:200]
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        probe = cpu_reference_run(B, D, T, K, 1, 1)
+        probe = cpu_reference_run(args.workload, 1, 1)
         reps = max(3, min(50, int(args.cpu_seconds / max(probe["ms_per_step"] * 1e-3, 1e-3))))
-        r = cpu_reference_run(B, D, T, K, reps, 1)
-        cpu = {"value": r["value"], "unit": "vectors/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        r = cpu_reference_run(args.workload, reps, 1)
+        cpu = {"value": r["value"], "unit": "vectors/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
 
     if rank == 0:
         line = {
-            "metric": "quantized vectors/sec (VQ fwd+bwd)", "value": value, "unit": "vectors/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": ("f32" if args.exact else ("f32 (tcgen05 3xTF32 contraction, fp32 accumulate)" if not screen_used else
+            "metric": METRIC, "value": value, "unit": "vectors/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": ("f32" if args.exact or not tensor_path else ("f32 (tcgen05 3xTF32 contraction, fp32 accumulate)" if not screen_used else
                       "f32 (tcgen05 TF32 screening pass + exact fp32 refine of the candidates: indices bit-exact vs the fp32 oracle)")),
-            "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "B": B, "D": D, "T": T, "K": K, "rows_per_gpu": N, "beta": BETA,
-                       "encodings": "dense one-hot emitted" if emit_onehot else "indices only",
-                       "path": "exact CUDA-core" if args.exact else ("tcgen05" if lib.vq_forward_uses_tensor_path(N, K, D, fwd_flags) else "exact CUDA-core"),
-                       "l2": f"inputs rotate over {nbuf} z + {nbuf} g buffers ({2 * nbuf * N * D * 4 >> 20} MiB > 126 MiB L2)",
-                       "parallelism": f"dp{world}: rows sharded, one all-reduce of [dE|hist|sse] per step: {collective}" if world > 1 else "single GPU"},
+            "data": "synthetic", "config": config,
+            "notes": {"path": "tcgen05" if tensor_path else "exact CUDA-core",
+                      "launch": (f"one CUDA graph per input buffer ({n_graphs} graphs), {launches_per_step} kernels per step" if use_graph else f"eager, {launches_per_step} kernels per step"),
+                      "codebook_gradient": "code sums accumulated in the forward's row epilogue, backward = dz stream + scale" if S0["sums"] else "scatter-add in the backward",
+                      "l2": f"inputs rotate over {nbuf} z + {nbuf} g buffers ({2 * nbuf * N * D * 4 >> 20} MiB > 126 MiB L2)",
+                      "collective": collective},
             "clocks": sampler.summary(),
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "kernels": kern,
-            "loss": loss_val, "perplexity": perp_val,
+            "e2e": e2e, "e2e_lean": e2e_lean, "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu,
+            "kernels": kern, "peaks": {"hbm_gbs": peaks["hbm_gbs"], "hbm_source": peaks["source"], "tf32": tf32}, "sweep": sweep, "module": module,
+            "collective_check": coll_check, "loss": loss_val, "perplexity": perp_val,
         }
         print(json.dumps(line))
+    if exch is not None:
+        exch.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VQ_ABI_VERSION 16
+#define VQ_ABI_VERSION 17
 
 /* error codes */
 #define VQ_OK            0
@@ -49,12 +49,16 @@ extern "C" {
 #define VQ_FLAG_STATE_READY (1 << 8) /* forward: vq_prepare_step already reset hist and the workspace counter for this call */
 #define VQ_FLAG_NO_SCREEN  (1 << 9)  /* forward: 3xTF32 tensor kernels, never the screen (1xTF32) + exact-refine kernel */
 #define VQ_FLAG_SCREEN     (1 << 10) /* forward: force the screen + exact-refine kernel wherever its shape constraints allow */
-#define VQ_FLAG_NO_DZ      (1 << 11) /* backward: codebook gradient only (needs TRAIN_VQ; dz may be NULL).  Data parallel runs this, starts the
-                                      all-reduce of dE on a side stream and computes dz with a second call without TRAIN_VQ */
 #define VQ_FLAG_ZERO_DE    (1 << 5)  /* backward: dE = gradient instead of dE += gradient (a memset on `stream`, or plain stores on
                                         the bucket path, which writes every element exactly once) */
+#define VQ_FLAG_CODE_SUMS   (1 << 16) /* vq_step_forward: also accumulate the code sums S_k = sum_{n: idx_n = k} (E_k - z_n) (the codebook
+                                         gradient up to a scalar) in the workspace; vq_step_backward with the same flag then only
+                                         streams dz and scales S.  Applies where vq_step_uses_code_sums() says so */
+#define VQ_FLAG_OVERLAP_EXCHANGE (1 << 17) /* vq_step_backward with reduced_sums: the launch right before this one on the stream was
+                                         vq_dp_exchange_sums -- start the dz pass without waiting for it (ONLY then: with other
+                                         work in between the flag would let dz read inputs that are not complete yet) */
+#define VQ_FLAG_SELF_PREPARE (1 << 15) /* forward: set by vq_step_forward -- no prepare launch preceded this call (screen path only) */
 #define VQ_FLAG_BWD_FLAT    (1 << 12) /* backward: force the flat kernel (one 16-byte red.global.add per element of dE) */
-#define VQ_FLAG_BWD_BUCKET  (1 << 13) /* backward: force the bucket kernel (code-owner CTAs, no atomics) where the shape allows */
 #define VQ_FLAG_BWD_PRIVATE (1 << 14) /* backward: force the shared-memory-private kernel where the shape allows */
 
 typedef void* vq_stream_t;   /* cudaStream_t */
@@ -112,6 +116,21 @@ int vq_forward(const float* z, const float* E, const float* e_norm2,
                float* loss, float* perplexity,
                void* workspace, size_t workspace_bytes, vq_stream_t stream);
 
+/* One entry for "prepare + forward" (the call a training step makes: Adam has just changed E).  The scratch buffers
+ * e_norm2 (K), E_hi (K,D), E_lo (K,D) belong to the caller; E_hi / E_lo may be NULL for shapes the screen + refine
+ * kernel takes (K % 256 == 0, D in {32,64,96,128,192,256}), where the whole forward is ONE launch: the kernel
+ * computes |E_k|^2 itself and feeds the raw codebook to the tensor core (which drops the low 13 mantissa bits; the
+ * candidate margin is widened accordingly, the refine stays exact, indices stay bit-identical to the oracle).
+ * `workspace` (vq_workspace_bytes) must have been zeroed once with vq_workspace_init before its first use and must
+ * not be shared between streams: it carries the call counter and the usage accumulators from call to call.
+ * Outputs and flags as for vq_forward (VQ_FLAG_STATE_READY is implied). */
+int vq_workspace_init(void* workspace, size_t workspace_bytes, vq_stream_t stream);
+int vq_step_forward(const float* z, const float* E, int64_t n_rows, int K, int D, float beta, int flags,
+                    float* e_norm2, float* E_hi, float* E_lo,
+                    float* q_out, int32_t* idx, float* onehot, float* hist, float* sse,
+                    float* loss, float* perplexity,
+                    void* workspace, size_t workspace_bytes, vq_stream_t stream);
+
 /* loss / perplexity from (all-reduced) usage counts and squared error over n_rows_global rows. */
 int vq_finalize_stats(const float* hist, const float* sse, int64_t n_rows_global, int K, int D,
                       float beta, float* loss, float* perplexity, vq_stream_t stream);
@@ -129,8 +148,7 @@ int vq_backward(const float* g_q, const float* g_loss, const float* z, const flo
                 const int32_t* idx, int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE,
                 int K, int D, float beta, int flags, float* dz, float* dE, vq_stream_t stream);
 /* Which kernel vq_backward takes for dE (16-byte aligned pointers assumed): 0 flat (one red.global.add per element),
- * 1 bucket (code-owner CTAs sum their rows in registers: no atomics, every dE element written once; N up to ~200 k),
- * 2 private (per-CTA copy of dE in shared memory, flushed once; N >= 64 K).  dz may be NULL on paths 1 and 2
+ * 2 private (per-CTA copy of dE in shared memory, flushed once; N >> K and K*D small).  dz may be NULL on path 2
  * (codebook gradient only). */
 int vq_backward_path(int64_t n_rows, int K, int D, int flags);
 
@@ -148,39 +166,54 @@ int vq_scatter_add_rows(const int32_t* idx, const float* g, float* dWt, int B, i
 int vq_jitter_apply(float* q, const int32_t* src, int64_t rows, int T, vq_stream_t stream);
 int vq_jitter_backward(float* g, const int32_t* src, int64_t rows, int T, vq_stream_t stream);
 
-/* -- data parallel: one-shot all-reduce over NVLink peer memory ------------------------------------------ */
-/* out[i] = sum over ranks (in rank order: bit-identical everywhere) of rank p's payload[i], i < n_floats.
- * peer_buffers[p] = rank p's symmetric buffer as mapped into this process (torch symmetric memory / CUDA IPC),
- * laid out [payload (n_floats) ... | flags at flag_offset_floats: `world` uint32, zero-initialised].
- * `seq` must increase by one per call on a given buffer pair; callers alternate between TWO buffers so that a
- * buffer is only rewritten after every peer has passed the next call's barrier.  4 <= kid 7 in vq_profile_read. */
-int vq_allreduce_sum(const void* const* peer_buffers, int world, int rank, int64_t flag_offset_floats,
-                     int64_t n_floats, uint32_t seq, float* out, vq_stream_t stream);
+/* -- the backward that pairs with vq_step_forward --------------------------------------------------------------- */
+/* 1 when vq_step_forward(flags | VQ_FLAG_CODE_SUMS) accumulates the code sums for this shape (screen + refine path,
+ * q_out produced): the scatter-add of the codebook gradient then happens in the forward's row epilogue, where
+ * E[idx] - z is in registers anyway, and vq_step_backward is a pure streaming pass. */
+int vq_step_uses_code_sums(int64_t n_rows, int K, int D, int flags);
+/* Same contract as vq_backward.  With VQ_FLAG_CODE_SUMS | VQ_FLAG_TRAIN_VQ (and the flag honoured by the forward, see
+ * above): dz as usual, dE (+)= g_loss * 2 / (n_rows_dE * D) * S with S read from `workspace` (the one the forward
+ * used) or -- data parallel -- from `reduced_sums`, the all-reduced S that vq_dp_exchange_sums (launched on the same
+ * stream right before this call) writes: the dz pass then runs concurrently with the exchange.  Without the flag this
+ * is vq_backward (workspace / reduced_sums unused). */
+int vq_step_backward(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx,
+                     int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags,
+                     float* dz, float* dE, const void* workspace, size_t workspace_bytes,
+                     const float* reduced_sums, vq_stream_t stream);
 
-/* Push ("low-latency") variant: no barrier.  recv_buffers[p] = rank p's symmetric RECEIVE buffer as mapped into this
- * process: at least world x (ceil(n_floats/2) + 2) 16-byte lines {d0, seq, d1, seq}, zero-initialised.
- *   below 8 ranks: every rank stores its payload into slot [rank] of every receive buffer, then polls its own slots
- *     until all lines carry `seq` and sums them in rank order (one NVLink one-way latency);
- *   from 8 ranks: reduce-scatter + all-gather through the same buffers (rank j owns slice j: two latencies, but only
- *     2 x payload instead of world x payload lands in every rank).  B200VQ_AR_ALGO=1|2 forces either.
- * Results are bit-identical on every rank and between the two algorithms.  `seq` >= 1 and increases by one per call
- * on a given buffer; callers alternate between TWO receive buffers. */
-int vq_allreduce_push(const void* const* recv_buffers, void* multicast_or_null, int world, int rank,
-                      const float* payload, int64_t n_floats, uint32_t seq, float* out, vq_stream_t stream);
-
-/* Backward and the data-parallel all-reduce of the packed step buffer in ONE persistent kernel: the NVLink transfer
- * overlaps the dz pass (replaces vq_backward + vq_allreduce_push; the reference has no counterpart -- DDP would
- * all-reduce `_embedding.weight.grad` after backward).  `payload` = [dE (K*D, zeroed by the caller, e.g. by
- * vq_prepare_step) | extra floats (usage histogram, squared error) already in place], n_floats in total; it is reduced
- * into `out` on every rank, bit-identically.  Needs VQ_FLAG_TRAIN_VQ, D % 4 == 0, 16-byte aligned z / g_q / dz /
- * payload, world >= 2.  `grid_sync`: two zero-initialised uint32 in device memory owned by the caller and used by no
- * other stream.  recv_buffers / multicast_or_null / seq: as for vq_allreduce_push. */
-int vq_backward_allreduce(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx,
-                          int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags, float* dz,
-                          float* payload, int64_t n_floats, const void* const* recv_buffers, void* multicast_or_null,
-                          int world, int rank, uint32_t seq, uint32_t* grid_sync, float* out, vq_stream_t stream);
-/* multicast_or_null: the NVLS multicast mapping of the same receive buffer (torch symmetric memory's
- * `multicast_ptr`); when given, each line is sent with ONE multimem.st that the NVSwitch replicates to all ranks. */
+/* -- data parallel: sum all-reduce of the packed step buffer over NVLink peer memory -------------------------------- */
+/* Rows shard across ranks with no data-path collective; per step ONE packed buffer
+ *   [ code sums or dE (K*D) | usage histogram (K) | squared error (1) ]
+ * is summed over the ranks, in rank order (bit-identical on every rank).  Transport: every rank owns two symmetric
+ * RECEIVE buffers (alternating between calls) of vq_dp_recv_lines(world, n_floats) 16-byte lines, zero-initialised
+ * and mapped into every peer (torch symmetric memory / CUDA IPC); data travels as lines {d0, seq, d1, seq}, so a line
+ * whose flag words carry the call's sequence number is complete -- no barrier.  Below 8 ranks every rank stores its
+ * lines into every rank (one multimem.st per line with the NVLS multicast mappings), from 8 ranks on reduce-scatter +
+ * all-gather through the same buffers (B200VQ_AR_ALGO=1|2 forces either).  The sequence number lives in device
+ * memory and is advanced by the kernel, so the calls can be captured in a CUDA graph and replayed.  Waits are bounded
+ * (spin_limit polls, 0 = default of a few seconds): on expiry the kernel raises the error word and drains.
+ * The reference has no counterpart (single process); under DDP it would be the all-reduce of `_embedding.weight.grad`. */
+typedef struct vq_dp_ctx vq_dp_ctx;
+int64_t vq_dp_recv_lines(int world, int64_t n_floats);
+/* recv0 / recv1: host arrays of `world` device pointers, entry p = rank p's receive buffer (parity 0 / 1) as mapped
+ * into THIS process; multicast0 / multicast1: NVLS multicast mappings of the same buffers or NULL. */
+int  vq_dp_create(const void* const* recv0, const void* const* recv1, void* multicast0, void* multicast1,
+                  int world, int rank, int64_t n_floats, uint32_t spin_limit, vq_dp_ctx** out);
+void vq_dp_destroy(vq_dp_ctx* ctx);
+/* out[i] = sum over ranks of payload[i], i < n_floats (payload: written by earlier work on `stream`). */
+int  vq_dp_allreduce(vq_dp_ctx* ctx, const float* payload, float* out, vq_stream_t stream);
+/* The step's exchange: [code sums of the last vq_step_forward on `workspace` (K*D) | tail (n_tail floats: hist | sse)]
+ * -> out.  Everything it carries comes out of the forward, so it is launched right behind vq_step_forward; pass
+ * `out` as reduced_sums to the vq_step_backward that follows on the same stream. */
+int  vq_dp_exchange_sums(vq_dp_ctx* ctx, const void* workspace, size_t workspace_bytes, int64_t n_rows, int K, int D,
+                         const float* tail, int n_tail, float* out, vq_stream_t stream);
+/* Synchronises `stream`; calls completed and the error word (bit 0: a wait expired). */
+int  vq_dp_status(vq_dp_ctx* ctx, uint32_t* calls_done, uint32_t* error_word, vq_stream_t stream);
+/* Test hook: `world` emulated ranks on ONE GPU in a single cooperative launch (blockIdx.y = rank), `rounds` calls back
+ * to back.  payloads / outs: host arrays of `world` device pointers.  error_word: OR of the ranks' error words,
+ * bit 8 = a call counter that did not advance once per round. */
+int  vq_dp_emulate(int world, int two_step, int64_t n_floats, const float* const* payloads, float* const* outs,
+                   int rounds, uint32_t spin_limit, uint32_t* error_word, vq_stream_t stream);
 
 /* -- host-buffer entry points (what a non-torch caller binds; used for the end-to-end figure) - */
 typedef struct vq_host_ctx vq_host_ctx;

@@ -27,25 +27,43 @@ def _dev():
     return torch.device("cuda:0")
 
 
-def _forward(lib, z, E, flags, want_onehot=False):
+def _forward(lib, z, E, flags, want_onehot=False, step=False):
+    """step=False: vq_prepare_codebook + vq_forward.  step=True: vq_step_forward (ONE launch on the screen path: norms
+    in-kernel, raw codebook under the tensor map, usage counts ping-pong in the workspace) -- called three times on the
+    same workspace, every call must give the same outputs."""
     dev = z.device
     N, D = z.shape
     K = E.shape[0]
     st = torch.cuda.current_stream().cuda_stream
     e2 = torch.empty(K, device=dev); ehi = torch.empty_like(E); elo = torch.empty_like(E)
-    assert lib.vq_prepare_codebook(E.data_ptr(), K, D, e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(), st) == 0
     q = torch.empty_like(z); idx = torch.empty(N, dtype=torch.int32, device=dev)
     oh = torch.empty(N, K, device=dev) if want_onehot else None
     stats = torch.empty(K + 3, device=dev)
     fl = flags | (1 if want_onehot else 0)
     wsb = lib.vq_workspace_bytes(N, K, D, fl); ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     sp = stats.data_ptr()
-    rc = lib.vq_forward(z.data_ptr(), E.data_ptr(), e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(), N, K, D, BETA, fl,
-                        q.data_ptr(), idx.data_ptr(), None if oh is None else oh.data_ptr(), sp, sp + 4 * K, sp + 4 * (K + 1),
-                        sp + 4 * (K + 2), ws.data_ptr(), wsb, st)
-    assert rc == 0, lib.vq_last_error()
-    torch.cuda.synchronize()
-    return dict(q=q, idx=idx, onehot=oh, hist=stats[:K], sse=stats[K], loss=stats[K + 1], perplexity=stats[K + 2])
+    if not step:
+        assert lib.vq_prepare_codebook(E.data_ptr(), K, D, e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(), st) == 0
+        rc = lib.vq_forward(z.data_ptr(), E.data_ptr(), e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(), N, K, D, BETA, fl,
+                            q.data_ptr(), idx.data_ptr(), None if oh is None else oh.data_ptr(), sp, sp + 4 * K, sp + 4 * (K + 1),
+                            sp + 4 * (K + 2), ws.data_ptr(), wsb, st)
+        assert rc == 0, lib.vq_last_error()
+        torch.cuda.synchronize()
+        return dict(q=q, idx=idx, onehot=oh, hist=stats[:K], sse=stats[K], loss=stats[K + 1], perplexity=stats[K + 2], e_norm2=e2)
+    assert lib.vq_workspace_init(ws.data_ptr(), wsb, st) == 0
+    prev = None
+    for call in range(3):
+        stats.fill_(-5.0); idx.fill_(-1)
+        rc = lib.vq_step_forward(z.data_ptr(), E.data_ptr(), N, K, D, BETA, fl, e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(),
+                                 q.data_ptr(), idx.data_ptr(), None if oh is None else oh.data_ptr(), sp, sp + 4 * K, sp + 4 * (K + 1),
+                                 sp + 4 * (K + 2), ws.data_ptr(), wsb, st)
+        assert rc == 0, lib.vq_last_error()
+        torch.cuda.synchronize()
+        cur = (idx.clone(), stats.clone())
+        if prev is not None:
+            assert torch.equal(prev[0], cur[0]) and torch.equal(prev[1], cur[1]), f"vq_step_forward call {call} differs from call {call - 1}"
+        prev = cur
+    return dict(q=q, idx=idx, onehot=oh, hist=stats[:K], sse=stats[K], loss=stats[K + 1], perplexity=stats[K + 2], e_norm2=e2)
 
 
 def _near_tie_gap(z, E, idx_a, idx_b):
@@ -76,6 +94,10 @@ def test_full_size_properties(lib, name, N, D, K, onehot):
     z = torch.randn(N, D, device=dev)
     t = _forward(lib, z, E, 0, want_onehot=onehot)           # tensor path, fused
     assert lib.vq_forward_uses_tensor_path(N, K, D, 0) == 1
+    ts = _forward(lib, z, E, 0, want_onehot=onehot, step=True)   # the same through vq_step_forward (one launch, no prepare)
+    assert torch.equal(ts["idx"], t["idx"]) and torch.equal(ts["hist"], t["hist"]) and torch.equal(ts["q"], t["q"])
+    assert torch.equal(ts["e_norm2"], t["e_norm2"])
+    assert abs(float(ts["loss"]) - float(t["loss"])) <= 1e-6 * float(t["loss"]) and abs(float(ts["perplexity"]) - float(t["perplexity"])) <= 1e-6 * float(t["perplexity"])
     x = _forward(lib, z, E, 4)                                # exact CUDA-core path
     n_mis, gap = _near_tie_gap(z, E, t["idx"], x["idx"])
     # these shapes run the screen + refine kernel, whose indices are bit-exact: not one row may differ at full size
@@ -213,6 +235,10 @@ def test_screen_kernel_adversarial_inputs(lib, kind, D, K):
     ref = _oracle_idx(z, E)
     assert torch.equal(out["idx"].cpu(), ref), f"{kind} D={D} K={K}: {(out['idx'].cpu() != ref).sum().item()} rows differ from the oracle"
     assert float(out["hist"].sum()) == N
+    # the self-prepared launch (raw codebook truncated by the tensor core, wider margin) must be just as exact
+    out_s = _forward(lib, z, E, 1 << 10, step=True)
+    assert torch.equal(out_s["idx"].cpu(), ref), f"{kind} D={D} K={K} (vq_step_forward): {(out_s['idx'].cpu() != ref).sum().item()} rows differ"
+    assert torch.equal(out_s["hist"], out["hist"])
     out_oh = _forward(lib, z, E, 1 << 10, want_onehot=True)
     assert torch.equal(out_oh["idx"].cpu(), ref) and torch.equal(out_oh["onehot"].argmax(1).int().cpu(), ref)
     assert float(out_oh["onehot"].sum()) == N
@@ -257,9 +283,10 @@ def test_screen_kernel_fuzz_against_exact_path(lib):
         for want_onehot in (False, True):
             if want_onehot and N * K * 4 > (1 << 30):
                 continue
-            out = _forward(lib, z, E, 1 << 10, want_onehot=want_onehot)
-            bad = int((out["idx"] != exact).sum())
-            assert bad == 0, f"trial {trial}: kind {kind} N={N} K={K} D={D} onehot={want_onehot}: {bad} rows differ"
-            assert float(out["hist"].sum()) == N
+            for step in (False, True):
+                out = _forward(lib, z, E, 1 << 10, want_onehot=want_onehot, step=step)
+                bad = int((out["idx"] != exact).sum())
+                assert bad == 0, f"trial {trial}: kind {kind} N={N} K={K} D={D} onehot={want_onehot} step={step}: {bad} rows differ"
+                assert float(out["hist"].sum()) == N
             n_checked += 1
     assert n_checked >= 48

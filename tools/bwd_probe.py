@@ -14,6 +14,13 @@ HBM = 6534.0
 rows = []
 SHAPES = ((51456, 64, 1024), (16000, 128, 1024), (32000, 128, 1024), (1 << 20, 64, 512), (1 << 20, 64, 1024), (1 << 20, 128, 1024),
           (1 << 20, 128, 4096), (1 << 19, 256, 2048), (1 << 17, 64, 1024))
+only = [a for a in sys.argv if a.startswith("--only=")]
+if only:
+    SHAPES = tuple(SHAPES[int(i)] for i in only[0][7:].split(","))
+REPS = 50
+for a in sys.argv:
+    if a.startswith("--reps="):
+        REPS = int(a[7:])
 for (N, D, K) in SHAPES:
     torch.manual_seed(0)
     E = torch.randn(K, D, device=dev)
@@ -31,7 +38,7 @@ for (N, D, K) in SHAPES:
     gl = torch.ones((), device=dev)
     st = torch.cuda.current_stream().cuda_stream
 
-    def run(flags, reps=50):
+    def run(flags, reps=REPS):
         def one(i):
             L.check(lib.vq_backward(gs[i % nb].data_ptr(), gl.data_ptr(), zs[i % nb].data_ptr(), E.data_ptr(), idxs[i % nb].data_ptr(),
                                     N, N, N, K, D, 0.25, flags, dz.data_ptr(), dE.data_ptr(), st))
@@ -47,7 +54,7 @@ for (N, D, K) in SHAPES:
     roof = byts / (HBM * 1e9) * 1e6
     r = {"N": N, "D": D, "K": K, "bytes": byts, "roof_us": round(roof, 2), "default_path": lib.vq_backward_path(N, K, D, 0),
          "dz_only_us": round(run(0), 2)}
-    for name, fl in (("flat", L.FLAG_BWD_FLAT), ("bucket", L.FLAG_BWD_BUCKET), ("private", L.FLAG_BWD_PRIVATE)):
+    for name, fl in (("flat", L.FLAG_BWD_FLAT), ("private", L.FLAG_BWD_PRIVATE)):
         if fl != L.FLAG_BWD_FLAT and lib.vq_backward_path(N, K, D, fl) == 0:
             continue
         if name == "bucket" and N > (1 << 18):
