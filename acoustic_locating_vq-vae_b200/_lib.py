@@ -24,8 +24,6 @@ FLAG_NO_SCREEN = 1 << 9
 FLAG_SCREEN = 1 << 10
 FLAG_BWD_FLAT = 1 << 12
 FLAG_BWD_PRIVATE = 1 << 14
-FLAG_CODE_SUMS = 1 << 16
-FLAG_OVERLAP_EXCHANGE = 1 << 17
 
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -48,8 +46,7 @@ SIGNATURES = {
     "vq_workspace_bytes": (_sz, [_i64, _int, _int, _int]),
     "vq_forward": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _f32, _int,
                           _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "vq_workspace_init": (_int, [_vp, _sz, _vp]),
-    "vq_step_forward": (_int, [_vp, _vp, _i64, _int, _int, _f32, _int, _vp, _vp, _vp,
+    "vq_step_forward": (_int, [_vp, _vp, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "vq_finalize_stats": (_int, [_vp, _vp, _i64, _int, _int, _f32, _vp, _vp, _vp]),
     "vq_onehot": (_int, [_vp, _i64, _int, _vp, _vp]),
@@ -59,13 +56,10 @@ SIGNATURES = {
     "vq_scatter_add_rows": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _vp]),
     "vq_jitter_apply": (_int, [_vp, _vp, _i64, _int, _vp]),
     "vq_jitter_backward": (_int, [_vp, _vp, _i64, _int, _vp]),
-    "vq_step_uses_code_sums": (_int, [_i64, _int, _int, _int]),
-    "vq_step_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
     "vq_dp_recv_lines": (_i64, [_int, _i64]),
     "vq_dp_create": (_int, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _vp, _int, _int, _i64, ctypes.c_uint32, ctypes.POINTER(_vp)]),
     "vq_dp_destroy": (None, [_vp]),
     "vq_dp_allreduce": (_int, [_vp, _vp, _vp, _vp]),
-    "vq_dp_exchange_sums": (_int, [_vp, _vp, _sz, _i64, _int, _int, _vp, _int, _vp, _vp]),
     "vq_dp_status": (_int, [_vp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), _vp]),
     "vq_dp_emulate": (_int, [_int, _int, _i64, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _int, ctypes.c_uint32,
                              ctypes.POINTER(ctypes.c_uint32), _vp]),

@@ -229,7 +229,7 @@ int choose_splits(long long row_tiles, int code_tiles, int max_splits, int slots
 }
 
 struct WsLayout {
-    size_t partials_off, counter_off, keys_off, hist_off, sums_off, total;
+    size_t partials_off, counter_off, keys_off, total;
     int rows_grid;
 };
 
@@ -251,7 +251,7 @@ int rows_grid_for(long long N, int R) {
     return static_cast<int>(g);
 }
 
-WsLayout ws_layout(long long N, int K = 0, int D = 0) {
+WsLayout ws_layout(long long N) {
     WsLayout w;
     w.rows_grid = 0;
     w.partials_off = 0;
@@ -260,9 +260,7 @@ WsLayout ws_layout(long long N, int K = 0, int D = 0) {
     // the per-row key buffer (unfused paths) and the screen kernel's spill lists (fused path) share the tail
     const size_t keys_bytes = static_cast<size_t>(N) * sizeof(unsigned long long);
     const size_t spill_bytes = static_cast<size_t>(kNumSMs) * 4 * SC_SPILL * sizeof(int4);
-    w.hist_off = (w.keys_off + (keys_bytes > spill_bytes ? keys_bytes : spill_bytes) + 255) / 256 * 256;
-    w.sums_off = (w.hist_off + 2 * sizeof(float) * static_cast<size_t>(K) + 255) / 256 * 256;   // [2][K] usage accumulators (vq_step_forward)
-    w.total = w.sums_off + 2 * sizeof(float) * static_cast<size_t>(K) * static_cast<size_t>(D);      // [2][K*D] code sums (VQ_FLAG_CODE_SUMS)
+    w.total = w.keys_off + (keys_bytes > spill_bytes ? keys_bytes : spill_bytes);
     return w;
 }
 
@@ -387,9 +385,9 @@ int vq_forward_uses_tensor_path(int64_t n_rows, int K, int D, int flags) {
 }
 
 size_t vq_workspace_bytes(int64_t n_rows, int K, int D, int flags) {
-    (void)flags;
+    (void)K; (void)D; (void)flags;
     if (n_rows < 0) n_rows = 0;
-    return ws_layout(n_rows, K < 0 ? 0 : K, D < 0 ? 0 : D).total;
+    return ws_layout(n_rows).total;
 }
 
 static int prepare_impl(const float* E, int K, int D, float* e_norm2, float* E_hi, float* E_lo, float* hist,
@@ -398,14 +396,7 @@ static int prepare_impl(const float* E, int K, int D, float* e_norm2, float* E_h
     if (E == nullptr || e_norm2 == nullptr || K < 1 || D < 1) return fail(VQ_ERR_ARG, "vq_prepare: bad argument (K=%d D=%d)", K, D);
     if (E_hi == nullptr && E_lo != nullptr) return fail(VQ_ERR_ARG, "vq_prepare: E_lo without E_hi");
     ProfScope prof(KID_PREP, st);
-    cudaError_t e;
-    if (D % 4 == 0 && aligned16(E) && (E_hi == nullptr || (aligned16(E_hi) && aligned16(E_lo))) && (dE == nullptr || aligned16(dE))) {
-        // one thread per code runs the |E_k|^2 chain with its whole row in flight; split + state reset are coalesced
-        e = launch_pdl(prep_codebook_fast_kernel, dim3((K + 31) / 32), dim3(PREP_THREADS), 0, st, E, K, D, e_norm2, E_hi, E_lo, hist,
-                       counter, dE);
-    } else {
-        e = launch_pdl(prep_codebook_kernel, dim3((K + 7) / 8), dim3(256), 0, st, E, K, D, e_norm2, E_hi, E_lo, hist, counter, dE);
-    }
+    const cudaError_t e = launch_pdl(prep_codebook_kernel, dim3((K + 7) / 8), dim3(256), 0, st, E, K, D, e_norm2, E_hi, E_lo, hist, counter, dE);
     if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of prep_codebook_kernel failed: %s", cudaGetErrorString(e));
     LAUNCH_CHECK("prep_codebook_kernel");
     return VQ_OK;
@@ -439,7 +430,7 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
     if (quant && q_out == nullptr) return fail(VQ_ERR_ARG, "vq_forward: q_out is NULL without VQ_FLAG_NO_QUANT");
     if (want_onehot && onehot == nullptr) return fail(VQ_ERR_ARG, "vq_forward: VQ_FLAG_ONEHOT with onehot == NULL");
     if (!defer && (perplexity == nullptr || (quant && loss == nullptr))) return fail(VQ_ERR_ARG, "vq_forward: loss/perplexity NULL without VQ_FLAG_DEFER_STATS");
-    const WsLayout w = ws_layout(N, K, D);
+    const WsLayout w = ws_layout(N);
     if (workspace == nullptr || workspace_bytes < w.total)
         return fail(VQ_ERR_WORKSPACE, "vq_forward: workspace %zu B < required %zu B", workspace_bytes, w.total);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -456,14 +447,12 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
 
     // ---- 1. argmin ----------------------------------------------------------------------------------------
     unsigned long long* keys = nullptr;
-    const bool self = (flags & VQ_FLAG_SELF_PREPARE) != 0;
     // ---- screen + refine (one TF32 pass, exact fp32 refine of the candidates): the default fused forward ----
     // Indices are bit-identical to the fp32 oracle, and it is the faster kernel everywhere on B200 (RIR-256 with the
     // dense one-hot: 69.0 vs 69.6 us per step; 1.5x at D = 64 and 2x at D = 128 without the one-hot); D > 128 only
     // fits this kernel.  VQ_FLAG_NO_SCREEN / B200VQ_SCREEN=0 select the 3xTF32 kernel, VQ_FLAG_SCREEN forces this one.
-    const bool screen = screen_path_ok(N, K, D, flags, z, E, q_out, onehot) && (self || (E_hi != nullptr && aligned16(E_hi))) &&
-                        ((flags & VQ_FLAG_SCREEN) || self || screen_enabled());
-    if (self && !screen) return fail(VQ_ERR_ARG, "vq_forward: VQ_FLAG_SELF_PREPARE needs the screen + refine path (call vq_step_forward)");
+    const bool screen = screen_path_ok(N, K, D, flags, z, E, q_out, onehot) && E_hi != nullptr && aligned16(E_hi) &&
+                        ((flags & VQ_FLAG_SCREEN) || screen_enabled());
     if (screen) {
         FusedRowArgs fr{};
         fr.z = z; fr.E = E; fr.q_out = quant ? q_out : nullptr; fr.onehot = want_onehot ? onehot : nullptr; fr.hist = hist;
@@ -472,15 +461,10 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
         fr.spill = reinterpret_cast<int4*>(keys_buf);   // 16-byte aligned: keys_off is a multiple of 256
         static const int evict_first = [] { const char* e = getenv("B200VQ_ONEHOT_EVICT_FIRST"); return e != nullptr && e[0] == '0' ? 0 : 1; }();
         fr.onehot_evict_first = evict_first;
-        if (self) {     // no prepare launch: norms in-kernel, raw codebook under the tensor map, usage counts ping-pong in the workspace
-            fr.e_norm2_w = const_cast<float*>(e_norm2);
-            fr.hist_ws = reinterpret_cast<float*>(ws + w.hist_off);
-            if ((flags & VQ_FLAG_CODE_SUMS) && quant) fr.sums_ws = reinterpret_cast<float*>(ws + w.sums_off);
-        }
         CUtensorMap tz, thi;
         if (int rc = make_tmap(&tz, z, N, D)) return rc;
-        if (int rc = make_tmap(&thi, self ? E : E_hi, K, D)) return rc;
-        const bool ready = self || (flags & VQ_FLAG_STATE_READY) != 0;
+        if (int rc = make_tmap(&thi, E_hi, K, D)) return rc;
+        const bool ready = (flags & VQ_FLAG_STATE_READY) != 0;
         switch (D / TC_SLAB_FLOATS) {
             case 1: return launch_screen<1, 8, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
             case 2: return launch_screen<2, 8, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
@@ -592,31 +576,22 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
     return VQ_OK;
 }
 
-int vq_workspace_init(void* workspace, size_t workspace_bytes, vq_stream_t stream) {
-    if (workspace == nullptr) return fail(VQ_ERR_ARG, "vq_workspace_init: workspace is NULL");
-    CUDA_TRY(cudaMemsetAsync(workspace, 0, workspace_bytes, static_cast<cudaStream_t>(stream)));
-    return VQ_OK;
-}
-
-// prepare + forward behind ONE entry.  On the screen + refine path this is a single launch: the kernel computes
-// |E_k|^2 itself, reads the raw codebook through the tensor map and keeps its per-call state (usage accumulators,
-// call counter) in the workspace, which must have been zeroed ONCE with vq_workspace_init.  Other shapes run the
-// prepare launch followed by vq_forward.
+// prepare + forward behind ONE entry (the call a training step makes: Adam has just changed E): the prepare launch
+// (codebook norms, tf32 split, reset of hist / completion counter and -- when given -- of the dE accumulator the backward
+// will add into) and the fused forward, chained by programmatic dependent launch.
 int vq_step_forward(const float* z, const float* E, int64_t n_rows, int K, int D, float beta, int flags, float* e_norm2,
-                    float* E_hi, float* E_lo, float* q_out, int32_t* idx, float* onehot, float* hist, float* sse, float* loss,
-                    float* perplexity, void* workspace, size_t workspace_bytes, vq_stream_t stream) {
+                    float* E_hi, float* E_lo, float* dE_zero, float* q_out, int32_t* idx, float* onehot, float* hist, float* sse,
+                    float* loss, float* perplexity, void* workspace, size_t workspace_bytes, vq_stream_t stream) {
     if (int rc = check_device()) return rc;
     if (z == nullptr || E == nullptr || e_norm2 == nullptr || hist == nullptr || K < 1 || D < 1 || n_rows < 0)
         return fail(VQ_ERR_ARG, "vq_step_forward: bad argument");
-    const int fl = flags & ~(VQ_FLAG_STATE_READY | VQ_FLAG_SELF_PREPARE);
-    static const bool self_on = [] { const char* e = getenv("B200VQ_SELF_PREPARE"); return !(e != nullptr && e[0] == '0'); }();   // tuning knob
-    if (self_on && n_rows > 0 && screen_path_ok(n_rows, K, D, fl, z, E, q_out, onehot) && ((fl & VQ_FLAG_SCREEN) || screen_enabled()))
-        return vq_forward(z, E, e_norm2, nullptr, nullptr, n_rows, K, D, beta, fl | VQ_FLAG_SELF_PREPARE, q_out, idx, onehot, hist, sse,
-                          loss, perplexity, workspace, workspace_bytes, stream);
+    const int fl = flags & ~VQ_FLAG_STATE_READY;
     const bool tensor = tensor_path_ok(n_rows, K, D, fl);
-    if (tensor && (E_hi == nullptr || E_lo == nullptr)) return fail(VQ_ERR_ARG, "vq_step_forward: E_hi / E_lo scratch is NULL but this shape runs the 3xTF32 kernels");
-    if (int rc = vq_prepare_step(E, K, D, e_norm2, tensor ? E_hi : nullptr, tensor ? E_lo : nullptr, hist, workspace, workspace_bytes, nullptr,
-                                 stream))
+    const bool screen = n_rows > 0 && screen_path_ok(n_rows, K, D, fl, z, E, q_out, onehot) && ((fl & VQ_FLAG_SCREEN) || screen_enabled());
+    if (tensor && (E_hi == nullptr || (!screen && E_lo == nullptr)))
+        return fail(VQ_ERR_ARG, "vq_step_forward: E_hi (and, outside the screen + refine shapes, E_lo) scratch is NULL but this shape runs on the tensor path");
+    if (int rc = vq_prepare_step(E, K, D, e_norm2, tensor ? E_hi : nullptr, (tensor && !screen) ? E_lo : nullptr, hist, workspace, workspace_bytes,
+                                 dE_zero, stream))
         return rc;
     return vq_forward(z, E, e_norm2, E_hi, E_lo, n_rows, K, D, beta, fl | VQ_FLAG_STATE_READY, q_out, idx, onehot, hist, sse, loss, perplexity,
                       workspace, workspace_bytes, stream);
@@ -750,60 +725,7 @@ int vq_backward(const float* g_q, const float* g_loss, const float* z, const flo
 }
 
 // =========================================================================================================
-// step backward: the backward that pairs with vq_step_forward
-// =========================================================================================================
-int vq_step_uses_code_sums(int64_t n_rows, int K, int D, int flags) {
-    const int fl = flags & ~(VQ_FLAG_STATE_READY | VQ_FLAG_SELF_PREPARE);
-    static const bool self_on = [] { const char* e = getenv("B200VQ_SELF_PREPARE"); return !(e != nullptr && e[0] == '0'); }();
-    return (self_on && n_rows > 0 && (fl & VQ_FLAG_CODE_SUMS) && !(fl & VQ_FLAG_NO_QUANT) && screen_path_ok(n_rows, K, D, fl, nullptr, nullptr, nullptr, nullptr) &&
-            ((fl & VQ_FLAG_SCREEN) || screen_enabled())) ? 1 : 0;
-}
-
-int vq_step_backward(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx, int64_t n_rows,
-                     int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags, float* dz, float* dE,
-                     const void* workspace, size_t workspace_bytes, const float* reduced_sums, vq_stream_t stream) {
-    if (int rc = check_device()) return rc;
-    const long long N = n_rows;
-    const bool train = (flags & VQ_FLAG_TRAIN_VQ) != 0 && dE != nullptr;
-    if (!(flags & VQ_FLAG_CODE_SUMS) || !train) {
-        if (reduced_sums != nullptr) return fail(VQ_ERR_ARG, "vq_step_backward: reduced_sums needs VQ_FLAG_CODE_SUMS | VQ_FLAG_TRAIN_VQ and dE");
-        return vq_backward(g_q, g_loss, z, E, idx, n_rows, n_rows_dz, n_rows_dE, K, D, beta, flags, dz, dE, stream);
-    }
-    if (z == nullptr || E == nullptr || idx == nullptr || K < 1 || D < 4 || D % 4 != 0 || N < 1 || n_rows_dz < 1 || n_rows_dE < 1 ||
-        workspace == nullptr)
-        return fail(VQ_ERR_ARG, "vq_step_backward: bad argument");
-    if (!aligned16(z) || !aligned16(E) || !aligned16(dE) || (dz != nullptr && !aligned16(dz)) || (g_q != nullptr && !aligned16(g_q)) ||
-        (reduced_sums != nullptr && !aligned16(reduced_sums)))
-        return fail(VQ_ERR_ARG, "vq_step_backward: z / g_q / dz / E / dE / reduced_sums must be 16-byte aligned");
-    const WsLayout w = ws_layout(N, K, D);
-    if (workspace_bytes < w.total) return fail(VQ_ERR_WORKSPACE, "vq_step_backward: workspace %zu B < %zu B", workspace_bytes, w.total);
-    const uint8_t* ws = static_cast<const uint8_t*>(workspace);
-    const float* sums_ws = reinterpret_cast<const float*>(ws + w.sums_off);
-    const unsigned int* counter = reinterpret_cast<const unsigned int*>(ws + w.counter_off);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const float denom_dz = static_cast<float>(static_cast<double>(n_rows_dz) * static_cast<double>(D));
-    const float denom_dE = static_cast<float>(static_cast<double>(n_rows_dE) * static_cast<double>(D));
-    const long long n_el = dz != nullptr ? N * (D / 4) : 0;
-    long long g = (n_el + 511) / 512;                       // two 16-byte elements per thread
-    const long long g_min = (static_cast<long long>(K) * D / 4 + 255) / 256;
-    if (g < g_min) g = g_min;
-    if (g > static_cast<long long>(sm_count()) * 32) g = static_cast<long long>(sm_count()) * 32;
-    const int accumulate = (flags & VQ_FLAG_ZERO_DE) ? 0 : 1;
-    // VQ_FLAG_OVERLAP_EXCHANGE: our predecessor in the stream is the exchange, which we overlap (see backward_stream_kernel)
-    const int wait_first = (reduced_sums != nullptr && (flags & VQ_FLAG_OVERLAP_EXCHANGE)) ? 0 : 1;
-    ProfScope prof(KID_BACKWARD, st);
-    const cudaError_t e =
-        g_q != nullptr ? launch_pdl(backward_stream_kernel<true>, dim3(static_cast<unsigned>(g)), dim3(256), 0, st, g_q, g_loss, z, E, idx, N, denom_dz,
-                                    denom_dE, K, D, beta, dz, sums_ws, counter, reduced_sums, dE, accumulate, wait_first)
-                       : launch_pdl(backward_stream_kernel<false>, dim3(static_cast<unsigned>(g)), dim3(256), 0, st, g_q, g_loss, z, E, idx, N, denom_dz,
-                                    denom_dE, K, D, beta, dz, sums_ws, counter, reduced_sums, dE, accumulate, wait_first);
-    if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of backward_stream_kernel failed: %s", cudaGetErrorString(e));
-    LAUNCH_CHECK("backward_stream_kernel");
-    return VQ_OK;
-}
-
-// =========================================================================================================
-// data parallel: exchange of [code sums | usage histogram | squared error] over NVLink peer memory
+// data parallel: sum all-reduce of the packed step buffer [dE | usage histogram | squared error] over NVLink peer memory
 // =========================================================================================================
 struct vq_dp_ctx {
     DpCtxDev dev;
@@ -869,37 +791,19 @@ int vq_dp_status(vq_dp_ctx* c, uint32_t* calls_done, uint32_t* error_word, vq_st
     return VQ_OK;
 }
 
-static int dp_launch(vq_dp_ctx* c, const DpSource& src, float* out, cudaStream_t st) {
-    if (!aligned16(out)) return fail(VQ_ERR_ARG, "vq_dp: out is misaligned");
+// out[i] = sum over ranks (rank order: bit-identical everywhere) of payload[i]
+int vq_dp_allreduce(vq_dp_ctx* c, const float* payload, float* out, vq_stream_t stream) {
+    if (c == nullptr || payload == nullptr || out == nullptr) return fail(VQ_ERR_ARG, "vq_dp_allreduce: null");
+    if (!aligned16(out)) return fail(VQ_ERR_ARG, "vq_dp_allreduce: out is misaligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     long long blocks = (c->dev.L + DP_THREADS - 1) / DP_THREADS;
     const int cap = sm_count();
     if (blocks > cap) blocks = cap;                          // no CTA waits for another CTA of this grid: no residency requirement
     ProfScope prof(KID_ALLREDUCE, st);
-    const cudaError_t e = launch_pdl(dp_allreduce_kernel<true>, dim3(static_cast<unsigned>(blocks)), dim3(DP_THREADS), 0, st, c->dev, src, out);
+    const cudaError_t e = launch_pdl(dp_allreduce_kernel<true>, dim3(static_cast<unsigned>(blocks)), dim3(DP_THREADS), 0, st, c->dev, payload, out);
     if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of dp_allreduce_kernel failed: %s", cudaGetErrorString(e));
     LAUNCH_CHECK("dp_allreduce_kernel");
     return VQ_OK;
-}
-
-// out[i] = sum over ranks (rank order: bit-identical everywhere) of payload[i]
-int vq_dp_allreduce(vq_dp_ctx* c, const float* payload, float* out, vq_stream_t stream) {
-    if (c == nullptr || payload == nullptr || out == nullptr) return fail(VQ_ERR_ARG, "vq_dp_allreduce: null");
-    const DpSource src{payload, c->dev.n, nullptr, nullptr, 0};
-    return dp_launch(c, src, out, static_cast<cudaStream_t>(stream));
-}
-
-// the step's exchange: [code sums of the last vq_step_forward (in its workspace) | tail] -> out
-int vq_dp_exchange_sums(vq_dp_ctx* c, const void* workspace, size_t workspace_bytes, int64_t n_rows, int K, int D, const float* tail,
-                        int n_tail, float* out, vq_stream_t stream) {
-    if (c == nullptr || workspace == nullptr || out == nullptr || K < 1 || D < 1 || n_tail < 0 || (n_tail > 0 && tail == nullptr))
-        return fail(VQ_ERR_ARG, "vq_dp_exchange_sums: bad argument");
-    const long long kd = static_cast<long long>(K) * D;
-    if (c->dev.n != kd + n_tail) return fail(VQ_ERR_ARG, "vq_dp_exchange_sums: context holds %lld floats, K*D + n_tail = %lld", c->dev.n, kd + n_tail);
-    const WsLayout w = ws_layout(n_rows, K, D);
-    if (workspace_bytes < w.total) return fail(VQ_ERR_WORKSPACE, "vq_dp_exchange_sums: workspace %zu B < %zu B", workspace_bytes, w.total);
-    const uint8_t* ws = static_cast<const uint8_t*>(workspace);
-    const DpSource src{reinterpret_cast<const float*>(ws + w.sums_off), kd, tail, reinterpret_cast<const unsigned int*>(ws + w.counter_off), kd};
-    return dp_launch(c, src, out, static_cast<cudaStream_t>(stream));
 }
 
 // Single-GPU emulation of `world` ranks for the tests: ONE cooperative launch in which blockIdx.y plays the rank, all
@@ -1069,7 +973,6 @@ int vq_host_ctx_create(int64_t max_rows, int K, int D, vq_host_ctx** out) {
         A(reinterpret_cast<void**>(&l.idx), sizeof(int32_t) * max_rows);
         l.ws_bytes = vq_workspace_bytes(max_rows, K, D, 0);
         A(&l.ws, l.ws_bytes);
-        if (e == cudaSuccess) e = cudaMemsetAsync(l.ws, 0, l.ws_bytes, l.st);      // vq_workspace_init
     }
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev_start);
     if (e != cudaSuccess) {
@@ -1107,20 +1010,16 @@ int vq_host_step_async(vq_host_ctx* c, int lane, const float* z_host, const floa
         LAUNCH_CHECK("fill_kernel");
         l.gq_is_ones = true;
     }
-    // prepare + forward in one entry (one launch on the screen path); with a training codebook the forward also
-    // accumulates the code sums and the backward is the streaming pass.  Both lanes share the codebook scratch: a lane's
-    // forward rewrites e_norm2 / E_hi / E_lo with the values the other lane's kernels may be reading -- identical bits.
-    const int sums = train ? VQ_FLAG_CODE_SUMS : 0;
+    // prepare + forward in one entry (the prepare launch also zeroes the lane's dE accumulator).  Both lanes share the codebook
+    // scratch: a lane's prepare rewrites e_norm2 / E_hi / E_lo with the values the other lane's kernels may be reading -- identical bits.
     const int keep = VQ_FLAG_EXACT | VQ_FLAG_NO_SCREEN | VQ_FLAG_SCREEN | VQ_FLAG_NO_FUSE | VQ_FLAG_TC_1CTA;
-    if (int rc = vq_step_forward(l.z, c->E, n_rows, c->K, c->D, beta, (flags & keep) | sums, c->e_norm2, c->E_hi, c->E_lo, l.q, l.idx, nullptr, l.hist,
+    if (int rc = vq_step_forward(l.z, c->E, n_rows, c->K, c->D, beta, flags & keep, c->e_norm2, c->E_hi, c->E_lo, train ? l.dE : nullptr, l.q, l.idx, nullptr, l.hist,
                                  l.scal + 0, l.scal + 1, l.scal + 2, l.ws, l.ws_bytes, l.st))
         return rc;
     // gq_host == NULL: the lane's g_q buffer still holds the ones written at context creation, i.e. the
     // `(loss + quantized.sum()).backward()` workload; the kernel reads it like any upstream gradient.
-    const int use_sums = vq_step_uses_code_sums(n_rows, c->K, c->D, (flags & keep) | sums) ? VQ_FLAG_CODE_SUMS : 0;
-    if (int rc = vq_step_backward(l.gq, nullptr, l.z, c->E, l.idx, n_rows, n_rows, n_rows_dE > 0 ? n_rows_dE : n_rows, c->K, c->D, beta,
-                                  (flags & (VQ_FLAG_TRAIN_VQ | VQ_FLAG_BWD_FLAT | VQ_FLAG_BWD_PRIVATE)) | VQ_FLAG_ZERO_DE | use_sums, l.dz,
-                                  train ? l.dE : nullptr, l.ws, l.ws_bytes, nullptr, l.st))
+    if (int rc = vq_backward(l.gq, nullptr, l.z, c->E, l.idx, n_rows, n_rows, n_rows_dE > 0 ? n_rows_dE : n_rows, c->K, c->D, beta,
+                             flags & (VQ_FLAG_TRAIN_VQ | VQ_FLAG_BWD_FLAT | VQ_FLAG_BWD_PRIVATE), l.dz, train ? l.dE : nullptr, l.st))
         return rc;
     if (loss_host) CUDA_TRY(cudaMemcpyAsync(loss_host, l.scal + 1, sizeof(float), cudaMemcpyDeviceToHost, l.st));
     if (perplexity_host) CUDA_TRY(cudaMemcpyAsync(perplexity_host, l.scal + 2, sizeof(float), cudaMemcpyDeviceToHost, l.st));

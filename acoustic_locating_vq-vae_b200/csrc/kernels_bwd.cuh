@@ -3,20 +3,19 @@
 //   dz[n,:]  = g_q[n,:] - cz * (E[idx[n]] - z[n])          cz = g_loss * beta * 2 / (n_rows_dz * D)
 //   dE[k,:]  = ce * sum_{n : idx[n] == k} (E[k] - z[n])     ce = g_loss * 2 / (n_rows_dE * D)
 //
-// Where the scatter-add into dE happens decides the cost: the flat kernel in kernels_simt.cuh issues one 16-byte
-// red.global.add per 16-byte element of z (823 k atomics on 16 k addresses at the RIR-256 shape: 11.0 us against
-// 7.7 us for the dz pass alone).
-//   backward_stream_kernel   the step path: the FORWARD accumulated the code sums S_k = sum (E_k - z_n) in its row
-//       epilogue (E[idx] - z is in registers there and the kernel is bound by the one-hot write), so the backward is
-//       the pure streaming dz pass plus dE = ce * S.  Under data parallelism S is exchanged right after the forward
-//       and the exchange runs concurrently with this kernel.
-//   backward_private_kernel  N >> K without code sums (e.g. the indices-only sweep): persistent CTAs keep a PRIVATE
+// The flat kernel in kernels_simt.cuh issues one 16-byte red.global.add per 16-byte element of z (823 k atomics on
+// 16 k addresses at the RIR-256 shape: 11.0 us back to back against 7.7 us for the dz pass alone).
+//   backward_private_kernel  N >> K with a small codebook (the sweep's K = 512 corner): persistent CTAs keep a PRIVATE
 //       copy of (a column slice of) dE in shared memory; rows are bucketed by code inside a window so that every
 //       table row has one owning warp (plain shared-memory read-modify-write, no atomics) and the table is flushed
 //       once per CTA with 16-byte reds.
-// Measured and dropped (round 2): code-owner CTAs that scan idx, sort their rows and sum them in registers next to
-// the dz streamers in one grid (no atomics, single writer per dE element).  The owners' latency-bound chains (idx
-// scan, sort, row batches) stall while the streamers saturate the memory system: 45 - 65 us against 11 us flat.
+// Measured and dropped (round 2):
+//   * code-owner CTAs that scan idx, sort their rows and sum them in registers next to the dz streamers in one grid (no
+//     atomics, single writer per dE element): the owners' latency-bound chains (idx scan, sort, row batches) stall while
+//     the streamers saturate the memory system -- 45 - 65 us against 11 us flat;
+//   * accumulating the code sums S_k = sum (E_k - z_n) in the FORWARD's row epilogue (E[idx] - z is in registers there)
+//     and streaming dz only in the backward: the per-SM red issue rate (three worker warps per SM) puts 18 - 22 us on
+//     the forward's critical tail to save 1.5 us in the backward.
 #pragma once
 #include "common.cuh"
 
@@ -65,48 +64,6 @@ __device__ __forceinline__ void dz_stream(const float* __restrict__ g_q, const f
 // The owner code runs once per CTA, so its size is what it costs (instruction fetch): the rare paths are kept
 // out of line and there is a single flush site.
 // ---------------------------------------------------------------------------------------------
-// ---------------------------------------------------------------------------------------------
-// backward_stream_kernel: the backward when the forward already accumulated the code sums
-//   S_k = sum_{n : idx_n = k} (E_k - z_n)                       (vq_step_forward with VQ_FLAG_CODE_SUMS)
-// in its row epilogue, where E[idx] - z sits in registers anyway.  What is left is a pure streaming pass
-//   dz = g_q - cz * (E[idx] - z)
-// and dE = ce * S over K*D elements.  Under data parallelism S (with the usage histogram and the squared error) is
-// exchanged right after the FORWARD (none of it depends on upstream gradients), so the exchange kernel is this
-// kernel's predecessor in the stream and runs concurrently with the dz pass: with wait_first == 0 the pass starts
-// without waiting for it (the exchange triggers this launch only after it has itself seen the forward complete) and
-// the kernel orders itself behind the exchange just before it reads the reduced sums.
-// ---------------------------------------------------------------------------------------------
-template <bool HAS_GQ>
-__global__ void __launch_bounds__(256) backward_stream_kernel(const float* __restrict__ g_q, const float* __restrict__ g_loss,
-                                                              const float* __restrict__ z, const float* __restrict__ E,
-                                                              const int* __restrict__ idx, long long N, float denom_dz, float denom_dE,
-                                                              int K, int D, float beta, float* __restrict__ dz,
-                                                              const float* sums_ws, const unsigned int* counter, const float* reduced,
-                                                              float* __restrict__ dE, int accumulate, int wait_first) {
-    if (wait_first) pdl_wait_prior_grids();
-    pdl_launch_dependents();
-    const float gl = g_loss != nullptr ? __ldg(g_loss) : 1.0f;
-    const long long nthreads = static_cast<long long>(gridDim.x) * 256;
-    const long long first = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-    if (dz != nullptr) dz_stream<HAS_GQ>(g_q, z, E, idx, dz, K, D, gl * beta * 2.0f / denom_dz, first, N * (D >> 2), nthreads);
-    if (!wait_first) pdl_wait_prior_grids();
-    if (dE != nullptr) {
-        const float ce = gl * 2.0f / denom_dE;
-        const size_t kd = static_cast<size_t>(K) * D;
-        // single GPU: the buffer the last forward call filled (the call counter has been advanced past it)
-        const float* S = reduced != nullptr ? reduced : sums_ws + ((__ldcg(counter + 1) - 1u) & 1u) * kd;
-        for (size_t i = first; i < kd / 4; i += nthreads) {
-            float4 v = __ldcg(reinterpret_cast<const float4*>(S) + i);
-            v.x *= ce; v.y *= ce; v.z *= ce; v.w *= ce;
-            if (accumulate) {
-                const float4 o = reinterpret_cast<const float4*>(dE)[i];
-                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-            }
-            reinterpret_cast<float4*>(dE)[i] = v;
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // backward_private_kernel (N >> K): grid = (row chunks, column slices); a CTA owns the rows
 // [chunk * rows_per_cta, ...) and the columns [slice * 32 * NC, (slice + 1) * 32 * NC) of z / g_q / dz / dE and keeps
@@ -249,60 +206,6 @@ backward_private_kernel(const float* __restrict__ g_q, const float* __restrict__
             atomicAdd(reinterpret_cast<float4*>(dE + static_cast<size_t>(k) * D + col0) + c4, v);
         }
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// prep: |E_k|^2 as ONE sequential fmaf chain per code (the order oracle/vq_oracle.c:norm2_chain fixes), one THREAD per
-// code with all of its row loads in flight (the warp-per-code version serialised 64 shuffles per code); the tf32
-// hi / lo split of E and the per-step state reset are a coalesced grid-stride pass of the same launch.
-// Needs D % 4 == 0 and 16-byte aligned E / E_hi / E_lo / dE.
-// ---------------------------------------------------------------------------------------------
-constexpr int PREP_THREADS = 128;
-
-__global__ void __launch_bounds__(PREP_THREADS)
-prep_codebook_fast_kernel(const float* __restrict__ E, int K, int D, float* __restrict__ e_norm2, float* __restrict__ E_hi,
-                          float* __restrict__ E_lo, float* __restrict__ hist_zero, unsigned int* __restrict__ counter_zero,
-                          float* __restrict__ dE_zero) {
-    pdl_launch_dependents();
-    const int tid = blockIdx.x * PREP_THREADS + threadIdx.x, nth = gridDim.x * PREP_THREADS;
-    const int DV = D >> 2;
-    pdl_wait_prior_grids();      // E may have just been written (optimizer step); the outputs may still be in use
-    float acc = 0.0f;
-    const int code = blockIdx.x * 32 + threadIdx.x;             // warp 0 of every CTA: one code per lane
-    const bool owns = threadIdx.x < 32 && code < K;
-    if (owns) {
-        const float4* row = reinterpret_cast<const float4*>(E + static_cast<size_t>(code) * D);
-        for (int i0 = 0; i0 < DV; i0 += 8) {
-            float4 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = i0 + u < DV ? __ldg(row + i0 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {                       // zero padding adds exact zeros
-                acc = fmaf(v[u].x, v[u].x, acc);
-                acc = fmaf(v[u].y, v[u].y, acc);
-                acc = fmaf(v[u].z, v[u].z, acc);
-                acc = fmaf(v[u].w, v[u].w, acc);
-            }
-        }
-    }
-    if (owns) e_norm2[code] = acc;
-    if (E_hi != nullptr) {
-        for (int i = tid; i < K * DV; i += nth) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(E) + i);
-            float4 h, l;
-            h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-            reinterpret_cast<float4*>(E_hi)[i] = h;
-            if (E_lo != nullptr) {
-                l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-                reinterpret_cast<float4*>(E_lo)[i] = l;
-            }
-        }
-    }
-    if (hist_zero != nullptr)
-        for (int k = tid; k < K; k += nth) hist_zero[k] = 0.0f;
-    if (counter_zero != nullptr && tid == 0) *counter_zero = 0u;
-    if (dE_zero != nullptr)
-        for (int i = tid; i < K * DV; i += nth) reinterpret_cast<float4*>(dE_zero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 }  // namespace b200vq

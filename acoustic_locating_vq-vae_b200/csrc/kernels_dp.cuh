@@ -18,9 +18,8 @@
 // thread raises state[1] and the kernel drains without waiting any further (results are then garbage, the host
 // reads the error word with vq_dp_status).
 //
-// Everything the exchange carries -- code sums S (the codebook gradient up to a scalar), usage histogram, squared
-// error -- is produced by the FORWARD, so the exchange is launched right behind it and runs concurrently with the
-// backward's dz pass (backward_stream_kernel waits for it only before it reads the reduced sums).
+// The kernel is launched with the programmatic-launch attribute right behind the backward: its CTAs are resident and
+// past their prologue when the backward's last store lands, and the next step's first kernel is launched while it polls.
 #pragma once
 #include "common.cuh"
 
@@ -39,20 +38,6 @@ struct DpCtxDev {
     int world, rank;
     int two_step;
     unsigned int spin_limit;
-};
-
-// where the local contribution comes from: `n_main` floats at `main` (optionally one of two buffers `stride` floats
-// apart, chosen by the forward's call counter: the code sums in its workspace), then the rest of the payload at `tail`
-struct DpSource {
-    const float* main;
-    long long n_main;
-    const float* tail;
-    const unsigned int* counter;     // not NULL: main += ((counter[1] - 1) & 1) * stride
-    long long stride;
-    __device__ __forceinline__ const float* resolve() const {
-        return counter != nullptr ? main + ((__ldcg(counter + 1) - 1u) & 1u) * stride : main;
-    }
-    __device__ __forceinline__ float at(const float* m, long long f) const { return f < n_main ? __ldcg(m + f) : __ldcg(tail + (f - n_main)); }
 };
 
 struct DpCall {
@@ -199,7 +184,7 @@ __device__ __forceinline__ void dp_gather(const DpCtxDev& c, const DpCall& k, co
 
 // body shared by the production kernel (one rank per launch) and the single-GPU emulation (one rank per blockIdx.y)
 template <bool PUSH>
-__device__ __forceinline__ void dp_allreduce_body(const DpCtxDev& c, const DpSource& src, float* __restrict__ out, int* s_abort) {
+__device__ __forceinline__ void dp_allreduce_body(const DpCtxDev& c, const float* __restrict__ payload, float* __restrict__ out, int* s_abort) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     const long long first = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (threadIdx.x == 0) *s_abort = 0;
@@ -207,10 +192,9 @@ __device__ __forceinline__ void dp_allreduce_body(const DpCtxDev& c, const DpSou
     const DpCall k = dp_begin(c);
     const DpWaiter w{c, s_abort};
     if (PUSH) {
-        const float* m = src.resolve();
         for (long long i = first; i < c.L; i += stride) {
-            const float d0 = src.at(m, 2 * i);
-            const float d1 = (2 * i + 1 < c.n) ? src.at(m, 2 * i + 1) : 0.0f;
+            const float d0 = __ldcg(payload + 2 * i);
+            const float d1 = (2 * i + 1 < c.n) ? __ldcg(payload + 2 * i + 1) : 0.0f;
             dp_push_line(c, k, i, d0, d1);
         }
     }
@@ -235,19 +219,19 @@ __device__ __forceinline__ void dp_end(const DpCtxDev& c) {
     }
 }
 
-// PUSH = true : complete all-reduce of the local contribution (written by the previous kernel of the stream)
-// PUSH = false: the first hop was done by the producer; this kernel may start polling while the producer still runs
-//               and only orders itself behind it at its very end, which keeps "previous kernel complete" transitive
-//               along the stream for whatever follows.
+// PUSH = true : complete all-reduce of `payload` (written by the previous kernel of the stream)
+// PUSH = false: the first hop was done by the producer of the data; this kernel may start polling while the producer
+//               still runs and only orders itself behind it at its very end, which keeps "previous kernel complete"
+//               transitive along the stream for whatever follows (building block, not used by the library today).
 template <bool PUSH>
-__global__ void __launch_bounds__(DP_THREADS) dp_allreduce_kernel(const __grid_constant__ DpCtxDev c, const DpSource src,
+__global__ void __launch_bounds__(DP_THREADS) dp_allreduce_kernel(const __grid_constant__ DpCtxDev c, const float* __restrict__ payload,
                                                                   float* __restrict__ out) {
     __shared__ int s_abort;
     if (PUSH) {
         pdl_wait_prior_grids();      // the local contribution is complete ...
         pdl_launch_dependents();     // ... and whoever is launched behind us may rely on that without waiting for US
     }
-    dp_allreduce_body<PUSH>(c, src, out, &s_abort);
+    dp_allreduce_body<PUSH>(c, payload, out, &s_abort);
     if (!PUSH) {
         pdl_wait_prior_grids();
         pdl_launch_dependents();
@@ -264,8 +248,7 @@ __global__ void __launch_bounds__(DP_THREADS) dp_emulate_kernel(const DpCtxDev* 
     __shared__ DpCtxDev c;
     if (threadIdx.x == 0) c = ctxs[blockIdx.y];
     __syncthreads();
-    const DpSource src{payloads != nullptr ? payloads[blockIdx.y] : nullptr, c.n, nullptr, nullptr, 0};
-    dp_allreduce_body<PUSH>(c, src, outs[blockIdx.y], &s_abort);
+    dp_allreduce_body<PUSH>(c, payloads != nullptr ? payloads[blockIdx.y] : nullptr, outs[blockIdx.y], &s_abort);
     dp_end(c);
 }
 

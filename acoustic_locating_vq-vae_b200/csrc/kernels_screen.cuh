@@ -5,8 +5,9 @@
 //
 //   screen   s(n,k) = |E_k|^2 - 2 * <tf32(z_n), tf32(E_k)>          one tcgen05 TF32 pass, fp32 accumulate
 //            |s(n,k) + |z_n|^2 - dist(n,k)| <= eta_n                 eta_n = 2*eps_n + rounding,
-//                                                                    eps_n = 1.02 * 2^-10 * |z_n| * max_k|E_k|
-//            (each operand carries <= 2^-11 relative rounding error; Cauchy-Schwarz over the D products)
+//                                                                    eps_n = (1.02 * 2^-10 + 2 D 2^-24) |z_n| max_k|E_k|
+//            (each operand carries <= 2^-11 relative rounding error; Cauchy-Schwarz over the D products; the second
+//            term bounds the fp32 accumulation error of the tensor core and of the oracle's own fmaf chain)
 //   collect  every code with s(n,k) <= min_k s(n,k) + 2*eta_n is a CANDIDATE; the oracle's argmin -- including all
 //            of its exact ties -- is provably among them.  ~93 % of rows have exactly one candidate.
 //   refine   the row workers evaluate the candidates of the remaining rows in EXACT fp32 in the oracle's order,
@@ -32,12 +33,6 @@
 #include "kernels_tc.cuh"
 
 namespace b200vq {
-
-#ifdef VQ_X_LDG
-#define SC_LD_E2(p) __ldg(p)
-#else
-#define SC_LD_E2(p) __ldcg(p)
-#endif
 
 constexpr int SC_THREADS = 512;
 constexpr int SC_NC_OVERFLOW = 255;   // status: candidate set could not be bounded -> exact scan of the whole codebook
@@ -90,34 +85,10 @@ __device__ __forceinline__ float dot_chain_exact(const float* __restrict__ zr, c
     return acc;
 }
 
-// |E_k|^2 as ONE sequential fmaf chain over d (the order oracle/vq_oracle.c:norm2_chain fixes), the row's loads in flight
-template <int D>
-__device__ __forceinline__ float norm2_chain(const float* __restrict__ erow) {
-    const float4* row = reinterpret_cast<const float4*>(erow);
-    float acc = 0.0f;
-#pragma unroll 1
-    for (int i0 = 0; i0 < D / 4; i0 += 16) {
-        float4 v[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u)
-            if (i0 + u < D / 4) v[u] = __ldg(row + i0 + u);
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            if (i0 + u < D / 4) {
-                acc = fmaf(v[u].x, v[u].x, acc);
-                acc = fmaf(v[u].y, v[u].y, acc);
-                acc = fmaf(v[u].z, v[u].z, acc);
-                acc = fmaf(v[u].w, v[u].w, acc);
-            }
-        }
-    }
-    return acc;
-}
-
 template <int NSLAB, int NSTAGE, int ZBUF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SC_THREADS, 1)
 vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_ehi,
-                 const float* e_norm2, long long N, int K, int n_items, int* __restrict__ idx_out,
+                 const float* __restrict__ e_norm2, long long N, int K, int n_items, int* __restrict__ idx_out,
                  const FusedRowArgs fr) {
     extern __shared__ uint8_t smem_raw[];
 #ifdef VQ_TRACE
@@ -163,7 +134,6 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
     int* pair_count = reinterpret_cast<int*>(s_bmax + 8);     // [2]
     int* ovf_count = pair_count + 2;                          // [2]
     int* spill_cnt = ovf_count + 2;                           // [4] entries spilled for item it & 3
-    int* norms_local = spill_cnt + 4;                         // self-prepared mode: the other CTAs' norms did not arrive in time
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = cluster_ctarank();
@@ -213,19 +183,10 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait_prior_grids();
-    if (fr.sums_ws != nullptr) {
-        // code sums: the next call's accumulator (its last readers, the previous step's backward / exchange, are complete)
-        const size_t kd = static_cast<size_t>(K) * (NSLAB * TC_SLAB_FLOATS);
-        float4* nxt = reinterpret_cast<float4*>(fr.sums_ws + ((__ldcg(fr.counter + 1) + 1u) & 1u) * kd);
-        for (size_t i = static_cast<size_t>(blockIdx.x) * SC_THREADS + threadIdx.x; i < kd / 4; i += static_cast<size_t>(gridDim.x) * SC_THREADS)
-            nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
     // The next kernel of the stream may be LAUNCHED from here on: its CTAs only become resident as ours exit (this
     // kernel owns the SM's registers and shared memory) and they order themselves with griddepcontrol.wait, so the
     // trigger costs nothing and takes the launch latency off the step's critical path.
-#ifndef VQ_X_LATE_TRIGGER
     pdl_launch_dependents();
-#endif
     if (threadIdx.x == 0) {
         VQ_TR(7, 0);
 #ifdef VQ_TRACE
@@ -358,33 +319,10 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
         const int row = (ew & 3) * 32 + lane;
         const int et = threadIdx.x - 128;
         const uint32_t lane_base = static_cast<uint32_t>((ew & 3) * 32) << 16;
-        // max_k |E_k|^2 (for the margin): 256 threads scan e_norm2 once.  In self-prepared mode the norms are computed
-        // by THIS launch: every CTA takes the codes k = blockIdx.x (mod gridDim.x) (two row-worker warps, below),
-        // publishes them and bumps a counter in the workspace; here one thread waits until all CTAs have published.
-        // The wait is bounded: if the other CTAs do not show up (they are not resident -- a GPU shared with other
-        // work), this CTA computes all K norms itself (every CTA reading the whole codebook at once is what makes
-        // that path slow: +30 us at K = 1024, D = 64).
+        // max_k |E_k|^2 (for the margin): 256 threads scan e_norm2 once
         {
             float bm = 0.0f;
-            if (fr.e_norm2_w != nullptr) {
-                if (et == 0) {
-                    const unsigned long long* ready = reinterpret_cast<const unsigned long long*>(fr.counter + 2);
-                    const unsigned int call_no = __ldcg(fr.counter + 1);
-                    int ok = 0;
-                    for (unsigned int polls = 0; polls < (1u << 16) && !ok; ++polls) {
-                        unsigned long long v;
-                        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ready) : "memory");
-                        ok = (static_cast<unsigned int>(v >> 32) == call_no && static_cast<unsigned int>(v) >= gridDim.x) ? 1 : 0;
-                    }
-                    *norms_local = ok ? 0 : 1;
-                }
-                named_bar_sync(1, 256);
-                if (*norms_local) {
-                    for (int k = et; k < K; k += 256) fr.e_norm2_w[k] = norm2_chain<D>(fr.E + static_cast<size_t>(k) * D);
-                    named_bar_sync(1, 256);
-                }
-            }
-            for (int k = et; k < K; k += 256) bm = fmaxf(bm, SC_LD_E2(e_norm2 + k));
+            for (int k = et; k < K; k += 256) bm = fmaxf(bm, __ldg(e_norm2 + k));
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
             if (lane == 0) s_bmax[ew] = bm;
@@ -397,10 +335,6 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
             named_bar_sync(1, 256);
         }
         const float b_max = s_bmax[0];
-        // 4 * eps on the score scale (see the header).  Operand rounding: z is rounded to nearest (2^-11), the codebook
-        // either too (prepared tf32(E)) or truncated by the tensor core (raw E: 2^-10), each with 2 % slack; plus the
-        // fp32 accumulation error of the tensor core's and of the oracle's D-term sums, 2 * D * 2^-24 |z||E| together.
-        // (evaluated per item from the kernel parameters: nothing extra stays live across the register-bound tile scan)
         {   // help the z pipeline with the first tile
             mbar_wait(bar_z_full + 0, 0);
             named_bar_sync(5, 320);
@@ -409,16 +343,14 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
             named_bar_sync(5, 320);
         }
         int it = 0, ctg = 0;
-        float b_next = SC_LD_E2(e_norm2 + et);
+        float b_next = __ldg(e_norm2 + et);
         for (int w = pair; w < n_items; w += n_pairs, ++it) {
             mbar_wait(bar_a_ready + (it % TC2_ARING), (it / TC2_ARING) & 1);
             const float a_n = a_ring[(it % TC2_ARING) * TC_ROWS + row];
             // margin on the score scale: 2*eta = 4*eps + rounding slack (see the header)
-#ifdef VQ_X_NO_DTERM
-            const float margin_c = 0.00398438f;
-#else
-            const float margin_c = (fr.e_norm2_w != nullptr ? 1.5f * 0.00398438f : 0.00398438f) + static_cast<float>(D) * 4.7683716e-7f;
-#endif
+            // + the fp32 accumulation error of the tensor core's and of the oracle's D-term sums: 2 * D * 2^-24 |z||E|
+            // together, x 4 on this scale (negligible next to the operand term at D <= 256, but part of the bound)
+            constexpr float margin_c = 0.00398438f + static_cast<float>(D) * 4.7683716e-7f;
             const float margin = 1.0001f * (margin_c * sqrtf(a_n * b_max) + 1.9073486e-6f * (a_n + b_max));
             float rmin = INFINITY;   // running minimum of the screening scores of this (row, half)
             int n = 0;               // entries in this thread's candidate log
@@ -439,7 +371,7 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                 const int k0 = ct * TC2_CODES;
                 b_tile[buf * TC2_CODES + et] = b_next;
                 named_bar_sync(1, 256);
-                b_next = SC_LD_E2(e_norm2 + (ct + 1 == n_ctiles ? 0 : k0 + TC2_CODES) + et);   // for the next tile
+                b_next = __ldg(e_norm2 + (ct + 1 == n_ctiles ? 0 : k0 + TC2_CODES) + et);   // for the next tile
                 if (et == 0) VQ_TR(0, 3 * ctg);
                 mbar_wait(bar_acc_full + buf, (ctg >> 1) & 1);
                 if (et == 0) VQ_TR(0, 3 * ctg + 1);
@@ -657,27 +589,6 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
         int* const g_ocount = ovf_count + grp;
         unsigned long long* const g_okey = ovf_key + grp;
         float sse = 0.0f;
-        // self-prepared mode: the usage counts of call c accumulate in workspace buffer [c & 1] (zeroed by call c - 1)
-        unsigned int call_no = 0u;
-        float* hist_acc = fr.hist;
-        float* hist_reset = nullptr;
-        float* sums_acc = nullptr;
-        if (fr.hist_ws != nullptr) {
-            call_no = __ldcg(fr.counter + 1);
-            hist_acc = fr.hist_ws + static_cast<size_t>(call_no & 1u) * K;
-            hist_reset = fr.hist_ws + static_cast<size_t>((call_no + 1u) & 1u) * K;
-            if (fr.sums_ws != nullptr) sums_acc = fr.sums_ws + (call_no & 1u) * (static_cast<size_t>(K) * D);
-        }
-        if (fr.e_norm2_w != nullptr && threadIdx.x >= 448) {
-            // self-prepared mode: this CTA's share of the codebook norms (codes blockIdx.x, + gridDim.x, ...), one code
-            // per thread, then ONE release-add for the CTA; the epilogue warps of every CTA wait for the count
-            const int nt = threadIdx.x - 448;
-            for (int k = blockIdx.x + nt * static_cast<int>(gridDim.x); k < K; k += 64 * static_cast<int>(gridDim.x))
-                fr.e_norm2_w[k] = norm2_chain<D>(fr.E + static_cast<size_t>(k) * D);
-            __threadfence();
-            named_bar_sync(8, 64);
-            if (nt == 0) atomicAdd(reinterpret_cast<unsigned long long*>(fr.counter + 2), 1ull);
-        }
         for (int w = pair + grp * n_pairs, it = grp; w < n_items; w += groups * n_pairs, it += groups) {
             const long long row0 = static_cast<long long>(2 * w + static_cast<int>(cta_rank)) * TC_ROWS;
             const long long left = N - row0;
@@ -747,7 +658,7 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                     if (rc >= 0) {
                         const int r = rc >> 20, k = rc & 0xfffff;
                         const float c = dot_chain_exact<D>(fr.z + (row0 + r) * D, fr.E + static_cast<size_t>(k) * D);
-                        atomicMin(g_key + r, pack_key(fmaf(-2.0f, c, ans[r] + SC_LD_E2(e_norm2 + k)), k));
+                        atomicMin(g_key + r, pack_key(fmaf(-2.0f, c, ans[r] + __ldg(e_norm2 + k)), k));
                     }
                 }
             }
@@ -797,7 +708,7 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                     for (int j = 0; j < 4; ++j) {
                         const int k = kb + j * NW;
                         if (k < K) {
-                            const float dist = fmaf(-2.0f, acc[j], a + SC_LD_E2(e_norm2 + k));
+                            const float dist = fmaf(-2.0f, acc[j], a + __ldg(e_norm2 + k));
                             const unsigned long long kk = pack_key(dist, k);
                             key = kk < key ? kk : key;
                         }
@@ -819,7 +730,7 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
             for (int r = wt; r < rows_here; r += NW) {
                 const int code = g_idx[r];
                 idx_out[row0 + r] = code;
-                atomicAdd(hist_acc + code, 1.0f);
+                atomicAdd(fr.hist + code, 1.0f);
             }
             // -- q_out = fl(z + fl(E[idx] - z)), sse += (E[idx] - z)^2 ---------------------------------------------
             if (quant) {
@@ -830,14 +741,12 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
 #pragma unroll 1
                 for (int ub = 0; wt + ub * NW < n_el; ub += UB) {
                     float4 zv[UB], ev[UB];
-                    int eo[UB];                             // float4 offset of the element inside the codebook
 #pragma unroll
                     for (int u = 0; u < UB; ++u) {
                         const int e = wt + (ub + u) * NW;
                         if (e < n_el) {
                             zv[u] = __ldg(z4 + e);
-                            eo[u] = g_idx[e / DV] * DV + (e % DV);
-                            ev[u] = __ldg(reinterpret_cast<const float4*>(fr.E) + eo[u]);
+                            ev[u] = __ldg(reinterpret_cast<const float4*>(fr.E + static_cast<size_t>(g_idx[e / DV]) * D) + (e % DV));
                         }
                     }
 #pragma unroll
@@ -851,10 +760,6 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                             __stcs(q4 + e, qv);
                             sse = fmaf(df.x, df.x, sse); sse = fmaf(df.y, df.y, sse);
                             sse = fmaf(df.z, df.z, sse); sse = fmaf(df.w, df.w, sse);
-                            // the codebook gradient's scatter-add, while E[idx] - z is in registers (fire and forget, L2)
-#ifndef VQ_X_NO_SUMS
-                            if (sums_acc != nullptr) atomicAdd(reinterpret_cast<float4*>(sums_acc) + eo[u], df);
-#endif
                         }
                     }
                 }
@@ -870,14 +775,10 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
         }
         if (wt_all == 0) VQ_TR(6, 2);
         // per-CTA SSE partial, then last-CTA-done reduction in a fixed order (+ loss / perplexity)
-        publish_and_finalize(fr, sse, N, K, D, wt_all, NW_all, lane, have_oh ? warp - 13 : warp - 12, have_oh ? 3 : 4, red, 7, hist_acc, hist_reset,
-                             call_no);
+        publish_and_finalize(fr, sse, N, K, D, wt_all, NW_all, lane, have_oh ? warp - 13 : warp - 12, have_oh ? 3 : 4, red, 7);
     }
 
     if (threadIdx.x == 0) VQ_TR(7, 1);
-#ifdef VQ_X_LATE_TRIGGER
-    pdl_launch_dependents();
-#endif
     tc_fence_before();
     cluster_sync_all();
     if (threadIdx.x == 0) {

@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(256) onehot_kernel(const int* __restrict__ idx
     const long long warp0 = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     const long long nwarps = static_cast<long long>(gridDim.x) * 8;
     for (long long r = warp0; r < N; r += nwarps) {
-        const int code = idx[r];
+        const int code = idx[r];            // a value outside [0, K) leaves an all-zero row
         float* orow = onehot + r * K;
         if (vec_ok) {
             for (int c = lane; c < (K >> 2); c += 32) {
@@ -431,7 +431,10 @@ __global__ void __launch_bounds__(256) gather_sum_rows_kernel(const int* __restr
                                                               int K, int O) {
     extern __shared__ int s_rows[];                       // [T] row of Wt for every position of this sample
     const int b = blockIdx.x;
-    for (int t = threadIdx.x; t < T; t += blockDim.x) s_rows[t] = t * K + idx[b * T + t];
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        const int code = idx[b * T + t];
+        s_rows[t] = static_cast<unsigned>(code) < static_cast<unsigned>(K) ? t * K + code : -1;   // -1: not a code, contributes nothing
+    }
     __syncthreads();
     const int o4 = blockIdx.y * blockDim.x + threadIdx.x;  // float4 index along O
     if (o4 * 4 >= O) return;
@@ -439,18 +442,20 @@ __global__ void __launch_bounds__(256) gather_sum_rows_kernel(const int* __restr
     const int O4 = O >> 2;
     float4 acc = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias) + o4) : make_float4(0.f, 0.f, 0.f, 0.f);
     int t = 0;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto row_at = [&](int r) { return r >= 0 ? __ldg(W4 + static_cast<size_t>(r) * O4 + o4) : zero4; };
     for (; t + 4 <= T; t += 4) {                           // 4 independent row reads in flight
-        const float4 v0 = __ldg(W4 + static_cast<size_t>(s_rows[t]) * O4 + o4);
-        const float4 v1 = __ldg(W4 + static_cast<size_t>(s_rows[t + 1]) * O4 + o4);
-        const float4 v2 = __ldg(W4 + static_cast<size_t>(s_rows[t + 2]) * O4 + o4);
-        const float4 v3 = __ldg(W4 + static_cast<size_t>(s_rows[t + 3]) * O4 + o4);
+        const float4 v0 = row_at(s_rows[t]);
+        const float4 v1 = row_at(s_rows[t + 1]);
+        const float4 v2 = row_at(s_rows[t + 2]);
+        const float4 v3 = row_at(s_rows[t + 3]);
         acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
         acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
         acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
         acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
     }
     for (; t < T; ++t) {
-        const float4 v = __ldg(W4 + static_cast<size_t>(s_rows[t]) * O4 + o4);
+        const float4 v = row_at(s_rows[t]);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     reinterpret_cast<float4*>(y + static_cast<size_t>(b) * O)[o4] = acc;
@@ -460,7 +465,9 @@ __global__ void __launch_bounds__(256) gather_sum_rows_kernel(const int* __restr
 __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const int* __restrict__ idx, const float* __restrict__ g,
                                                                float* __restrict__ dWt, int T, int K, int O) {
     const int b = blockIdx.x, t = blockIdx.y;
-    const size_t row = static_cast<size_t>(t) * K + idx[b * T + t];
+    const int code = idx[b * T + t];
+    if (static_cast<unsigned>(code) >= static_cast<unsigned>(K)) return;      // not a code: no gradient row
+    const size_t row = static_cast<size_t>(t) * K + code;
     const int O4 = O >> 2;
     for (int o4 = threadIdx.x; o4 < O4; o4 += blockDim.x) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(g + static_cast<size_t>(b) * O) + o4);
@@ -482,7 +489,7 @@ __global__ void __launch_bounds__(256) jitter_gather_kernel(float* __restrict__ 
     __syncthreads();
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
         const int sc = src[t];
-        if (sc != t) qr[t] = jrow[sc];
+        if (sc != t && static_cast<unsigned>(sc) < static_cast<unsigned>(T)) qr[t] = jrow[sc];
     }
 }
 __global__ void __launch_bounds__(256) jitter_backward_kernel(float* __restrict__ g, const int* __restrict__ src, long long rows, int T) {

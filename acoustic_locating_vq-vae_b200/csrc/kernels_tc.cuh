@@ -310,15 +310,6 @@ struct FusedRowArgs {
     int onehot_evict_first;    // 1: one-hot stores carry an L2 evict_first policy (tuning knob)
     int4* spill;               // screen kernel: [grid][4][SC_SPILL] {row, score, code | chain-instance, type} (workspace)
     long long* trace;          // VQ_TRACE builds only: [cta][role 0..7][64] clock64 stamps
-    // self-prepared mode (vq_step_forward, screen kernel): no prepare launch precedes the forward.
-    float* e_norm2_w;          // not NULL: the kernel computes |E_k|^2 itself into this buffer (the e_norm2 argument) and the
-                               // tensor map covers the RAW codebook (the tensor core drops the low mantissa bits itself)
-    float* hist_ws;            // not NULL: [2][K] usage accumulators in the workspace; call c counts into [c & 1], its last CTA
-                               // copies the counts to `hist` and zeroes [(c + 1) & 1] for the next call; counter[1] = c
-    float* sums_ws;            // not NULL (needs hist_ws, q_out): [2][K*D] code sums S_k = sum_{n: idx_n = k} (E_k - z_n), the whole
-                               // codebook gradient up to the scalar g_loss * 2 / (N * D) (autograd of vector_quantizer.py:43-50):
-                               // call c accumulates into [c & 1] with 16-byte reds while E[idx] - z is in registers anyway;
-                               // every CTA zeroes a slice of [(c + 1) & 1] at its start
 };
 
 // The '1's of the dense one-hot (vector_quantizer.py:40).  The filler thread zero-fills whole rows with bulk copies;
@@ -366,13 +357,7 @@ __device__ __forceinline__ void patch_onehot_ones(float* __restrict__ onehot, co
 // `bar_id`); `red` is 5 doubles of shared scratch.  This is the tail of the kernel's critical path: the partials and
 // the first 12 histogram entries per thread are fetched in ONE round trip, later batches 12 at a time.
 __device__ __forceinline__ void publish_and_finalize(const FusedRowArgs& fr, float sse, long long N, int K, int D, int wt, int nw,
-                                                     int lane, int wwarp, int n_warps, double* red, int bar_id,
-                                                     const float* hist_acc = nullptr, float* hist_reset = nullptr,
-                                                     unsigned int call_no = 0u) {
-    // hist_acc: where this call counted code usage (default: fr.hist itself); in self-prepared mode the counts are
-    // copied to fr.hist, `hist_reset` (the next call's accumulator) is zeroed and the call counter advances
-    const bool self = hist_reset != nullptr;
-    if (hist_acc == nullptr) hist_acc = fr.hist;
+                                                     int lane, int wwarp, int n_warps, double* red, int bar_id) {
     auto red_total = [&]() {
         double t = red[0];
         for (int i = 1; i < n_warps; ++i) t += red[i];
@@ -398,7 +383,7 @@ __device__ __forceinline__ void publish_and_finalize(const FusedRowArgs& fr, flo
     const double p1 = wt + nw < g ? __ldcg(fr.partials + wt + nw) : 0.0;
     float h[HB];
 #pragma unroll
-    for (int u = 0; u < HB; ++u) h[u] = ((fin || self) && wt + u * nw < K) ? __ldcg(hist_acc + wt + u * nw) : 0.0f;
+    for (int u = 0; u < HB; ++u) h[u] = (fin && wt + u * nw < K) ? __ldcg(fr.hist + wt + u * nw) : 0.0f;
     double t = p0 + p1;
     for (int i = wt + 2 * nw; i < g; i += nw) t += __ldcg(fr.partials + i);
     t = warp_sum_d(t);
@@ -410,8 +395,8 @@ __device__ __forceinline__ void publish_and_finalize(const FusedRowArgs& fr, flo
         *fr.sse_out = static_cast<float>(total);
         *fr.counter = 0u;
     }
-    if (!fin && !self) return;
-    if (fin && wt == 0 && fr.q_out != nullptr) {
+    if (!fin) return;
+    if (wt == 0 && fr.q_out != nullptr) {
         const float m = static_cast<float>(total / (static_cast<double>(N) * static_cast<double>(D)));
         *fr.loss = __fadd_rn(m, __fmul_rn(fr.beta, m));                      // vector_quantizer.py:52
     }
@@ -420,26 +405,16 @@ __device__ __forceinline__ void publish_and_finalize(const FusedRowArgs& fr, flo
     for (int kb = wt; kb < K; kb += HB * nw) {
         if (kb != wt) {
 #pragma unroll
-            for (int u = 0; u < HB; ++u) h[u] = kb + u * nw < K ? __ldcg(hist_acc + kb + u * nw) : 0.0f;
+            for (int u = 0; u < HB; ++u) h[u] = kb + u * nw < K ? __ldcg(fr.hist + kb + u * nw) : 0.0f;
         }
 #pragma unroll
         for (int u = 0; u < HB; ++u) {
             if (kb + u * nw < K) {
-                if (self) {
-                    fr.hist[kb + u * nw] = h[u];
-                    hist_reset[kb + u * nw] = 0.0f;
-                }
                 const float p = __fdiv_rn(h[u], nf);                         // vector_quantizer.py:55
                 ent += static_cast<double>(p * logf(p + 1e-10f));            // :56
             }
         }
     }
-    if (self && wt == 0) {
-        fr.counter[1] = call_no + 1u;
-        // the norms-published counter of the next call: tag = its call number, count = 0 (every CTA is past its wait)
-        *reinterpret_cast<unsigned long long*>(fr.counter + 2) = static_cast<unsigned long long>(call_no + 1u) << 32;
-    }
-    if (!fin) return;
     ent = warp_sum_d(ent);
     named_bar_sync(bar_id, nw);
     if (lane == 0) red[wwarp] = ent;

@@ -6,6 +6,11 @@ decisions are drawn on the host with the SAME np.random calls in the same order 
 result, including the reference's quirk that a column is replaced with probability 1 - p, jitter.py:50), and
 applied by ONE in-place gather kernel.  As in the reference the input tensor is mutated and returned, and the
 replaced columns carry no gradient (their values come from a detached clone).
+
+Attribution: the decision procedure reproduced by `draw_source_columns` (replace with a fixed probability, first / last
+column take their only neighbour, otherwise left or right with equal probability) is that of the reference's jitter.py,
+which carries an MIT licence header: Copyright (C) 2019 Charly Lamothe, part of VQ-VAE-Speech.  Only the sequence of
+random draws is mirrored here (it is the contract a numpy seed pins); the tensor work is this repository's own kernel.
 """
 from __future__ import annotations
 
@@ -24,6 +29,8 @@ def draw_source_columns(length: int, probability: float) -> np.ndarray:
         replace = [True, False][np.random.choice([1, 0], p=[probability, 1 - probability])]
         if replace:
             if i == 0:
+                if length < 2:      # the reference indexes column 1 of a single-column tensor here (jitter.py:57,68)
+                    raise IndexError("index 1 is out of bounds for dimension 2 with size 1")
                 src[i] = i + 1
             elif i == length - 1:
                 src[i] = i - 1
@@ -37,7 +44,8 @@ class _JitterFn(torch.autograd.Function):
     def forward(ctx, quantized, src):
         lib = _lib.load()
         B, D, T = quantized.shape
-        check(lib.vq_jitter_apply(quantized.data_ptr(), src.data_ptr(), B * D, T, torch.cuda.current_stream().cuda_stream))
+        with torch.cuda.device(quantized.device):      # the C ABI launches on the current device: follow the tensor
+            check(lib.vq_jitter_apply(quantized.data_ptr(), src.data_ptr(), B * D, T, torch.cuda.current_stream(quantized.device).cuda_stream))
         ctx.mark_dirty(quantized)
         ctx.save_for_backward(src)
         return quantized
@@ -48,7 +56,8 @@ class _JitterFn(torch.autograd.Function):
         lib = _lib.load()
         g = g.contiguous().clone()
         B, D, T = g.shape
-        check(lib.vq_jitter_backward(g.data_ptr(), src.data_ptr(), B * D, T, torch.cuda.current_stream().cuda_stream))
+        with torch.cuda.device(g.device):
+            check(lib.vq_jitter_backward(g.data_ptr(), src.data_ptr(), B * D, T, torch.cuda.current_stream(g.device).cuda_stream))
         return g, None
 
 

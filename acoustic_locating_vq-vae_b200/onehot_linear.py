@@ -25,10 +25,11 @@ class _GatherSum(torch.autograd.Function):
         B, T = idx.shape
         O = weight_t.shape[1]
         y = torch.empty(B, O, dtype=torch.float32, device=weight_t.device)
-        st = torch.cuda.current_stream().cuda_stream
         w = weight_t.detach()
-        check(lib.vq_gather_sum_rows(idx.data_ptr(), w.data_ptr(), None if bias is None else bias.detach().data_ptr(),
-                                     y.data_ptr(), B, T, K, O, st))
+        with torch.cuda.device(weight_t.device):       # the C ABI launches on the current device: follow the tensors
+            st = torch.cuda.current_stream(weight_t.device).cuda_stream
+            check(lib.vq_gather_sum_rows(idx.data_ptr(), w.data_ptr(), None if bias is None else bias.detach().data_ptr(),
+                                         y.data_ptr(), B, T, K, O, st))
         ctx.save_for_backward(idx)
         ctx.shape = (weight_t.shape[0], O, K, bias is not None, sparse_grad)
         return y
@@ -48,8 +49,9 @@ class _GatherSum(torch.autograd.Function):
             else:
                 lib = _lib.load()
                 gw = torch.zeros(rows_total, O, dtype=torch.float32, device=g.device)
-                check(lib.vq_scatter_add_rows(idx.data_ptr(), g.data_ptr(), gw.data_ptr(), B, T, K, O,
-                                              torch.cuda.current_stream().cuda_stream))
+                with torch.cuda.device(g.device):
+                    check(lib.vq_scatter_add_rows(idx.data_ptr(), g.data_ptr(), gw.data_ptr(), B, T, K, O,
+                                                  torch.cuda.current_stream(g.device).cuda_stream))
         gb = g.sum(0) if (has_bias and ctx.needs_input_grad[2]) else None
         return None, gw, gb, None, None
 
@@ -95,5 +97,5 @@ class OneHotLinear(nn.Module):
             raise RuntimeError("b200vq.OneHotLinear runs on a B200 GPU only (no CPU fallback)")
         if indices.dim() != 2 or indices.shape[1] != self.positions:
             raise RuntimeError(f"expected (B, {self.positions}) code indices, got {tuple(indices.shape)}")
-        idx = indices.to(torch.int32).contiguous()
+        idx = indices.to(torch.int32).contiguous()     # codes outside [0, K) contribute nothing (the kernels skip them)
         return _GatherSum.apply(idx, self.weight_t, self.bias, self.num_embeddings, self.sparse_grad)

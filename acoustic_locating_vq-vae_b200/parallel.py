@@ -114,14 +114,6 @@ class PeerExchange:
         self.check(self.lib.vq_dp_allreduce(self.ctx, payload.data_ptr(), out.data_ptr(), stream_ptr))
         return out
 
-    def exchange_sums(self, workspace: torch.Tensor, n_rows: int, K: int, D: int, tail: torch.Tensor, out: torch.Tensor,
-                      stream_ptr: int) -> torch.Tensor:
-        """out = sum over ranks of [code sums of the last vq_step_forward on `workspace` | tail]."""
-        assert K * D + tail.numel() == self.n and out.numel() == self.n
-        self.check(self.lib.vq_dp_exchange_sums(self.ctx, workspace.data_ptr(), workspace.numel(), n_rows, K, D, tail.data_ptr(),
-                                                tail.numel(), out.data_ptr(), stream_ptr))
-        return out
-
     def status(self, stream_ptr: int = 0):
         """(calls completed, error word) -- synchronises the stream; error bit 0 = a bounded wait expired."""
         import ctypes

@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, parallel
-from ._lib import (FLAG_CODE_SUMS, FLAG_EXACT, FLAG_ONEHOT, FLAG_TRAIN_VQ, FLAG_ZERO_DE, check)
+from ._lib import (FLAG_EXACT, FLAG_ONEHOT, FLAG_TRAIN_VQ, FLAG_ZERO_DE, check)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -37,15 +37,13 @@ class _Buffers:
     """Per-module device scratch, grown on demand and reused (stream-ordered, one stream per module)."""
 
     def __init__(self):
-        self.ws = None       # workspace of vq_step_forward: carries the call counter / accumulators from call to call
+        self.ws = None
         self.code = None     # (e_norm2, E_hi, E_lo)
         self.ws_bytes = {}   # (N, K, D) -> vq_workspace_bytes
-        self.sums = {}       # (N, K, D) -> vq_step_uses_code_sums
 
-    def workspace(self, lib, nbytes: int, device, stream: int) -> torch.Tensor:
+    def workspace(self, nbytes: int, device) -> torch.Tensor:
         if self.ws is None or self.ws.numel() < nbytes or self.ws.device != device:
             self.ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
-            check(lib.vq_workspace_init(self.ws.data_ptr(), self.ws.numel(), stream))     # once per allocation
         return self.ws
 
     def codebook(self, K: int, D: int, device):
@@ -58,12 +56,8 @@ class _Buffers:
 
 
 class _VQFunction(torch.autograd.Function):
-    """forward = vq_step_forward (ONE launch on the screen + refine path); backward = vq_step_backward.
-
-    When the codebook trains, the forward also accumulates the code sums S_k = sum (E_k - z_n) (VQ_FLAG_CODE_SUMS) and
-    the backward is a pure streaming pass; under data parallelism [S | usage histogram | squared error] is exchanged
-    right behind the forward (nothing in it depends on upstream gradients), so the collective overlaps whatever the
-    model does between the quantizer's forward and backward."""
+    """forward = vq_step_forward (codebook preparation + fused forward behind one C call); backward = vq_backward,
+    followed under data parallelism by ONE sum all-reduce of the packed [dE | usage histogram | squared error]."""
 
     @staticmethod
     def forward(ctx, inputs, weight, module, flags, want_onehot):
@@ -80,38 +74,31 @@ class _VQFunction(torch.autograd.Function):
         e_norm2, e_hi, e_lo = bufs.codebook(K, D, dev)
         q_out = torch.empty_like(inputs)
         idx = torch.empty(N, dtype=torch.int32, device=dev)
-        scal = torch.empty(K + 3, dtype=torch.float32, device=dev)     # [hist (K) | sse | loss | perplexity]
+        dp = module.process_group is not None or module.data_parallel
+        packed = None
+        if dp and bool(module._train_vq) and weight.requires_grad and torch.is_grad_enabled():
+            # data parallel: the forward writes hist | sse straight behind the slot of dE in the packed step buffer
+            packed = torch.empty(K * D + K + 3, dtype=torch.float32, device=dev)
+            scal = packed[K * D:]
+        else:
+            scal = torch.empty(K + 3, dtype=torch.float32, device=dev)     # [hist (K) | sse | loss | perplexity]
         onehot = torch.empty(N, K, dtype=torch.float32, device=dev) if want_onehot else None
-        train_vq = bool(module._train_vq)
-        wants_dE = train_vq and weight.requires_grad and torch.is_grad_enabled()
+        fl = flags | (FLAG_ONEHOT if want_onehot else 0)
         key = (N, K, D)
         nbytes = bufs.ws_bytes.get(key)
         if nbytes is None:
             nbytes = bufs.ws_bytes[key] = lib.vq_workspace_bytes(N, K, D, 0)
-            bufs.sums[key] = bool(lib.vq_step_uses_code_sums(N, K, D, flags | FLAG_CODE_SUMS))
-        sums = wants_dE and bufs.sums[key]
-        fl = flags | (FLAG_ONEHOT if want_onehot else 0) | (FLAG_CODE_SUMS if sums else 0)
-        ws = bufs.workspace(lib, nbytes, dev, st)
+        ws = bufs.workspace(nbytes, dev)
         sp = scal.data_ptr()
         check(lib.vq_step_forward(_ptr(flat), _ptr(w), N, K, D, float(module._commitment_cost), fl,
-                                  _ptr(e_norm2), _ptr(e_hi), _ptr(e_lo), _ptr(q_out), _ptr(idx), _ptr(onehot),
+                                  _ptr(e_norm2), _ptr(e_hi), _ptr(e_lo), None, _ptr(q_out), _ptr(idx), _ptr(onehot),
                                   sp, sp + 4 * K, sp + 4 * (K + 1), sp + 4 * (K + 2), _ptr(ws), ws.numel(), st))
         loss = scal[K + 1]
         perplexity = scal[K + 2]
-        reduced = None
-        if sums and (module.process_group is not None or module.data_parallel):
-            # data parallel: everything the exchange carries exists now -- launch it right behind the forward
-            ex = module._peer_exchange(K, D, dev, module.process_group)
-            if ex is not None:
-                reduced = torch.empty(K * D + K + 1, dtype=torch.float32, device=dev)
-                ex.exchange_sums(ws, N, K, D, scal[:K + 1], reduced, st)
         ctx.save_for_backward(inputs, weight, idx)
         ctx.module = module
-        ctx.stats = scal
-        ctx.train_vq = train_vq
-        ctx.sums = sums
-        ctx.reduced = reduced
-        ctx.ws = ws
+        ctx.packed = packed
+        ctx.train_vq = bool(module._train_vq)
         if onehot is not None:
             ctx.mark_non_differentiable(perplexity, idx, onehot)
         else:
@@ -154,32 +141,25 @@ class _VQFunction(torch.autograd.Function):
                 check(lib.vq_backward(_ptr(g_q), _ptr(g_loss), _ptr(inputs), _ptr(w), _ptr(idx), N, n_dz, n_dE, K, D, beta, 0,
                                       _ptr(dz), None, st))
             return dz, None, None, None, None
-        dE = torch.empty(K, D, dtype=torch.float32, device=dev)
-        if ctx.sums and (world == 1 or ctx.reduced is not None):
-            # the forward accumulated the code sums: stream dz, scale S (all-reduced at forward time under data parallelism)
-            red = ctx.reduced
-            check(lib.vq_step_backward(_ptr(g_q), _ptr(g_loss), _ptr(inputs), _ptr(w), _ptr(idx), N, n_dz, n_dE, K, D, beta,
-                                       FLAG_TRAIN_VQ | FLAG_ZERO_DE | FLAG_CODE_SUMS, _ptr(dz), _ptr(dE), _ptr(ctx.ws), ctx.ws.numel(),
-                                       _ptr(red), st))
-            if red is not None:
-                module.__dict__["_global_stats"] = (red[K * D:], N * world)
-            return dz, dE, None, None, None
-        if world == 1:
+        packed = ctx.packed
+        if world == 1 or packed is None:
+            dE = torch.empty(K, D, dtype=torch.float32, device=dev)
             check(lib.vq_backward(_ptr(g_q), _ptr(g_loss), _ptr(inputs), _ptr(w), _ptr(idx), N, n_dz, n_dE, K, D, beta,
                                   FLAG_TRAIN_VQ | FLAG_ZERO_DE, _ptr(dz), _ptr(dE), st))
+            if world > 1:       # the codebook was frozen when the forward ran: nothing was packed -- plain all-reduce of dE
+                import torch.distributed as dist
+                dist.all_reduce(dE, group=pg)
             return dz, dE, None, None, None
-        # data parallel without code sums (shapes outside the screen path): one all-reduce of [dE | hist | sse] after the backward
-        packed = parallel.new_packed(K, D, dev)
-        dEp = parallel.packed_views(packed, K, D)[0]
-        check(lib.vq_backward(_ptr(g_q), _ptr(g_loss), _ptr(inputs), _ptr(w), _ptr(idx), N, n_dz, n_dE, K, D, beta, FLAG_TRAIN_VQ,
-                              _ptr(dz), _ptr(dEp), st))
-        packed[K * D:] = ctx.stats[:K + 1]
+        # data parallel: dE lands in front of the statistics the forward left in the packed buffer; ONE all-reduce
+        check(lib.vq_backward(_ptr(g_q), _ptr(g_loss), _ptr(inputs), _ptr(w), _ptr(idx), N, n_dz, n_dE, K, D, beta,
+                              FLAG_TRAIN_VQ | FLAG_ZERO_DE, _ptr(dz), _ptr(packed), st))
+        n = K * D + K + 1
         ex = module._peer_exchange(K, D, dev, pg)
         if ex is not None:
-            reduced = torch.empty_like(packed)
-            ex.allreduce(packed, reduced, st)
+            reduced = torch.empty(n, dtype=torch.float32, device=dev)      # fresh: autograd may keep dE as the gradient
+            ex.allreduce(packed[:n], reduced, st)
         else:
-            reduced = parallel.all_reduce_packed(packed, pg)
+            reduced = parallel.all_reduce_packed(packed[:n], pg)
         module.__dict__["_global_stats"] = (reduced[K * D:], N * world)
         return dz, reduced[:K * D].view(K, D), None, None, None
 

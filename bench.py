@@ -5,11 +5,11 @@
 
 One "step" = one pass of the hot path (vector_quantizer.py:29-58 and its autograd) over one batch of synthetic
 latents of the shape `_pre_vq_conv` hands to the quantizer:
-    vq_step_forward   codebook norms + distances + argmin + one-hot + gather + losses + perplexity (+ code sums)
-    vq_step_backward  dz and dE
+    vq_step_forward   codebook norms + distances + argmin + one-hot + gather + losses + perplexity
+    vq_backward       dz and dE
 Default workload = BASELINE.json configs[1]: RIR VQ-VAE quantizer from train_rir.py defaults at batch 256 ->
 z (256, 64, 201), N = 51 456 rows, K = 1024, D = 64, beta = 0.25, dense one-hot `encodings` emitted (the reference
-always returns it).  The step is captured once per input buffer in a CUDA graph and replayed (--no-graph: eager).
+always returns it).  N = 1: eager launches chained by programmatic dependent launch; N > 1: replayed from CUDA graphs.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   roofline          dominant kernel: algorithmic bytes|flops per launch / CUDA-event time per launch
@@ -23,8 +23,8 @@ Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   collective_check  N > 1: the NVLink exchange against NCCL on the same payload, and the step's dE against an
                     NCCL all-reduce of the local gradients
 Under torchrun (N > 1) every rank runs the same per-rank workload on its own rows (weak scaling); the only exchange
-is ONE sum all-reduce per step of [code sums | usage histogram | squared error], launched right behind the forward
-(nothing in it depends on upstream gradients) so that it runs concurrently with the backward's dz pass.
+is ONE sum all-reduce per step of the packed [dE | usage histogram | squared error] over NVLink peer memory
+(vq_dp_allreduce: device-side sequence numbers, so the whole step replays from a CUDA graph; --nccl for NCCL).
 """
 from __future__ import annotations
 
@@ -256,10 +256,9 @@ def main():
     ap.add_argument("--exact", action="store_true", help="CUDA-core exact path instead of tcgen05")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-screen", action="store_true", help="3xTF32 tensor kernels instead of screen + exact refine (VQ_FLAG_NO_SCREEN)")
-    ap.add_argument("--no-sums", action="store_true", help="scatter-add dE in the backward (flat / private kernel) instead of code sums in the forward")
-    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per input buffer")
+    ap.add_argument("--graph", action="store_true", help="N = 1: replay the step from CUDA graphs (default there: eager launches, which keep the PDL chain unbroken)")
+    ap.add_argument("--no-graph", action="store_true", help="N > 1: eager launches instead of CUDA graphs")
     ap.add_argument("--nccl", action="store_true", help="N > 1: NCCL all_reduce of [dE|hist|sse] after the backward instead of the NVLink exchange")
-    ap.add_argument("--no-overlap", action="store_true", help="N > 1: the backward waits for the exchange before it starts (no overlap with the dz pass)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the configs[3] corner points")
@@ -327,17 +326,17 @@ def main():
         s["e2"] = torch.empty(K, device=dev); s["ehi"] = torch.empty(K, D, device=dev); s["elo"] = torch.empty(K, D, device=dev)
         s["q"] = torch.empty(N, D, device=dev); s["idx"] = torch.empty(N, dtype=torch.int32, device=dev)
         s["onehot"] = torch.empty(N, K, device=dev) if onehot_on else None
-        s["stats"] = torch.zeros(K + 3, device=dev)                     # [hist (K) | sse | loss | perplexity]
-        s["dz"] = torch.empty(N, D, device=dev); s["dE"] = torch.zeros(K, D, device=dev)
+        # the packed step buffer [dE (K*D) | hist (K) | sse] + loss, perplexity: the forward writes the statistics and
+        # the backward the gradient straight into it, so data parallel all-reduces it as it stands
+        s["packed"] = torch.zeros(K * D + K + 3, device=dev)
+        s["stats"] = s["packed"][K * D:]                                # [hist (K) | sse | loss | perplexity]
+        s["dE"] = s["packed"][:K * D].view(K, D)
+        s["dz"] = torch.empty(N, D, device=dev)
         s["g_loss"] = torch.ones((), device=dev)
-        s["reduced"] = torch.zeros(K * D + K + 1, device=dev)           # data parallel: all-reduced [S | hist | sse]
-        s["packed"] = torch.zeros(K * D + K + 1, device=dev)            # data parallel without code sums: [dE | hist | sse]
+        s["reduced"] = torch.zeros(K * D + K + 1, device=dev)           # data parallel: the all-reduced packed buffer
         s["wsb"] = lib.vq_workspace_bytes(N, K, D, 0)
         s["ws"] = torch.empty(s["wsb"], dtype=torch.uint8, device=dev)
-        L.check(lib.vq_workspace_init(P(s["ws"]), s["wsb"], torch.cuda.current_stream().cuda_stream))
-        fwd = (L.FLAG_ONEHOT if onehot_on else 0) | (L.FLAG_EXACT if args.exact else 0) | (L.FLAG_NO_SCREEN if args.no_screen else 0)
-        s["sums"] = (not args.no_sums) and not args.nccl and bool(lib.vq_step_uses_code_sums(N, K, D, fwd | L.FLAG_CODE_SUMS))
-        s["fwd_flags"] = fwd | (L.FLAG_CODE_SUMS if s["sums"] else 0)
+        s["fwd_flags"] = (L.FLAG_ONEHOT if onehot_on else 0) | (L.FLAG_EXACT if args.exact else 0) | (L.FLAG_NO_SCREEN if args.no_screen else 0)
         return s
 
     nbuf = max(3, int(1.25 * L2_BYTES / (N * D * 4)) + 1)                # rotating inputs: set larger than L2
@@ -358,9 +357,8 @@ def main():
             exch = None
             collective = f"NCCL all_reduce (NVLink exchange unavailable on some rank{': ' + why if why else ''})"
         else:
-            collective = ("[code sums | hist | sse] over NVLink peer memory (vq_dp_exchange_sums, " + ("NVLS multimem.st" if exch.nvls else "P2P stores") + ", "
-                          + ("reduce-scatter + all-gather" if world >= 8 else "one step") + "), launched behind the forward, "
-                          + ("serialised before" if args.no_overlap else "concurrent with") + " the backward's dz pass")
+            collective = ("[dE | hist | sse] over NVLink peer memory (vq_dp_allreduce, " + ("NVLS multimem.st" if exch.nvls else "P2P stores") + ", "
+                          + ("reduce-scatter + all-gather" if world >= 8 else "one step") + ", device-side sequence numbers)")
     elif world > 1:
         collective = "NCCL all_reduce of [dE | hist | sse] after the backward"
     n_dE_scale = world
@@ -370,61 +368,66 @@ def main():
         N_, K_, D_ = s["N"], s["K"], s["D"]
         z, gq = s["zs"][i % s["nbuf"]], s["gs"][i % s["nbuf"]]
         sp = P(s["stats"])
-        L.check(lib.vq_step_forward(P(z), P(s["E"]), N_, K_, D_, BETA, s["fwd_flags"], P(s["e2"]), P(s["ehi"]), P(s["elo"]), P(s["q"]), P(s["idx"]),
+        # the prepare launch also zeroes the dE accumulator: no memset node between forward and backward (PDL chain intact)
+        L.check(lib.vq_step_forward(P(z), P(s["E"]), N_, K_, D_, BETA, s["fwd_flags"], P(s["e2"]), P(s["ehi"]), P(s["elo"]), P(s["dE"]), P(s["q"]), P(s["idx"]),
                                     P(s["onehot"]), sp, sp + 4 * K_, sp + 4 * (K_ + 1), sp + 4 * (K_ + 2), P(s["ws"]), s["wsb"], st))
         n_dE = N_ * n_dE_scale
-        if s["sums"]:
-            red = None
-            bfl = L.FLAG_TRAIN_VQ | L.FLAG_ZERO_DE | L.FLAG_CODE_SUMS
-            if exch is not None:
-                exch.exchange_sums(s["ws"], N_, K_, D_, s["stats"][:K_ + 1], s["reduced"], st)
-                red = s["reduced"]
-                if not args.no_overlap:
-                    bfl |= L.FLAG_OVERLAP_EXCHANGE
-            L.check(lib.vq_step_backward(P(gq), P(s["g_loss"]), P(z), P(s["E"]), P(s["idx"]), N_, N_, n_dE, K_, D_, BETA, bfl, P(s["dz"]), P(s["dE"]),
-                                         P(s["ws"]), s["wsb"], P(red), st))
-            return
-        if world == 1:
-            L.check(lib.vq_backward(P(gq), P(s["g_loss"]), P(z), P(s["E"]), P(s["idx"]), N_, N_, n_dE, K_, D_, BETA, L.FLAG_TRAIN_VQ | L.FLAG_ZERO_DE,
-                                    P(s["dz"]), P(s["dE"]), st))
-            return
-        # data parallel without code sums: backward into the packed buffer, then one all-reduce of [dE | hist | sse]
-        pk = s["packed"]
-        L.check(lib.vq_backward(P(gq), P(s["g_loss"]), P(z), P(s["E"]), P(s["idx"]), N_, N_, n_dE, K_, D_, BETA, L.FLAG_TRAIN_VQ | L.FLAG_ZERO_DE,
-                                P(s["dz"]), P(pk), st))
-        pk[K_ * D_:].copy_(s["stats"][:K_ + 1])
-        if exch is not None:
-            exch.allreduce(pk, s["reduced"], st)
-        else:
-            dist.all_reduce(pk)
+        L.check(lib.vq_backward(P(gq), P(s["g_loss"]), P(z), P(s["E"]), P(s["idx"]), N_, N_, n_dE, K_, D_, BETA, L.FLAG_TRAIN_VQ,
+                                P(s["dz"]), P(s["dE"]), st))
+        if exch is not None:            # data parallel: one sum all-reduce of [dE | hist | sse]
+            L.check(lib.vq_dp_allreduce(exch.ctx, P(s["packed"]), P(s["reduced"]), st))
+        elif world > 1:
+            dist.all_reduce(s["packed"][:K_ * D_ + K_ + 1])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    use_graph = not args.no_graph and not (world > 1 and exch is None)   # NCCL stays eager
+    # CUDA graphs take the host out of the loop (under data parallelism every rank's launch jitter otherwise turns into
+    # waiting inside the exchange).  Programmatic dependent launch does not cross graph boundaries, so one graph holds a
+    # whole round over the input buffers (nbuf steps); single-step graphs cover the remainder.  On one GPU the step is
+    # GPU-bound and eager launches keep the PDL chain unbroken: graphs only with --graph there.
+    use_graph = (args.graph or world > 1) and not args.no_graph and not (world > 1 and exch is None)   # NCCL stays eager
     cur = torch.cuda.current_stream()
 
     def build_runner(s):
-        """returns run(i): replays the captured step for buffer i (or launches it eagerly)"""
+        """returns run_steps(k): enqueues k consecutive steps starting at input buffer 0"""
+        nb = s["nbuf"]
         if not use_graph:
-            return lambda i: step(s, i, cur.cuda_stream), 0
-        for i in range(min(3, s["nbuf"])):          # warm every code path before capture (lazy attribute setting, descriptors)
+            def run_eager(k):
+                for i in range(k):
+                    step(s, i, cur.cuda_stream)
+            return run_eager, 0
+        for i in range(min(3, nb)):          # warm every code path before capture (lazy attribute setting, descriptors)
             step(s, i, cur.cuda_stream)
         torch.cuda.synchronize()
-        graphs = []
+        singles = []
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            for i in range(s["nbuf"]):
+            for i in range(nb):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=side):
                     step(s, i, torch.cuda.current_stream().cuda_stream)
-                graphs.append(g)
+                singles.append(g)
+            whole = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(whole, stream=side):
+                for i in range(nb):
+                    step(s, i, torch.cuda.current_stream().cuda_stream)
         cur.wait_stream(side)
         torch.cuda.synchronize()
-        return (lambda i: graphs[i % s["nbuf"]].replay()), len(graphs)
+
+        def run_graphs(k):
+            i = 0
+            while i < k:
+                if i % nb == 0 and k - i >= nb:
+                    whole.replay()
+                    i += nb
+                else:
+                    singles[i % nb].replay()
+                    i += 1
+        return run_graphs, len(singles) + 1
 
     run0, n_graphs = build_runner(S0)
     l0 = lib.vq_launch_count()
@@ -434,14 +437,12 @@ def main():
 
     sampler = ClockSampler(local_rank)
     # ---- device-resident throughput ------------------------------------------------------------------
-    for i in range(args.warmup):
-        run0(i)
+    run0(args.warmup)
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for i in range(args.steps):
-        run0(args.warmup + i)
+    run0(args.steps)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -505,8 +506,8 @@ def main():
         bound, peak, achieved, unit, per_launch = "hbm", peaks["hbm_gbs"], work["bytes"] / dur_s / 1e9, "GB/s", work["bytes"]
     tensor_path = bool(lib.vq_forward_uses_tensor_path(N, K, D, S0["fwd_flags"]))
     screen_used = tensor_path and not args.no_screen and K % 256 == 0 and D in (32, 64, 96, 128, 192, 256) and os.environ.get("B200VQ_SCREEN", "1")[:1] != "0"
-    kname = {"forward": ("vq_screen_kernel (fused forward: codebook norms, TF32 screen + exact refine, row epilogue, one-hot"
-                         + (", code sums" if S0["sums"] else "") + ")") if screen_used else "fused forward (argmin_tc2: 3xTF32 + row epilogue)"}.get(dom, dom)
+    kname = {"forward": "vq_screen_kernel (fused forward: TF32 screen + exact refine, row epilogue, one-hot)" if screen_used
+                        else "fused forward (argmin_tc2: 3xTF32 + row epilogue)"}.get(dom, dom)
     tr = traffic.get(args.workload, {})
     roofline = {"kernel": kname, "bound": bound, "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": unit,
                 "frac": round(achieved / peak, 4), "traffic": tr.get(dom),
@@ -530,7 +531,7 @@ def main():
         # the step's gradient: DP step vs NCCL all-reduce of the local gradients (same rows, same scale)
         step(S0, 0, cur.cuda_stream)
         torch.cuda.synchronize()
-        dE_dp = S0["dE"].clone()
+        dE_dp = S0["reduced"][:K * D].view(K, D).clone()
         stats_dp = S0["reduced"][K * D:].clone()
         loc = torch.zeros(K, D, device=dev)
         L.check(lib.vq_backward(P(S0["gs"][0]), P(S0["g_loss"]), P(S0["zs"][0]), P(S0["E"]), P(S0["idx"]), N, N, N * world, K, D, BETA,
@@ -648,7 +649,7 @@ def main():
                                     "fwd_tflops": round(fl / (t_f * 1e-6) / 1e12, 1), "frac_fwd": round(fl / (t_f * 1e-6) / 1e12 / tf32_sus, 3),
                                     "bwd_frac_hbm": round(bb / (t_b * 1e-6) / 1e9 / peaks["hbm_gbs"], 3),
                                     "frac": round(t_roof * 1e6 / (t_f + t_b), 3), "vectors_per_s": round(SWEEP_N / (t_step * 1e-6)),
-                                    "code_sums": s["sums"], "backward_path": "streaming (code sums)" if s["sums"] else ["flat", "", "private"][lib.vq_backward_path(SWEEP_N, k_, d_, 0)]})
+                                    "backward_path": ["flat", "", "private"][lib.vq_backward_path(SWEEP_N, k_, d_, 0)]})
             del s
 
     # ---- the drop-in nn.Module on the same workload (north star: the module is the deliverable) ------------------
@@ -711,8 +712,8 @@ def main():
                       "f32 (tcgen05 TF32 screening pass + exact fp32 refine of the candidates: indices bit-exact vs the fp32 oracle)")),
             "data": "synthetic", "config": config,
             "notes": {"path": "tcgen05" if tensor_path else "exact CUDA-core",
-                      "launch": (f"one CUDA graph per input buffer ({n_graphs} graphs), {launches_per_step} kernels per step" if use_graph else f"eager, {launches_per_step} kernels per step"),
-                      "codebook_gradient": "code sums accumulated in the forward's row epilogue, backward = dz stream + scale" if S0["sums"] else "scatter-add in the backward",
+                      "launch": (f"CUDA graphs (one per round over the {nbuf} input buffers + single-step graphs for the remainder), {launches_per_step} kernels per step"
+                                 if use_graph else f"eager launches chained by programmatic dependent launch, {launches_per_step} kernels per step"),
                       "l2": f"inputs rotate over {nbuf} z + {nbuf} g buffers ({2 * nbuf * N * D * 4 >> 20} MiB > 126 MiB L2)",
                       "collective": collective},
             "clocks": sampler.summary(),

@@ -51,13 +51,6 @@ extern "C" {
 #define VQ_FLAG_SCREEN     (1 << 10) /* forward: force the screen + exact-refine kernel wherever its shape constraints allow */
 #define VQ_FLAG_ZERO_DE    (1 << 5)  /* backward: dE = gradient instead of dE += gradient (a memset on `stream`, or plain stores on
                                         the bucket path, which writes every element exactly once) */
-#define VQ_FLAG_CODE_SUMS   (1 << 16) /* vq_step_forward: also accumulate the code sums S_k = sum_{n: idx_n = k} (E_k - z_n) (the codebook
-                                         gradient up to a scalar) in the workspace; vq_step_backward with the same flag then only
-                                         streams dz and scales S.  Applies where vq_step_uses_code_sums() says so */
-#define VQ_FLAG_OVERLAP_EXCHANGE (1 << 17) /* vq_step_backward with reduced_sums: the launch right before this one on the stream was
-                                         vq_dp_exchange_sums -- start the dz pass without waiting for it (ONLY then: with other
-                                         work in between the flag would let dz read inputs that are not complete yet) */
-#define VQ_FLAG_SELF_PREPARE (1 << 15) /* forward: set by vq_step_forward -- no prepare launch preceded this call (screen path only) */
 #define VQ_FLAG_BWD_FLAT    (1 << 12) /* backward: force the flat kernel (one 16-byte red.global.add per element of dE) */
 #define VQ_FLAG_BWD_PRIVATE (1 << 14) /* backward: force the shared-memory-private kernel where the shape allows */
 
@@ -116,17 +109,14 @@ int vq_forward(const float* z, const float* E, const float* e_norm2,
                float* loss, float* perplexity,
                void* workspace, size_t workspace_bytes, vq_stream_t stream);
 
-/* One entry for "prepare + forward" (the call a training step makes: Adam has just changed E).  The scratch buffers
- * e_norm2 (K), E_hi (K,D), E_lo (K,D) belong to the caller; E_hi / E_lo may be NULL for shapes the screen + refine
- * kernel takes (K % 256 == 0, D in {32,64,96,128,192,256}), where the whole forward is ONE launch: the kernel
- * computes |E_k|^2 itself and feeds the raw codebook to the tensor core (which drops the low 13 mantissa bits; the
- * candidate margin is widened accordingly, the refine stays exact, indices stay bit-identical to the oracle).
- * `workspace` (vq_workspace_bytes) must have been zeroed once with vq_workspace_init before its first use and must
- * not be shared between streams: it carries the call counter and the usage accumulators from call to call.
+/* One entry for "prepare + forward" (the call a training step makes: Adam has just changed E): vq_prepare_step followed
+ * by vq_forward, chained by programmatic dependent launch.  The scratch buffers e_norm2 (K), E_hi (K,D), E_lo (K,D)
+ * belong to the caller; E_lo may be NULL for shapes the screen + refine kernel takes (K % 256 == 0, D in
+ * {32,64,96,128,192,256}), both for shapes that run the exact path.  dE_zero: NULL, or the (K,D) accumulator the
+ * backward will add into -- zeroed by the prepare launch, so that vq_backward needs no VQ_FLAG_ZERO_DE memset.
  * Outputs and flags as for vq_forward (VQ_FLAG_STATE_READY is implied). */
-int vq_workspace_init(void* workspace, size_t workspace_bytes, vq_stream_t stream);
 int vq_step_forward(const float* z, const float* E, int64_t n_rows, int K, int D, float beta, int flags,
-                    float* e_norm2, float* E_hi, float* E_lo,
+                    float* e_norm2, float* E_hi, float* E_lo, float* dE_zero,
                     float* q_out, int32_t* idx, float* onehot, float* hist, float* sse,
                     float* loss, float* perplexity,
                     void* workspace, size_t workspace_bytes, vq_stream_t stream);
@@ -166,24 +156,9 @@ int vq_scatter_add_rows(const int32_t* idx, const float* g, float* dWt, int B, i
 int vq_jitter_apply(float* q, const int32_t* src, int64_t rows, int T, vq_stream_t stream);
 int vq_jitter_backward(float* g, const int32_t* src, int64_t rows, int T, vq_stream_t stream);
 
-/* -- the backward that pairs with vq_step_forward --------------------------------------------------------------- */
-/* 1 when vq_step_forward(flags | VQ_FLAG_CODE_SUMS) accumulates the code sums for this shape (screen + refine path,
- * q_out produced): the scatter-add of the codebook gradient then happens in the forward's row epilogue, where
- * E[idx] - z is in registers anyway, and vq_step_backward is a pure streaming pass. */
-int vq_step_uses_code_sums(int64_t n_rows, int K, int D, int flags);
-/* Same contract as vq_backward.  With VQ_FLAG_CODE_SUMS | VQ_FLAG_TRAIN_VQ (and the flag honoured by the forward, see
- * above): dz as usual, dE (+)= g_loss * 2 / (n_rows_dE * D) * S with S read from `workspace` (the one the forward
- * used) or -- data parallel -- from `reduced_sums`, the all-reduced S that vq_dp_exchange_sums (launched on the same
- * stream right before this call) writes: the dz pass then runs concurrently with the exchange.  Without the flag this
- * is vq_backward (workspace / reduced_sums unused). */
-int vq_step_backward(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx,
-                     int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags,
-                     float* dz, float* dE, const void* workspace, size_t workspace_bytes,
-                     const float* reduced_sums, vq_stream_t stream);
-
 /* -- data parallel: sum all-reduce of the packed step buffer over NVLink peer memory -------------------------------- */
 /* Rows shard across ranks with no data-path collective; per step ONE packed buffer
- *   [ code sums or dE (K*D) | usage histogram (K) | squared error (1) ]
+ *   [ dE (K*D) | usage histogram (K) | squared error (1) ]
  * is summed over the ranks, in rank order (bit-identical on every rank).  Transport: every rank owns two symmetric
  * RECEIVE buffers (alternating between calls) of vq_dp_recv_lines(world, n_floats) 16-byte lines, zero-initialised
  * and mapped into every peer (torch symmetric memory / CUDA IPC); data travels as lines {d0, seq, d1, seq}, so a line
@@ -202,11 +177,6 @@ int  vq_dp_create(const void* const* recv0, const void* const* recv1, void* mult
 void vq_dp_destroy(vq_dp_ctx* ctx);
 /* out[i] = sum over ranks of payload[i], i < n_floats (payload: written by earlier work on `stream`). */
 int  vq_dp_allreduce(vq_dp_ctx* ctx, const float* payload, float* out, vq_stream_t stream);
-/* The step's exchange: [code sums of the last vq_step_forward on `workspace` (K*D) | tail (n_tail floats: hist | sse)]
- * -> out.  Everything it carries comes out of the forward, so it is launched right behind vq_step_forward; pass
- * `out` as reduced_sums to the vq_step_backward that follows on the same stream. */
-int  vq_dp_exchange_sums(vq_dp_ctx* ctx, const void* workspace, size_t workspace_bytes, int64_t n_rows, int K, int D,
-                         const float* tail, int n_tail, float* out, vq_stream_t stream);
 /* Synchronises `stream`; calls completed and the error word (bit 0: a wait expired). */
 int  vq_dp_status(vq_dp_ctx* ctx, uint32_t* calls_done, uint32_t* error_word, vq_stream_t stream);
 /* Test hook: `world` emulated ranks on ONE GPU in a single cooperative launch (blockIdx.y = rank), `rounds` calls back

@@ -28,9 +28,8 @@ def _dev():
 
 
 def _forward(lib, z, E, flags, want_onehot=False, step=False):
-    """step=False: vq_prepare_codebook + vq_forward.  step=True: vq_step_forward (ONE launch on the screen path: norms
-    in-kernel, raw codebook under the tensor map, usage counts ping-pong in the workspace) -- called three times on the
-    same workspace, every call must give the same outputs."""
+    """step=False: vq_prepare_codebook + vq_forward.  step=True: vq_step_forward (prepare launch with the state / dE reset
+    + forward behind one entry) -- called three times on the same workspace, every call must give the same outputs."""
     dev = z.device
     N, D = z.shape
     K = E.shape[0]
@@ -50,16 +49,17 @@ def _forward(lib, z, E, flags, want_onehot=False, step=False):
         assert rc == 0, lib.vq_last_error()
         torch.cuda.synchronize()
         return dict(q=q, idx=idx, onehot=oh, hist=stats[:K], sse=stats[K], loss=stats[K + 1], perplexity=stats[K + 2], e_norm2=e2)
-    assert lib.vq_workspace_init(ws.data_ptr(), wsb, st) == 0
     prev = None
+    dEz = torch.full((K, D), 3.0, device=dev)
     for call in range(3):
-        stats.fill_(-5.0); idx.fill_(-1)
-        rc = lib.vq_step_forward(z.data_ptr(), E.data_ptr(), N, K, D, BETA, fl, e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(),
+        stats.fill_(-5.0); idx.fill_(-1); dEz.fill_(3.0)
+        rc = lib.vq_step_forward(z.data_ptr(), E.data_ptr(), N, K, D, BETA, fl, e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(), dEz.data_ptr(),
                                  q.data_ptr(), idx.data_ptr(), None if oh is None else oh.data_ptr(), sp, sp + 4 * K, sp + 4 * (K + 1),
                                  sp + 4 * (K + 2), ws.data_ptr(), wsb, st)
         assert rc == 0, lib.vq_last_error()
         torch.cuda.synchronize()
         cur = (idx.clone(), stats.clone())
+        assert float(dEz.abs().max()) == 0.0                 # the prepare launch zeroed the accumulator
         if prev is not None:
             assert torch.equal(prev[0], cur[0]) and torch.equal(prev[1], cur[1]), f"vq_step_forward call {call} differs from call {call - 1}"
         prev = cur
@@ -94,7 +94,7 @@ def test_full_size_properties(lib, name, N, D, K, onehot):
     z = torch.randn(N, D, device=dev)
     t = _forward(lib, z, E, 0, want_onehot=onehot)           # tensor path, fused
     assert lib.vq_forward_uses_tensor_path(N, K, D, 0) == 1
-    ts = _forward(lib, z, E, 0, want_onehot=onehot, step=True)   # the same through vq_step_forward (one launch, no prepare)
+    ts = _forward(lib, z, E, 0, want_onehot=onehot, step=True)   # the same through vq_step_forward
     assert torch.equal(ts["idx"], t["idx"]) and torch.equal(ts["hist"], t["hist"]) and torch.equal(ts["q"], t["q"])
     assert torch.equal(ts["e_norm2"], t["e_norm2"])
     assert abs(float(ts["loss"]) - float(t["loss"])) <= 1e-6 * float(t["loss"]) and abs(float(ts["perplexity"]) - float(t["perplexity"])) <= 1e-6 * float(t["perplexity"])
@@ -235,7 +235,7 @@ def test_screen_kernel_adversarial_inputs(lib, kind, D, K):
     ref = _oracle_idx(z, E)
     assert torch.equal(out["idx"].cpu(), ref), f"{kind} D={D} K={K}: {(out['idx'].cpu() != ref).sum().item()} rows differ from the oracle"
     assert float(out["hist"].sum()) == N
-    # the self-prepared launch (raw codebook truncated by the tensor core, wider margin) must be just as exact
+    # the same through the one-call step entry
     out_s = _forward(lib, z, E, 1 << 10, step=True)
     assert torch.equal(out_s["idx"].cpu(), ref), f"{kind} D={D} K={K} (vq_step_forward): {(out_s['idx'].cpu() != ref).sum().item()} rows differ"
     assert torch.equal(out_s["hist"], out["hist"])

@@ -156,3 +156,17 @@ def test_jitter_oracle_pinned():
     jit = import_module("acoustic_locating_vq-vae_b200.jitter")
     np.random.seed(int(g["seed"]))
     assert np.array_equal(jit.draw_source_columns(int(g["T"]), float(g["p"])), g["src"].astype(np.int32))
+
+
+def test_jitter_single_column_raises_like_the_reference():
+    """jitter.py:57,68: with T == 1 a drawn replacement indexes column 1 of a one-column tensor -> IndexError; the host-side
+    decision draw must fail the same way (and not hand the kernel a source column outside the row)."""
+    import numpy as np
+    from importlib import import_module
+    jit = import_module("acoustic_locating_vq-vae_b200.jitter")
+    np.random.seed(0)
+    with pytest.raises(IndexError):
+        for _ in range(200):                       # the reference replaces with probability 1 - p (jitter.py:50)
+            jit.draw_source_columns(1, 0.001)
+    np.random.seed(0)
+    assert jit.draw_source_columns(1, 1.0).tolist() == [0]      # no replacement drawn: untouched, like the reference

@@ -1,5 +1,6 @@
-"""torchrun --nproc-per-node N tools/test_allreduce_multigpu.py : vq_allreduce_sum vs NCCL on N GPUs."""
-import os, sys, time
+"""torchrun --nproc-per-node N tools/mgpu_allreduce.py : the NVLink exchange (vq_dp_allreduce) against NCCL on N GPUs.
+Values (vs dist.all_reduce), bit-identity across ranks, replay from a CUDA graph (device-side sequence numbers), time."""
+import os, sys
 import torch, torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -10,25 +11,36 @@ rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(
 torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
 dist.init_process_group("nccl", device_id=dev)
 n = 1024 * 64 + 1024 + 1
-ar = (par.SymmetricAllReduce if "--pull" in sys.argv else par.PushAllReduce)(n, dev)
-st = torch.cuda.current_stream().cuda_stream
+ex = par.PeerExchange(n, dev)
+cur = torch.cuda.current_stream()
 ok = True
+pay = torch.empty(n, device=dev); out = torch.empty(n, device=dev)
 for step in range(12):
     torch.manual_seed(100 * step + rank)
-    x = torch.randn(n, device=dev)
-    ar.payload().copy_(x)
-    ref = x.clone(); dist.all_reduce(ref)
-    out = ar.reduce(st)
+    pay.copy_(torch.randn(n, device=dev))
+    ref = pay.clone(); dist.all_reduce(ref)
+    ex.allreduce(pay, out, cur.cuda_stream)
     torch.cuda.synchronize()
-    # rank-order sum is deterministic and identical on all ranks; NCCL may use another order
-    err = float((out - ref).abs().max() / ref.abs().max())
+    err = float((out - ref).abs().max() / ref.abs().max())      # rank-order sum vs NCCL's order
     gathered = [torch.empty_like(out) for _ in range(world)]
     dist.all_gather(gathered, out)
     same = all(torch.equal(gathered[0], g) for g in gathered)
     ok = ok and err < 1e-6 and same
     if rank == 0: print(f"step {step}: max rel err vs NCCL {err:.2e}, bit-identical across ranks: {same}")
-# timing
-for name, fn in (("vq_allreduce_sum", lambda: ar.reduce(st)), ("nccl all_reduce", lambda: dist.all_reduce(ar.out))):
+# the same call replayed from a CUDA graph: sequence numbers and buffer parity advance on the device
+g = torch.cuda.CUDAGraph()
+side = torch.cuda.Stream(device=dev); side.wait_stream(cur)
+with torch.cuda.stream(side):
+    with torch.cuda.graph(g, stream=side):
+        ex.allreduce(pay, out, torch.cuda.current_stream().cuda_stream)
+cur.wait_stream(side)
+for rep in range(5):
+    pay.copy_(torch.randn(n, device=dev)); ref = pay.clone(); dist.all_reduce(ref)
+    g.replay(); torch.cuda.synchronize()
+    err = float((out - ref).abs().max() / ref.abs().max())
+    ok = ok and err < 1e-6
+    if rank == 0: print(f"graph replay {rep}: max rel err vs NCCL {err:.2e}")
+for name, fn in (("vq_dp_allreduce", lambda: ex.allreduce(pay, out, cur.cuda_stream)), ("vq_dp_allreduce (graph)", g.replay), ("nccl all_reduce", lambda: dist.all_reduce(out))):
     for _ in range(20): fn()
     torch.cuda.synchronize(); dist.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -36,5 +48,8 @@ for name, fn in (("vq_allreduce_sum", lambda: ar.reduce(st)), ("nccl all_reduce"
     for _ in range(200): fn()
     b.record(); torch.cuda.synchronize()
     if rank == 0: print(f"{name}: {a.elapsed_time(b) / 200 * 1e3:.1f} us per call ({n * 4 / 1024:.0f} KiB, {world} ranks)")
-if rank == 0: print("ALLREDUCE TEST", "PASSED" if ok else "FAILED", "| nvls:", getattr(ar, "nvls", None))
+calls, err = ex.status(cur.cuda_stream)
+ok = ok and err == 0
+if rank == 0: print("ALLREDUCE TEST", "PASSED" if ok else "FAILED", "| nvls:", ex.nvls, "| calls:", calls, "| error word:", err)
+ex.close()
 dist.destroy_process_group()

@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node N tools/test_module_dp_multigpu.py : the nn.Module under data parallelism on N GPUs.
+"""torchrun --nproc-per-node N tools/mgpu_module_dp.py : the nn.Module under data parallelism on N GPUs.
 Every rank quantizes its batch shard; dE / global loss / perplexity must equal the single-process oracle on the
 full batch, and dE must be bit-identical on every rank."""
 import os, sys
@@ -40,11 +40,11 @@ for exact in (True, False):
     gathered = [torch.empty_like(dE) for _ in range(world)]
     dist.all_gather(gathered, dE)
     same = all(torch.equal(gathered[0], t) for t in gathered)
-    used_push = vq._push_ar not in (None, False)
+    used_push = vq._peer_ex not in (None, False)
     good = e1 < 1e-5 and e2 < 1e-6 and e3 < 1e-5 and e4 < 1e-5 and same
     ok = ok and good
     if rank == 0:
         print(f"exact={exact}: dE rel err {e1:.1e}, dz abs err {e2:.1e}, global loss rel err {e3:.1e}, perplexity rel err {e4:.1e}, "
-              f"dE bit-identical across {world} ranks: {same}, push all-reduce used: {used_push} -> {'ok' if good else 'FAIL'}")
+              f"dE bit-identical across {world} ranks: {same}, NVLink exchange used: {used_push} -> {'ok' if good else 'FAIL'}")
 if rank == 0: print("MODULE DP TEST", "PASSED" if ok else "FAILED")
 dist.destroy_process_group()
