@@ -700,7 +700,17 @@ int vq_backward(const float* g_q, const float* g_loss, const float* z, const flo
         return nc == 2 ? run_private<false, 2>(g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, K, D, beta, dz, dE, st)
                        : run_private<false, 1>(g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, K, D, beta, dz, dE, st);
     }
-    if (dz == nullptr) return fail(VQ_ERR_ARG, "vq_backward: dz == NULL needs the private path (shape / alignment rule it out here)");
+    if (dz == nullptr) {   // codebook gradient only
+        const long long n_e = N * (vec ? D / 4 : D);
+        long long gb = (n_e + 255) / 256;
+        if (gb > kNumSMs * 32) gb = kNumSMs * 32;
+        ProfScope prof(KID_BACKWARD, st);
+        const cudaError_t e = vec ? launch_pdl(backward_dE_kernel<4>, dim3(static_cast<unsigned>(gb)), dim3(256), 0, st, g_loss, z, E, idx, N, denom_dE, D, dE)
+                                  : launch_pdl(backward_dE_kernel<1>, dim3(static_cast<unsigned>(gb)), dim3(256), 0, st, g_loss, z, E, idx, N, denom_dE, D, dE);
+        if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of backward_dE_kernel failed: %s", cudaGetErrorString(e));
+        LAUNCH_CHECK("backward_dE_kernel");
+        return VQ_OK;
+    }
     const long long n_el = N * (vec ? D / 4 : D);
     long long g = (n_el + 255) / 256;
     if (g > kNumSMs * 32) g = kNumSMs * 32;
@@ -800,7 +810,7 @@ int vq_dp_allreduce(vq_dp_ctx* c, const float* payload, float* out, vq_stream_t 
     const int cap = sm_count();
     if (blocks > cap) blocks = cap;                          // no CTA waits for another CTA of this grid: no residency requirement
     ProfScope prof(KID_ALLREDUCE, st);
-    const cudaError_t e = launch_pdl(dp_allreduce_kernel<true>, dim3(static_cast<unsigned>(blocks)), dim3(DP_THREADS), 0, st, c->dev, payload, out);
+    const cudaError_t e = launch_pdl(dp_allreduce_kernel, dim3(static_cast<unsigned>(blocks)), dim3(DP_THREADS), 0, st, c->dev, payload, out);
     if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of dp_allreduce_kernel failed: %s", cudaGetErrorString(e));
     LAUNCH_CHECK("dp_allreduce_kernel");
     return VQ_OK;
@@ -843,14 +853,14 @@ int vq_dp_emulate(int world, int two_step, int64_t n_floats, const float* const*
             cudaStreamSynchronize(st) != cudaSuccess) { rc = fail(VQ_ERR_CUDA, "vq_dp_emulate: setup copies failed"); break; }
         long long blocks = (L + DP_THREADS - 1) / DP_THREADS;
         int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_emulate_kernel<true>, DP_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_emulate_kernel, DP_THREADS, 0);
         const long long cap = static_cast<long long>(per_sm < 1 ? 1 : per_sm) * sm_count() / world;   // all ranks resident at once
         if (blocks > cap) blocks = cap;
         if (blocks < 1) { rc = fail(VQ_ERR_ARG, "vq_dp_emulate: world too large for a cooperative launch"); break; }
         const DpCtxDev* a0 = d_ctx; const float* const* a1 = d_pay; float* const* a2 = d_out;
         void* args[] = {&a0, &a1, &a2};
         for (int i = 0; i < rounds && rc == VQ_OK; ++i) {
-            const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(dp_emulate_kernel<true>),
+            const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(dp_emulate_kernel),
                                                               dim3(static_cast<unsigned>(blocks), static_cast<unsigned>(world)), dim3(DP_THREADS), args, 0, st);
             if (e != cudaSuccess) rc = fail(VQ_ERR_CUDA, "vq_dp_emulate: cooperative launch failed: %s", cudaGetErrorString(e));
             else g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -73,7 +73,7 @@ __device__ __forceinline__ void dp_store_all(const DpCtxDev& c, int which, long 
     if (c.mc[which] != nullptr) {
         multimem_st_v4(reinterpret_cast<uint4*>(c.mc[which]) + off, line);
     } else {
-        for (int p = 0; p < c.world; ++p) {
+        for (int p = 1; p < c.world; ++p) {             // not to ourselves: the reducer takes our own lines from the local payload
             const int dst = (c.rank + p) % c.world;     // spread the ranks' first targets over the links
             st_volatile_v4(reinterpret_cast<uint4*>(c.recv[which][dst]) + off, line);
         }
@@ -85,7 +85,7 @@ __device__ __forceinline__ void dp_push_line(const DpCtxDev& c, const DpCall& k,
     const uint4 line = make_uint4(__float_as_uint(d0), k.seq, __float_as_uint(d1), k.seq);
     if (c.two_step) {
         const long long j = i / c.S, l = i - j * c.S;
-        st_volatile_v4(reinterpret_cast<uint4*>(c.recv[k.which][j]) + static_cast<long long>(c.rank) * c.S + l, line);
+        if (j != c.rank) st_volatile_v4(reinterpret_cast<uint4*>(c.recv[k.which][j]) + static_cast<long long>(c.rank) * c.S + l, line);
     } else {
         dp_store_all(c, k.which, static_cast<long long>(c.rank) * c.L + i, line);
     }
@@ -112,21 +112,28 @@ struct DpWaiter {
 };
 
 // one step: sum our `world` slots in rank order as the lines arrive
-__device__ __forceinline__ void dp_collect_one_step(const DpCtxDev& c, const DpCall& k, const DpWaiter& w, float* __restrict__ out,
-                                                    long long first, long long stride) {
+__device__ __forceinline__ void dp_collect_one_step(const DpCtxDev& c, const DpCall& k, const DpWaiter& w, const float* __restrict__ payload,
+                                                    float* __restrict__ out, long long first, long long stride) {
     const uint4* mine = reinterpret_cast<const uint4*>(c.recv[k.which][c.rank]);
     for (long long i = first; i < c.L; i += stride) {
         uint4 v[DP_MAX_RANKS];
 #pragma unroll
         for (int p = 0; p < DP_MAX_RANKS; ++p)
-            if (p < c.world) v[p] = ld_volatile_v4(mine + static_cast<long long>(p) * c.L + i);
+            if (p < c.world && p != c.rank) v[p] = ld_volatile_v4(mine + static_cast<long long>(p) * c.L + i);
+        // our own contribution never travels: it is read where it lies, at its place in the rank order
+        const float own0 = __ldcg(payload + 2 * i), own1 = (2 * i + 1 < c.n) ? __ldcg(payload + 2 * i + 1) : 0.0f;
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
         for (int p = 0; p < DP_MAX_RANKS; ++p) {
             if (p < c.world) {
-                w.wait(mine + static_cast<long long>(p) * c.L + i, k.seq, v[p]);
-                a0 += __uint_as_float(v[p].x);
-                a1 += __uint_as_float(v[p].z);
+                if (p == c.rank) {
+                    a0 += own0;
+                    a1 += own1;
+                } else {
+                    w.wait(mine + static_cast<long long>(p) * c.L + i, k.seq, v[p]);
+                    a0 += __uint_as_float(v[p].x);
+                    a1 += __uint_as_float(v[p].z);
+                }
             }
         }
         out[2 * i] = a0;
@@ -135,27 +142,37 @@ __device__ __forceinline__ void dp_collect_one_step(const DpCtxDev& c, const DpC
 }
 
 // two steps, (2): reduce our own slice in rank order and broadcast it into region B of every rank
-__device__ __forceinline__ void dp_reduce_bcast(const DpCtxDev& c, const DpCall& k, const DpWaiter& w, long long first, long long stride) {
+__device__ __forceinline__ void dp_reduce_bcast(const DpCtxDev& c, const DpCall& k, const DpWaiter& w, const float* __restrict__ payload,
+                                                float* __restrict__ out, long long first, long long stride) {
     const uint4* mine = reinterpret_cast<const uint4*>(c.recv[k.which][c.rank]);
     const long long own = min(c.S, c.L - static_cast<long long>(c.rank) * c.S);
     const long long b_off = static_cast<long long>(c.world) * c.S + static_cast<long long>(c.rank) * c.S;
     for (long long l = first; l < own; l += stride) {
+        const long long gi = static_cast<long long>(c.rank) * c.S + l;        // this line in the payload: our own share stays local
+        const float own0 = __ldcg(payload + 2 * gi), own1 = (2 * gi + 1 < c.n) ? __ldcg(payload + 2 * gi + 1) : 0.0f;
         float a0 = 0.f, a1 = 0.f;
         for (int p0 = 0; p0 < c.world; p0 += 8) {           // 8 slots requested together, summed in rank order
             uint4 v[8];
 #pragma unroll
             for (int p = 0; p < 8; ++p)
-                if (p0 + p < c.world) v[p] = ld_volatile_v4(mine + static_cast<long long>(p0 + p) * c.S + l);
+                if (p0 + p < c.world && p0 + p != c.rank) v[p] = ld_volatile_v4(mine + static_cast<long long>(p0 + p) * c.S + l);
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
                 if (p0 + p < c.world) {
-                    w.wait(mine + static_cast<long long>(p0 + p) * c.S + l, k.seq, v[p]);
-                    a0 += __uint_as_float(v[p].x);
-                    a1 += __uint_as_float(v[p].z);
+                    if (p0 + p == c.rank) {
+                        a0 += own0;
+                        a1 += own1;
+                    } else {
+                        w.wait(mine + static_cast<long long>(p0 + p) * c.S + l, k.seq, v[p]);
+                        a0 += __uint_as_float(v[p].x);
+                        a1 += __uint_as_float(v[p].z);
+                    }
                 }
             }
         }
         dp_store_all(c, k.which, b_off + l, make_uint4(__float_as_uint(a0), k.seq, __float_as_uint(a1), k.seq));
+        out[2 * gi] = a0;                                   // our own slice needs no second hop
+        if (2 * gi + 1 < c.n) out[2 * gi + 1] = a1;
     }
 }
 
@@ -163,17 +180,18 @@ __device__ __forceinline__ void dp_reduce_bcast(const DpCtxDev& c, const DpCall&
 __device__ __forceinline__ void dp_gather(const DpCtxDev& c, const DpCall& k, const DpWaiter& w, float* __restrict__ out, long long first,
                                           long long stride) {
     const uint4* gathered = reinterpret_cast<const uint4*>(c.recv[k.which][c.rank]) + static_cast<long long>(c.world) * c.S;
+    const long long own_lo = static_cast<long long>(c.rank) * c.S, own_hi = own_lo + c.S;   // reduced by ourselves: already in `out`
     for (long long i0 = first; i0 < c.L; i0 += 4 * stride) {
         uint4 v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const long long i = i0 + u * stride;
-            if (i < c.L) v[u] = ld_volatile_v4(gathered + i);
+            if (i < c.L && (i < own_lo || i >= own_hi)) v[u] = ld_volatile_v4(gathered + i);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const long long i = i0 + u * stride;
-            if (i < c.L) {
+            if (i < c.L && (i < own_lo || i >= own_hi)) {
                 w.wait(gathered + i, k.seq, v[u]);
                 out[2 * i] = __uint_as_float(v[u].x);
                 if (2 * i + 1 < c.n) out[2 * i + 1] = __uint_as_float(v[u].z);
@@ -183,7 +201,6 @@ __device__ __forceinline__ void dp_gather(const DpCtxDev& c, const DpCall& k, co
 }
 
 // body shared by the production kernel (one rank per launch) and the single-GPU emulation (one rank per blockIdx.y)
-template <bool PUSH>
 __device__ __forceinline__ void dp_allreduce_body(const DpCtxDev& c, const float* __restrict__ payload, float* __restrict__ out, int* s_abort) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     const long long first = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -191,18 +208,16 @@ __device__ __forceinline__ void dp_allreduce_body(const DpCtxDev& c, const float
     __syncthreads();
     const DpCall k = dp_begin(c);
     const DpWaiter w{c, s_abort};
-    if (PUSH) {
-        for (long long i = first; i < c.L; i += stride) {
-            const float d0 = __ldcg(payload + 2 * i);
-            const float d1 = (2 * i + 1 < c.n) ? __ldcg(payload + 2 * i + 1) : 0.0f;
-            dp_push_line(c, k, i, d0, d1);
-        }
+    for (long long i = first; i < c.L; i += stride) {
+        const float d0 = __ldcg(payload + 2 * i);
+        const float d1 = (2 * i + 1 < c.n) ? __ldcg(payload + 2 * i + 1) : 0.0f;
+        dp_push_line(c, k, i, d0, d1);
     }
     if (c.two_step) {
-        dp_reduce_bcast(c, k, w, first, stride);
+        dp_reduce_bcast(c, k, w, payload, out, first, stride);
         dp_gather(c, k, w, out, first, stride);
     } else {
-        dp_collect_one_step(c, k, w, out, first, stride);
+        dp_collect_one_step(c, k, w, payload, out, first, stride);
     }
 }
 
@@ -219,36 +234,25 @@ __device__ __forceinline__ void dp_end(const DpCtxDev& c) {
     }
 }
 
-// PUSH = true : complete all-reduce of `payload` (written by the previous kernel of the stream)
-// PUSH = false: the first hop was done by the producer of the data; this kernel may start polling while the producer
-//               still runs and only orders itself behind it at its very end, which keeps "previous kernel complete"
-//               transitive along the stream for whatever follows (building block, not used by the library today).
-template <bool PUSH>
+// complete sum all-reduce of `payload` (written by the previous kernel of the stream)
 __global__ void __launch_bounds__(DP_THREADS) dp_allreduce_kernel(const __grid_constant__ DpCtxDev c, const float* __restrict__ payload,
                                                                   float* __restrict__ out) {
     __shared__ int s_abort;
-    if (PUSH) {
-        pdl_wait_prior_grids();      // the local contribution is complete ...
-        pdl_launch_dependents();     // ... and whoever is launched behind us may rely on that without waiting for US
-    }
-    dp_allreduce_body<PUSH>(c, payload, out, &s_abort);
-    if (!PUSH) {
-        pdl_wait_prior_grids();
-        pdl_launch_dependents();
-    }
+    pdl_wait_prior_grids();      // the local contribution is complete
+    pdl_launch_dependents();
+    dp_allreduce_body(c, payload, out, &s_abort);
     dp_end(c);
 }
 
 // single-GPU emulation of `world` ranks (tests): blockIdx.y is the rank, launched cooperatively so that all ranks'
 // CTAs are resident at once -- the ranks wait for each other's lines exactly as they do across GPUs.
-template <bool PUSH>
 __global__ void __launch_bounds__(DP_THREADS) dp_emulate_kernel(const DpCtxDev* __restrict__ ctxs, const float* const* __restrict__ payloads,
                                                                 float* const* __restrict__ outs) {
     __shared__ int s_abort;
     __shared__ DpCtxDev c;
     if (threadIdx.x == 0) c = ctxs[blockIdx.y];
     __syncthreads();
-    dp_allreduce_body<PUSH>(c, payloads != nullptr ? payloads[blockIdx.y] : nullptr, outs[blockIdx.y], &s_abort);
+    dp_allreduce_body(c, payloads[blockIdx.y], outs[blockIdx.y], &s_abort);
     dp_end(c);
 }
 

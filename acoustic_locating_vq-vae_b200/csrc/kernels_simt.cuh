@@ -419,6 +419,34 @@ __global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__
     }
 }
 
+// codebook gradient only (vq_backward with dz == NULL): dE[idx] += ce * (E[idx] - z)
+template <int VEC>
+__global__ void __launch_bounds__(256) backward_dE_kernel(const float* __restrict__ g_loss, const float* __restrict__ z,
+                                                          const float* __restrict__ E, const int* __restrict__ idx, long long N,
+                                                          float denom_dE, int D, float* __restrict__ dE) {
+    pdl_launch_dependents();
+    pdl_wait_prior_grids();
+    const float gl = g_loss != nullptr ? __ldg(g_loss) : 1.0f;
+    const float ce = gl * 2.0f / denom_dE;
+    const int DV = D / VEC;
+    const long long n_el = N * DV;
+    const long long stride = static_cast<long long>(gridDim.x) * 256;
+    for (long long e = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; e < n_el; e += stride) {
+        const long long r = e / DV;
+        const int c = static_cast<int>(e - r * DV);
+        const int code = __ldg(idx + r);
+        if (VEC == 4) {
+            const float4 zv = __ldg(reinterpret_cast<const float4*>(z) + e);
+            const float4 ev = __ldg(reinterpret_cast<const float4*>(E + static_cast<size_t>(code) * D) + c);
+            float4 a;
+            a.x = ce * (ev.x - zv.x); a.y = ce * (ev.y - zv.y); a.z = ce * (ev.z - zv.z); a.w = ce * (ev.w - zv.w);
+            atomicAdd(reinterpret_cast<float4*>(dE + static_cast<size_t>(code) * D) + c, a);
+        } else {
+            atomicAdd(dE + static_cast<size_t>(code) * D + c, ce * (__ldg(E + static_cast<size_t>(code) * D + c) - z[e]));
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // SURVEY 8(f) rank 1 -- the consumer of the dense one-hot as an index gather.
 // LocationModule.fc_1 (location_model.py:10,21) multiplies flatten(one_hot(B, T, K)) by a (O, T*K) weight: a

@@ -60,7 +60,7 @@ class _VQFunction(torch.autograd.Function):
     followed under data parallelism by ONE sum all-reduce of the packed [dE | usage histogram | squared error]."""
 
     @staticmethod
-    def forward(ctx, inputs, weight, module, flags, want_onehot):
+    def forward(ctx, inputs, weight, module, flags, want_onehot, pack):
         lib = _lib.load()
         K, D = weight.shape
         flat = inputs.view(-1, D)                     # vector_quantizer.py:32 (raises like the reference)
@@ -74,9 +74,8 @@ class _VQFunction(torch.autograd.Function):
         e_norm2, e_hi, e_lo = bufs.codebook(K, D, dev)
         q_out = torch.empty_like(inputs)
         idx = torch.empty(N, dtype=torch.int32, device=dev)
-        dp = module.process_group is not None or module.data_parallel
         packed = None
-        if dp and bool(module._train_vq) and weight.requires_grad and torch.is_grad_enabled():
+        if pack:
             # data parallel: the forward writes hist | sse straight behind the slot of dE in the packed step buffer
             packed = torch.empty(K * D + K + 3, dtype=torch.float32, device=dev)
             scal = packed[K * D:]
@@ -140,7 +139,7 @@ class _VQFunction(torch.autograd.Function):
             if need_dz:
                 check(lib.vq_backward(_ptr(g_q), _ptr(g_loss), _ptr(inputs), _ptr(w), _ptr(idx), N, n_dz, n_dE, K, D, beta, 0,
                                       _ptr(dz), None, st))
-            return dz, None, None, None, None
+            return dz, None, None, None, None, None
         packed = ctx.packed
         if world == 1 or packed is None:
             dE = torch.empty(K, D, dtype=torch.float32, device=dev)
@@ -149,19 +148,19 @@ class _VQFunction(torch.autograd.Function):
             if world > 1:       # the codebook was frozen when the forward ran: nothing was packed -- plain all-reduce of dE
                 import torch.distributed as dist
                 dist.all_reduce(dE, group=pg)
-            return dz, dE, None, None, None
+            return dz, dE, None, None, None, None
         # data parallel: dE lands in front of the statistics the forward left in the packed buffer; ONE all-reduce
-        check(lib.vq_backward(_ptr(g_q), _ptr(g_loss), _ptr(inputs), _ptr(w), _ptr(idx), N, n_dz, n_dE, K, D, beta,
-                              FLAG_TRAIN_VQ | FLAG_ZERO_DE, _ptr(dz), _ptr(packed), st))
         n = K * D + K + 1
         ex = module._peer_exchange(K, D, dev, pg)
+        check(lib.vq_backward(_ptr(g_q), _ptr(g_loss), _ptr(inputs), _ptr(w), _ptr(idx), N, n_dz, n_dE, K, D, beta,
+                              FLAG_TRAIN_VQ | FLAG_ZERO_DE, _ptr(dz), _ptr(packed), st))
         if ex is not None:
             reduced = torch.empty(n, dtype=torch.float32, device=dev)      # fresh: autograd may keep dE as the gradient
             ex.allreduce(packed[:n], reduced, st)
         else:
             reduced = parallel.all_reduce_packed(packed[:n], pg)
         module.__dict__["_global_stats"] = (reduced[K * D:], N * world)
-        return dz, reduced[:K * D].view(K, D), None, None, None
+        return dz, reduced[:K * D].view(K, D), None, None, None, None
 
 
 class VectorQuantizer(nn.Module):
@@ -239,13 +238,17 @@ class VectorQuantizer(nn.Module):
             raise RuntimeError("view size is not compatible with input tensor's size and stride "
                                "(b200vq needs a contiguous input, like the reference's .view)")
         flags = FLAG_EXACT if self.exact else 0
+        # data parallel with a training codebook: the forward writes its statistics straight into the packed step buffer
+        # (decided here: grad mode is off inside autograd.Function.forward)
+        pack = bool((self.process_group is not None or self.data_parallel) and self._train_vq and weight.requires_grad
+                    and torch.is_grad_enabled())
         if inputs.device.index != torch.cuda.current_device():      # the C ABI launches on the current device
             with torch.cuda.device(inputs.device):
                 loss, quantized, perplexity, encodings, idx = _VQFunction.apply(
-                    inputs, weight, self, flags, bool(self.return_encodings))
+                    inputs, weight, self, flags, bool(self.return_encodings), pack)
         else:
             loss, quantized, perplexity, encodings, idx = _VQFunction.apply(
-                inputs, weight, self, flags, bool(self.return_encodings))
+                inputs, weight, self, flags, bool(self.return_encodings), pack)
         self.__dict__["last_indices"] = idx
         return loss, quantized, perplexity, encodings
 

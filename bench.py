@@ -256,8 +256,8 @@ def main():
     ap.add_argument("--exact", action="store_true", help="CUDA-core exact path instead of tcgen05")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-screen", action="store_true", help="3xTF32 tensor kernels instead of screen + exact refine (VQ_FLAG_NO_SCREEN)")
-    ap.add_argument("--graph", action="store_true", help="N = 1: replay the step from CUDA graphs (default there: eager launches, which keep the PDL chain unbroken)")
-    ap.add_argument("--no-graph", action="store_true", help="N > 1: eager launches instead of CUDA graphs")
+    ap.add_argument("--graph", action="store_true", help="N = 1: replay the step from CUDA graphs (default there: eager launches chained by programmatic dependent launch)")
+    ap.add_argument("--no-graph", action="store_true", help="N > 1: eager launches (default there: CUDA graphs, which keep the ranks' launch jitter out of the exchange)")
     ap.add_argument("--nccl", action="store_true", help="N > 1: NCCL all_reduce of [dE|hist|sse] after the backward instead of the NVLink exchange")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -374,7 +374,7 @@ def main():
         n_dE = N_ * n_dE_scale
         L.check(lib.vq_backward(P(gq), P(s["g_loss"]), P(z), P(s["E"]), P(s["idx"]), N_, N_, n_dE, K_, D_, BETA, L.FLAG_TRAIN_VQ,
                                 P(s["dz"]), P(s["dE"]), st))
-        if exch is not None:            # data parallel: one sum all-reduce of [dE | hist | sse]
+        if exch is not None:            # data parallel: ONE sum all-reduce of [dE | hist | sse]
             L.check(lib.vq_dp_allreduce(exch.ctx, P(s["packed"]), P(s["reduced"]), st))
         elif world > 1:
             dist.all_reduce(s["packed"][:K_ * D_ + K_ + 1])
@@ -384,11 +384,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # CUDA graphs take the host out of the loop (under data parallelism every rank's launch jitter otherwise turns into
-    # waiting inside the exchange).  Programmatic dependent launch does not cross graph boundaries, so one graph holds a
-    # whole round over the input buffers (nbuf steps); single-step graphs cover the remainder.  On one GPU the step is
-    # GPU-bound and eager launches keep the PDL chain unbroken: graphs only with --graph there.
-    use_graph = (args.graph or world > 1) and not args.no_graph and not (world > 1 and exch is None)   # NCCL stays eager
+    # CUDA graphs take the host out of the loop (the exchange carries its sequence number on the device, so the data-parallel
+    # step replays too).  Programmatic dependent launch does not cross graph boundaries, so one graph holds a whole round over
+    # the input buffers (nbuf steps); single-step graphs cover the remainder.  One GPU: eager by default -- the step is
+    # GPU-bound, the host stays ahead and the PDL chain is never broken (68.8 vs 72.2 us).  Data parallel: graphs by default --
+    # every rank's Python launch jitter otherwise turns into waiting inside the exchange (2 GPUs: 83.0 - 83.5 us replayed,
+    # 83.2 - 90.7 us eager).
+    use_graph = (args.graph or (world > 1 and not args.no_graph)) and not (world > 1 and exch is None)   # NCCL stays eager
     cur = torch.cuda.current_stream()
 
     def build_runner(s):

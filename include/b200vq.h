@@ -133,7 +133,7 @@ int vq_onehot(const int32_t* idx, int64_t n_rows, int K, float* onehot, vq_strea
  *   dE[idx[n],:] += g_loss*2*(E[idx] - z)/(n_rows_dE*D)   when VQ_FLAG_TRAIN_VQ and dE != NULL
  * dE is accumulated into: zero it first or pass VQ_FLAG_ZERO_DE (under data parallelism the caller
  * all-reduces it afterwards).  g_loss is a device scalar (NULL means 1).  The straight-through output sends
- * no gradient to E. */
+ * no gradient to E.  dz == NULL with VQ_FLAG_TRAIN_VQ computes the codebook gradient only. */
 int vq_backward(const float* g_q, const float* g_loss, const float* z, const float* E,
                 const int32_t* idx, int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE,
                 int K, int D, float beta, int flags, float* dz, float* dE, vq_stream_t stream);

@@ -124,7 +124,7 @@ def test_accumulate_and_overwrite(lib, path):
     np.testing.assert_allclose((dE_acc - init).cpu().numpy(), dE_ref, rtol=0, atol=5e-6 + 1e-5 * np.abs(dE_ref).max())
 
 
-@pytest.mark.parametrize("path", [PRIVATE])
+@pytest.mark.parametrize("path", [FLAT, PRIVATE])
 def test_codebook_gradient_only(lib, path):
     N, D, K = 7001, 64, 512
     E, z, g, idx = _make(N, D, K, seed=11)
