@@ -201,12 +201,10 @@ __device__ __forceinline__ void dp_gather(const DpCtxDev& c, const DpCall& k, co
 }
 
 // body shared by the production kernel (one rank per launch) and the single-GPU emulation (one rank per blockIdx.y)
-__device__ __forceinline__ void dp_allreduce_body(const DpCtxDev& c, const float* __restrict__ payload, float* __restrict__ out, int* s_abort) {
+__device__ __forceinline__ void dp_allreduce_body(const DpCtxDev& c, const DpCall& k, const float* __restrict__ payload, float* __restrict__ out,
+                                                  int* s_abort) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     const long long first = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (threadIdx.x == 0) *s_abort = 0;
-    __syncthreads();
-    const DpCall k = dp_begin(c);
     const DpWaiter w{c, s_abort};
     for (long long i = first; i < c.L; i += stride) {
         const float d0 = __ldcg(payload + 2 * i);
@@ -238,9 +236,12 @@ __device__ __forceinline__ void dp_end(const DpCtxDev& c) {
 __global__ void __launch_bounds__(DP_THREADS) dp_allreduce_kernel(const __grid_constant__ DpCtxDev c, const float* __restrict__ payload,
                                                                   float* __restrict__ out) {
     __shared__ int s_abort;
-    pdl_wait_prior_grids();      // the local contribution is complete
-    pdl_launch_dependents();
-    dp_allreduce_body(c, payload, out, &s_abort);
+    pdl_launch_dependents();     // whatever follows orders itself behind this kernel's completion
+    if (threadIdx.x == 0) s_abort = 0;
+    __syncthreads();
+    pdl_wait_prior_grids();      // the local contribution is complete -- and so is a previous exchange (its counter update)
+    const DpCall k = dp_begin(c);
+    dp_allreduce_body(c, k, payload, out, &s_abort);
     dp_end(c);
 }
 
@@ -250,9 +251,13 @@ __global__ void __launch_bounds__(DP_THREADS) dp_emulate_kernel(const DpCtxDev* 
                                                                 float* const* __restrict__ outs) {
     __shared__ int s_abort;
     __shared__ DpCtxDev c;
-    if (threadIdx.x == 0) c = ctxs[blockIdx.y];
+    if (threadIdx.x == 0) {
+        c = ctxs[blockIdx.y];
+        s_abort = 0;
+    }
     __syncthreads();
-    dp_allreduce_body(c, payloads[blockIdx.y], outs[blockIdx.y], &s_abort);
+    const DpCall k = dp_begin(c);
+    dp_allreduce_body(c, k, payloads[blockIdx.y], outs[blockIdx.y], &s_abort);
     dp_end(c);
 }
 
