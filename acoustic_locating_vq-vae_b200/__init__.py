@@ -10,8 +10,9 @@ from ._lib import B200VQError, load as load_library
 from .quantizer import VectorQuantizer, swap_quantizers
 from .onehot_linear import OneHotLinear
 from .jitter import Jitter
+from .time_mean import time_mean, time_mean_quantize
 
 build_extension = _build.build
 SO_PATH = _build.SO_PATH
 
-__all__ = ["VectorQuantizer", "swap_quantizers", "OneHotLinear", "Jitter", "load_library", "build_extension", "B200VQError", "SO_PATH"]
+__all__ = ["VectorQuantizer", "swap_quantizers", "OneHotLinear", "Jitter", "time_mean", "time_mean_quantize", "load_library", "build_extension", "B200VQError", "SO_PATH"]

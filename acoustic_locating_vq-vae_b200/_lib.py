@@ -51,9 +51,12 @@ SIGNATURES = {
     "vq_finalize_stats": (_int, [_vp, _vp, _i64, _int, _int, _f32, _vp, _vp, _vp]),
     "vq_onehot": (_int, [_vp, _i64, _int, _vp, _vp]),
     "vq_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp]),
+    "vq_step_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _sz, _int, _vp]),
     "vq_backward_path": (_int, [_i64, _int, _int, _int]),
     "vq_gather_sum_rows": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp]),
     "vq_scatter_add_rows": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _vp]),
+    "vq_time_mean": (_int, [_vp, _i64, _int, _vp, _vp]),
+    "vq_time_mean_backward": (_int, [_vp, _i64, _int, _vp, _vp]),
     "vq_jitter_apply": (_int, [_vp, _vp, _i64, _int, _vp]),
     "vq_jitter_backward": (_int, [_vp, _vp, _i64, _int, _vp]),
     "vq_dp_recv_lines": (_i64, [_int, _i64]),

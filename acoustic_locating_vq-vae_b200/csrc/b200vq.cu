@@ -671,9 +671,9 @@ int vq_backward_path(int64_t n_rows, int K, int D, int flags) {
     return choose_bwd_path(n_rows, K, D, flags, D % 4 == 0);
 }
 
-int vq_backward(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx,
-                int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags, float* dz,
-                float* dE, vq_stream_t stream) {
+static int backward_impl(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx,
+                         int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags, float* dz,
+                         float* dE, const unsigned int* ready, vq_stream_t stream) {
     if (int rc = check_device()) return rc;
     const long long N = n_rows;
     const bool train = (flags & VQ_FLAG_TRAIN_VQ) != 0 && dE != nullptr;
@@ -716,7 +716,7 @@ int vq_backward(const float* g_q, const float* g_loss, const float* z, const flo
     if (g > kNumSMs * 32) g = kNumSMs * 32;
     const int grid = static_cast<int>(g);
     ProfScope prof(KID_BACKWARD, st);
-#define BWD_ARGS g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, D, beta, dz, dE
+#define BWD_ARGS g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, D, beta, dz, dE, ready
 #define BWD_LAUNCH(TR, GQ)                                                                                        \
     do {                                                                                                          \
         cudaError_t e__;                                                                                          \
@@ -732,6 +732,32 @@ int vq_backward(const float* g_q, const float* g_loss, const float* z, const flo
 #undef BWD_ARGS
     LAUNCH_CHECK("backward_kernel");
     return VQ_OK;
+}
+
+int vq_backward(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx,
+                int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags, float* dz,
+                float* dE, vq_stream_t stream) {
+    return backward_impl(g_q, g_loss, z, E, idx, n_rows, n_rows_dz, n_rows_dE, K, D, beta, flags, dz, dE, nullptr, stream);
+}
+
+// The backward launched RIGHT BEHIND vq_step_forward on the same stream and workspace (nothing in between): on the
+// screen + refine path the flat kernel starts as soon as the forward's last CTA has raised the workspace's ready word --
+// indices and everything else it reads are complete then -- and overlaps the forward's serial statistics tail.
+int vq_step_backward(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx,
+                     int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags, float* dz,
+                     float* dE, const void* workspace, size_t workspace_bytes, int forward_flags, vq_stream_t stream) {
+    const unsigned int* ready = nullptr;
+    const int ff = forward_flags & ~VQ_FLAG_STATE_READY;
+    const bool train = (flags & VQ_FLAG_TRAIN_VQ) != 0 && dE != nullptr;
+    const bool vec = D % 4 == 0;
+    if (workspace != nullptr && n_rows > 0 && dz != nullptr && !(flags & VQ_FLAG_ZERO_DE) &&
+        screen_path_ok(n_rows, K, D, ff, z, E, nullptr, nullptr) && ((ff & VQ_FLAG_SCREEN) || screen_enabled()) &&
+        (!train || choose_bwd_path(n_rows, K, D, flags, vec) == BWD_FLAT)) {
+        const WsLayout w = ws_layout(n_rows);
+        if (workspace_bytes < w.total) return fail(VQ_ERR_WORKSPACE, "vq_step_backward: workspace %zu B < %zu B", workspace_bytes, w.total);
+        ready = reinterpret_cast<const unsigned int*>(static_cast<const uint8_t*>(workspace) + w.counter_off) + 2;
+    }
+    return backward_impl(g_q, g_loss, z, E, idx, n_rows, n_rows_dz, n_rows_dE, K, D, beta, flags, dz, dE, ready, stream);
 }
 
 // =========================================================================================================
@@ -907,6 +933,31 @@ int vq_scatter_add_rows(const int32_t* idx, const float* g, float* dWt, int B, i
     return VQ_OK;
 }
 
+// SURVEY 8(f) rank 2, first half: the time-mean variant in front of the quantizer (convolutional_vq_vae.py:96-97).
+int vq_time_mean(const float* x, int64_t rows, int T, float* z, vq_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    if (x == nullptr || z == nullptr || rows < 0 || T < 1) return fail(VQ_ERR_ARG, "vq_time_mean: bad argument");
+    if (rows == 0) return VQ_OK;
+    long long blocks = (rows + 7) / 8;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const cudaError_t e = launch_pdl(time_mean_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st, x, static_cast<long long>(rows), T, z);
+    if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of time_mean_kernel failed: %s", cudaGetErrorString(e));
+    LAUNCH_CHECK("time_mean_kernel");
+    return VQ_OK;
+}
+
+int vq_time_mean_backward(const float* dz, int64_t rows, int T, float* dx, vq_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    if (dz == nullptr || dx == nullptr || rows < 0 || T < 1) return fail(VQ_ERR_ARG, "vq_time_mean_backward: bad argument");
+    if (rows == 0) return VQ_OK;
+    long long blocks = (rows * T + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    time_mean_backward_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(dz, static_cast<long long>(rows), T, dx);
+    LAUNCH_CHECK("time_mean_backward_kernel");
+    return VQ_OK;
+}
+
 // Jitter (modules/jitter.py:47-70) -- in-place gather along time of a (rows, T) tensor.
 int vq_jitter_apply(float* q, const int32_t* src, int64_t rows, int T, vq_stream_t stream) {
     if (int rc = check_device()) return rc;
@@ -1028,8 +1079,9 @@ int vq_host_step_async(vq_host_ctx* c, int lane, const float* z_host, const floa
         return rc;
     // gq_host == NULL: the lane's g_q buffer still holds the ones written at context creation, i.e. the
     // `(loss + quantized.sum()).backward()` workload; the kernel reads it like any upstream gradient.
-    if (int rc = vq_backward(l.gq, nullptr, l.z, c->E, l.idx, n_rows, n_rows, n_rows_dE > 0 ? n_rows_dE : n_rows, c->K, c->D, beta,
-                             flags & (VQ_FLAG_TRAIN_VQ | VQ_FLAG_BWD_FLAT | VQ_FLAG_BWD_PRIVATE), l.dz, train ? l.dE : nullptr, l.st))
+    if (int rc = vq_step_backward(l.gq, nullptr, l.z, c->E, l.idx, n_rows, n_rows, n_rows_dE > 0 ? n_rows_dE : n_rows, c->K, c->D, beta,
+                                  flags & (VQ_FLAG_TRAIN_VQ | VQ_FLAG_BWD_FLAT | VQ_FLAG_BWD_PRIVATE), l.dz, train ? l.dE : nullptr, l.ws, l.ws_bytes,
+                                  flags & keep, l.st))
         return rc;
     if (loss_host) CUDA_TRY(cudaMemcpyAsync(loss_host, l.scal + 1, sizeof(float), cudaMemcpyDeviceToHost, l.st));
     if (perplexity_host) CUDA_TRY(cudaMemcpyAsync(perplexity_host, l.scal + 2, sizeof(float), cudaMemcpyDeviceToHost, l.st));

@@ -293,6 +293,9 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // programmatic dependent launch (PDL): let the next kernel in the stream start its prologue early / wait for

@@ -183,6 +183,13 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait_prior_grids();
+    // the workspace's ready word (raised by the last CTA once everything but loss / perplexity is complete): lowered
+    // before any dependent can be launched -- the trigger below is issued by this very thread after the store
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        fr.counter[2] = 0u;
+        __threadfence();
+    }
+    __syncthreads();
     // The next kernel of the stream may be LAUNCHED from here on: its CTAs only become resident as ours exit (this
     // kernel owns the SM's registers and shared memory) and they order themselves with griddepcontrol.wait, so the
     // trigger costs nothing and takes the launch latency off the step's critical path.

@@ -381,9 +381,24 @@ __global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__
                                                        const float* __restrict__ z, const float* __restrict__ E,
                                                        const int* __restrict__ idx, long long N, float denom_dz,
                                                        float denom_dE, int D, float beta, float* __restrict__ dz,
-                                                       float* __restrict__ dE) {
+                                                       float* __restrict__ dE, const unsigned int* ready) {
     pdl_launch_dependents();
-    pdl_wait_prior_grids();
+    // ready != NULL (vq_step_backward right behind the fused forward): start as soon as the forward's last CTA has raised
+    // the workspace's ready word -- everything this kernel reads is complete then; the forward's serial statistics tail
+    // (loss / perplexity) overlaps this kernel.  Bounded: after a few thousand polls fall back to the full dependency.
+    if (ready != nullptr) {
+        __shared__ int s_ok;
+        if (threadIdx.x == 0) {
+            unsigned int polls = 0;
+            while (ld_acquire_gpu_u32(ready) != 1u && ++polls < 4096u) {
+            }
+            s_ok = polls < 4096u ? 1 : 0;
+        }
+        __syncthreads();
+        if (!s_ok) pdl_wait_prior_grids();
+    } else {
+        pdl_wait_prior_grids();
+    }
     const float gl = g_loss != nullptr ? __ldg(g_loss) : 1.0f;
     const float cz = gl * beta * 2.0f / denom_dz;
     const float ce = gl * 2.0f / denom_dE;
@@ -417,6 +432,8 @@ __global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__
             if (TRAIN_VQ) atomicAdd(dE + static_cast<size_t>(code) * D + c, ce * df);
         }
     }
+    // order this kernel behind the forward's completion before it exits: "previous kernel complete" stays transitive
+    if (ready != nullptr) pdl_wait_prior_grids();
 }
 
 // codebook gradient only (vq_backward with dz == NULL): dE[idx] += ce * (E[idx] - z)
@@ -501,6 +518,46 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const int* __rest
         const float4 v = __ldg(reinterpret_cast<const float4*>(g + static_cast<size_t>(b) * O) + o4);
         atomicAdd(reinterpret_cast<float4*>(dWt + row * O) + o4, v);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SURVEY 8(f) rank 2 (first half) -- the time-mean variant in front of the quantizer
+// (convolutional_vq_vae.py:96-97: `z = torch.mean(z, dim=2, keepdim=True)` between `_pre_vq_conv` and `_vq`).
+// x is (rows = B*D, T); z[row] = sum_t x[row, t] / T.  One warp per row: coalesced 16-byte loads, a fixed summation
+// order (per-lane partial sums over t = lane*4 + 128*i + j in increasing i, then the xor-shuffle tree), so the result
+// is reproducible run to run; it differs from torch.mean's order by fp32 rounding only.
+// The backward spreads dz[row] / T over the T positions.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) time_mean_kernel(const float* __restrict__ x, long long rows, int T, float* __restrict__ z) {
+    pdl_launch_dependents();
+    pdl_wait_prior_grids();
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    const long long nwarps = static_cast<long long>(gridDim.x) * 8;
+    const bool vec = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
+    for (long long r = warp0; r < rows; r += nwarps) {
+        const float* xr = x + r * T;
+        float acc = 0.0f;
+        if (vec) {
+            const float4* x4 = reinterpret_cast<const float4*>(xr);
+            for (int i = lane; i < (T >> 2); i += 32) {
+                const float4 v = __ldcs(x4 + i);
+                acc += v.x; acc += v.y; acc += v.z; acc += v.w;
+            }
+        } else {
+            for (int t = lane; t < T; t += 32) acc += xr[t];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) z[r] = acc / static_cast<float>(T);
+    }
+}
+
+__global__ void __launch_bounds__(256) time_mean_backward_kernel(const float* __restrict__ dz, long long rows, int T, float* __restrict__ dx) {
+    const long long n = rows * T;
+    const float inv = 1.0f / static_cast<float>(T);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        dx[i] = __ldg(dz + i / T) * inv;
 }
 
 // ---------------------------------------------------------------------------------------------

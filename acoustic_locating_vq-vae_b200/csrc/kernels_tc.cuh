@@ -371,7 +371,15 @@ __device__ __forceinline__ void publish_and_finalize(const FusedRowArgs& fr, flo
         fr.partials[blockIdx.x] = red_total();
         __threadfence();
         const unsigned int done = atomicAdd(fr.counter, 1u);
-        *last_flag = (done == gridDim.x - 1) ? 1 : 0;
+        const bool last = done == gridDim.x - 1;
+        *last_flag = last ? 1 : 0;
+        if (last) {
+            // every CTA has published (fence + atomic above): indices, q_out, one-hot and the usage counts are complete.
+            // Raise the workspace's ready word NOW: a backward launched behind this kernel (vq_step_backward) starts on it and
+            // overlaps the serial statistics tail below (loss / perplexity, ~5 us), which it does not need.
+            __threadfence();
+            st_release_gpu_u32(fr.counter + 2, 1u);
+        }
     }
     named_bar_sync(bar_id, nw);
     if (!*last_flag) return;

@@ -15,8 +15,23 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from . import _lib, parallel
+import os
+
+from . import _lib, build as _build, parallel
 from ._lib import (FLAG_EXACT, FLAG_ONEHOT, FLAG_TRAIN_VQ, FLAG_ZERO_DE, check)
+
+
+_ext = None
+
+
+def _binding():
+    """The C++ autograd node (csrc/torch_binding.cpp): same logic as _VQFunction below, without ~120 us of Python per step.
+    B200VQ_PY_AUTOGRAD=1 selects the Python node (debugging); both drive the same kernels through the same C ABI."""
+    global _ext
+    if _ext is None:
+        _lib.load()
+        _ext = False if os.environ.get("B200VQ_PY_AUTOGRAD") == "1" else _build.load_torch_binding()
+    return _ext
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -240,8 +255,36 @@ class VectorQuantizer(nn.Module):
         flags = FLAG_EXACT if self.exact else 0
         # data parallel with a training codebook: the forward writes its statistics straight into the packed step buffer
         # (decided here: grad mode is off inside autograd.Function.forward)
-        pack = bool((self.process_group is not None or self.data_parallel) and self._train_vq and weight.requires_grad
-                    and torch.is_grad_enabled())
+        dp = self.process_group is not None or self.data_parallel
+        pack = bool(dp and self._train_vq and weight.requires_grad and torch.is_grad_enabled())
+        ext = _binding()
+        if ext:
+            K, D = self._num_embeddings, self._embedding_dim
+            dev = inputs.device
+            N = inputs.numel() // D
+            world, dp_ptr = 1, 0
+            if dp:
+                import torch.distributed as dist
+                world = dist.get_world_size(self.process_group)
+                if pack:
+                    ex = self._peer_exchange(K, D, dev, self.process_group)
+                    dp_ptr = 0 if ex is None else int(ex.ctx.value)
+            if not (pack and dp_ptr == 0):     # data parallel over NCCL (no NVLink exchange): the Python node below handles it
+                bufs = self._bufs
+                e_norm2, e_hi, e_lo = bufs.codebook(K, D, dev)
+                nbytes = bufs.ws_bytes.get((N, K, D))
+                if nbytes is None:
+                    nbytes = bufs.ws_bytes[(N, K, D)] = ext.workspace_bytes(N, K, D)
+                ws = bufs.workspace(nbytes, dev)
+                loss, quantized, perplexity, onehot, idx, stats, reduced = ext.vq_apply(
+                    inputs, weight, float(self._commitment_cost), flags, bool(self.return_encodings), bool(self._train_vq), world, dp_ptr, pack,
+                    e_norm2, e_hi, e_lo, ws)
+                d = self.__dict__
+                d["last_indices"] = idx
+                d["_last_stats"] = stats[K * D:] if pack else stats
+                if pack:
+                    d["_global_stats"] = (reduced[K * D:], N * world)      # filled by the backward's all-reduce
+                return loss, quantized, perplexity, (onehot if self.return_encodings else None)
         if inputs.device.index != torch.cuda.current_device():      # the C ABI launches on the current device
             with torch.cuda.device(inputs.device):
                 loss, quantized, perplexity, encodings, idx = _VQFunction.apply(

@@ -6,7 +6,7 @@
 One "step" = one pass of the hot path (vector_quantizer.py:29-58 and its autograd) over one batch of synthetic
 latents of the shape `_pre_vq_conv` hands to the quantizer:
     vq_step_forward   codebook norms + distances + argmin + one-hot + gather + losses + perplexity
-    vq_backward       dz and dE
+    vq_step_backward  dz and dE
 Default workload = BASELINE.json configs[1]: RIR VQ-VAE quantizer from train_rir.py defaults at batch 256 ->
 z (256, 64, 201), N = 51 456 rows, K = 1024, D = 64, beta = 0.25, dense one-hot `encodings` emitted (the reference
 always returns it).  N = 1: eager launches chained by programmatic dependent launch; N > 1: replayed from CUDA graphs.
@@ -85,7 +85,7 @@ def make_config(name, world):
     """The workload description both arms print (identical dictionaries, so the driver can pair them)."""
     B, D, T, K, desc = WORKLOADS[name]
     return {"workload": f"{name}: {desc}", "B": B, "D": D, "T": T, "K": K, "rows_per_gpu": B * T, "beta": BETA,
-            "encodings": "dense one-hot" if B * T * K * 4 <= (8 << 30) else "indices only",
+            "encodings": "indices only" if name.startswith("sweep") else "dense one-hot",
             "parallelism": f"dp{world}" if world > 1 else "single GPU"}
 
 
@@ -272,7 +272,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     B, D, T, K, desc = WORKLOADS[args.workload]
     N = B * T
-    emit_onehot = not args.no_onehot and N * K * 4 <= (8 << 30)
+    # configs[3] (the sweep) is indices-only by definition (a dense one-hot would be up to 34 GB)
+    emit_onehot = not args.no_onehot and not args.workload.startswith("sweep")
     config = make_config(args.workload, max(world, args.gpus))
     if args.no_onehot:
         config["encodings"] = "indices only"
@@ -372,8 +373,9 @@ def main():
         L.check(lib.vq_step_forward(P(z), P(s["E"]), N_, K_, D_, BETA, s["fwd_flags"], P(s["e2"]), P(s["ehi"]), P(s["elo"]), P(s["dE"]), P(s["q"]), P(s["idx"]),
                                     P(s["onehot"]), sp, sp + 4 * K_, sp + 4 * (K_ + 1), sp + 4 * (K_ + 2), P(s["ws"]), s["wsb"], st))
         n_dE = N_ * n_dE_scale
-        L.check(lib.vq_backward(P(gq), P(s["g_loss"]), P(z), P(s["E"]), P(s["idx"]), N_, N_, n_dE, K_, D_, BETA, L.FLAG_TRAIN_VQ,
-                                P(s["dz"]), P(s["dE"]), st))
+        # right behind the forward: starts on the workspace's ready word and overlaps the forward's statistics tail
+        L.check(lib.vq_step_backward(P(gq), P(s["g_loss"]), P(z), P(s["E"]), P(s["idx"]), N_, N_, n_dE, K_, D_, BETA, L.FLAG_TRAIN_VQ,
+                                     P(s["dz"]), P(s["dE"]), P(s["ws"]), s["wsb"], s["fwd_flags"], st))
         if exch is not None:            # data parallel: ONE sum all-reduce of [dE | hist | sse]
             L.check(lib.vq_dp_allreduce(exch.ctx, P(s["packed"]), P(s["reduced"]), st))
         elif world > 1:

@@ -137,6 +137,16 @@ int vq_onehot(const int32_t* idx, int64_t n_rows, int K, float* onehot, vq_strea
 int vq_backward(const float* g_q, const float* g_loss, const float* z, const float* E,
                 const int32_t* idx, int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE,
                 int K, int D, float beta, int flags, float* dz, float* dE, vq_stream_t stream);
+/* vq_backward launched RIGHT BEHIND vq_step_forward on the same stream and workspace (nothing in between; `forward_flags`
+ * = the flags that forward got): on the screen + refine path the kernel starts as soon as the forward's last CTA has
+ * raised the workspace's ready word -- everything the backward reads is complete then -- and overlaps the forward's
+ * serial statistics tail (loss / perplexity, ~5 us), which it does not need.  It orders itself behind the forward's
+ * completion before it exits, and falls back to the full dependency when the word does not show up.  Elsewhere (other
+ * shapes, VQ_FLAG_ZERO_DE, dz == NULL, the private path) it is vq_backward. */
+int vq_step_backward(const float* g_q, const float* g_loss, const float* z, const float* E,
+                     const int32_t* idx, int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE,
+                     int K, int D, float beta, int flags, float* dz, float* dE,
+                     const void* workspace, size_t workspace_bytes, int forward_flags, vq_stream_t stream);
 /* Which kernel vq_backward takes for dE (16-byte aligned pointers assumed): 0 flat (one red.global.add per element),
  * 2 private (per-CTA copy of dE in shared memory, flushed once; N >> K and K*D small).  dz may be NULL on path 2
  * (codebook gradient only). */
@@ -149,6 +159,14 @@ int vq_backward_path(int64_t n_rows, int K, int D, int flags);
 int vq_gather_sum_rows(const int32_t* idx, const float* Wt, const float* bias_or_null, float* y,
                        int B, int T, int K, int O, vq_stream_t stream);
 int vq_scatter_add_rows(const int32_t* idx, const float* g, float* dWt, int B, int T, int K, int O, vq_stream_t stream);
+
+/* -- the time-mean variant in front of the quantizer (first half) ------------------------------ */
+/* convolutional_vq_vae.py:96-97 (`encoder_average_pooling`): z = mean over time of the `_pre_vq_conv` output, x (B, D, T)
+ * -> z (B, D, 1), which the quantizer then sees as B rows.  z[row] = sum_t x[row, t] / T with rows = B*D, in a fixed
+ * summation order; launched with the programmatic-launch attribute so that the forward behind it chains without a gap.
+ * The backward spreads dz[row] / T over the T positions. */
+int vq_time_mean(const float* x, int64_t rows, int T, float* z, vq_stream_t stream);
+int vq_time_mean_backward(const float* dz, int64_t rows, int T, float* dx, vq_stream_t stream);
 
 /* -- Jitter on the quantizer's output (modules/jitter.py:47-70) ------------------------- */
 /* In place on q (rows = B*D, T): column t becomes the ORIGINAL column src[t] (src[t] in {t-1, t, t+1}; the host

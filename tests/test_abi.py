@@ -102,3 +102,41 @@ def test_reference_state_dict_loads():
     mine = b200vq.VectorQuantizer(64, 16, 0.25)
     mine.load_state_dict(ref.state_dict())
     assert torch.equal(mine._embedding.weight, ref._embedding.weight)
+
+
+def test_whole_model_pickle_round_trip_then_swap(tmp_path):
+    """The reference checkpoints are whole pickled modules (train_speech.py:117-118 `torch.save(model, path)`, reloaded with
+    `torch.load(path)` at train_echoed_speech.py:18-19 / train_location.py:38): a model saved that way must load, swap its
+    quantizers for the B200 ones and keep codebooks, frozen flags and state-dict keys -- and the swapped model must itself
+    survive torch.save / torch.load (scratch buffers and process groups do not travel)."""
+    from oracle.vq_oracle import import_reference_class
+    import b200vq
+    if import_reference_class() is None:
+        pytest.skip("/root/reference absent")
+    from acoustic_locating_vq_vae.vq_vae.convolutional_vq_vae import ConvolutionalVQVAE
+    from acoustic_locating_vq_vae.vq_vae.echoed_speech_model import EchoedSpeechReconModel
+    torch.manual_seed(21)
+    rir = ConvolutionalVQVAE(20, 16, 8, 1, 8, 0.25, 32, use_jitter=False, out_channels=1)
+    speech = ConvolutionalVQVAE(12, 16, 8, 1, 8, 0.25, 32)
+    model = EchoedSpeechReconModel(rir, speech, 12, 16, 1, 8, True)
+    path = tmp_path / "model_echoed_speech.pt"
+    torch.save(model, path)                                             # exactly what the scripts do
+    loaded = torch.load(path, weights_only=False)
+    keys = sorted(loaded.state_dict().keys())
+    codebooks = {n: p.detach().clone() for n, p in loaded.named_parameters() if n.endswith("_vq._embedding.weight")}
+    assert len(codebooks) == 2
+    assert b200vq.swap_quantizers(loaded) == 2
+    assert sorted(loaded.state_dict().keys()) == keys                   # same checkpoint layout after the swap
+    for n, w in codebooks.items():
+        assert torch.equal(dict(loaded.named_parameters())[n], w)
+    assert loaded.rir_model._vq._train_vq is False and loaded.speech_model._vq._train_vq is False
+    path2 = tmp_path / "model_swapped.pt"
+    torch.save(loaded, path2)
+    again = torch.load(path2, weights_only=False)
+    assert isinstance(again.rir_model._vq, b200vq.VectorQuantizer) and again.rir_model._vq._bufs is not None
+    assert sorted(again.state_dict().keys()) == keys
+    for n, w in codebooks.items():
+        assert torch.equal(dict(again.named_parameters())[n], w)
+    # and the reference class loads a state dict written by the swapped model (checkpoints stay exchangeable)
+    ref_speech = ConvolutionalVQVAE(12, 16, 8, 1, 8, 0.25, 32)
+    ref_speech.load_state_dict(again.speech_model.state_dict())

@@ -230,3 +230,42 @@ def test_dp_exchange_bounded_wait(lib):
     assert lib.vq_dp_status(ctx, ctypes.byref(calls), ctypes.byref(err), st) == 0
     assert err.value & 1 == 1 and calls.value == 1
     lib.vq_dp_destroy(ctx)
+
+
+def test_step_backward_behind_the_forward(lib):
+    """vq_step_backward starts on the workspace's ready word, before the forward's statistics tail has finished: over many
+    back-to-back steps with fresh inputs it must see complete indices every time (dz bit-identical to a backward run
+    after a full synchronise, dE within tolerance), and the forward's loss / perplexity must be complete afterwards."""
+    dev = _dev()
+    for (N, D, K, onehot) in ((51456, 64, 1024, True), (16000, 128, 1024, False), (3216, 64, 1024, True), (300, 32, 256, False)):
+        st = torch.cuda.current_stream().cuda_stream
+        E = torch.randn(K, D, device=dev)
+        e2 = torch.empty(K, device=dev); ehi = torch.empty_like(E); elo = torch.empty_like(E)
+        wsb = lib.vq_workspace_bytes(N, K, D, 0); ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        q = torch.empty(N, D, device=dev); idx = torch.empty(N, dtype=torch.int32, device=dev)
+        oh = torch.empty(N, K, device=dev) if onehot else None
+        stats = torch.empty(K + 3, device=dev); sp = stats.data_ptr()
+        dz = torch.empty(N, D, device=dev); dE = torch.empty(K, D, device=dev)
+        gl = torch.tensor(0.7, device=dev)
+        fl = 1 if onehot else 0
+        zs = [torch.randn(N, D, device=dev) for _ in range(6)]
+        gs = [torch.randn(N, D, device=dev) for _ in range(6)]
+        outs = []
+        for i in range(6):                                   # enqueue everything, no synchronisation in between
+            rc = lib.vq_step_forward(zs[i].data_ptr(), E.data_ptr(), N, K, D, BETA, fl, e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(), dE.data_ptr(),
+                                     q.data_ptr(), idx.data_ptr(), None if oh is None else oh.data_ptr(), sp, sp + 4 * K, sp + 4 * (K + 1),
+                                     sp + 4 * (K + 2), ws.data_ptr(), wsb, st)
+            assert rc == 0, lib.vq_last_error()
+            rc = lib.vq_step_backward(gs[i].data_ptr(), gl.data_ptr(), zs[i].data_ptr(), E.data_ptr(), idx.data_ptr(), N, N, N, K, D, BETA, TRAIN,
+                                      dz.data_ptr(), dE.data_ptr(), ws.data_ptr(), wsb, fl, st)
+            assert rc == 0, lib.vq_last_error()
+            outs.append((idx.clone(), dz.clone(), dE.clone(), stats.clone()))
+        torch.cuda.synchronize()
+        for i, (ix, dz_i, dE_i, st_i) in enumerate(outs):
+            dz_ref, dE_ref = _backward(lib, gs[i], 0.7, zs[i], E, ix, TRAIN | ZERO_DE | FLAT)
+            assert torch.equal(dz_i, dz_ref), f"N={N} step {i}"
+            assert _rel(dE_i.cpu().numpy(), dE_ref.cpu().numpy()) <= 1e-5, f"N={N} step {i}"
+            d = (zs[i] * zs[i]).sum(1, keepdim=True) + (E * E).sum(1) - 2 * zs[i] @ E.t()
+            assert float((ix.long() != d.argmin(1)).float().mean()) < 1e-3          # same codes as the plain torch argmin (up to near-ties)
+            m = float(((E[ix.long()] - zs[i]) ** 2).mean())
+            assert abs(float(st_i[K + 1]) - 1.25 * m) <= 1e-5 * 1.25 * m and float(st_i[K + 2]) > 1.0

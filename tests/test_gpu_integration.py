@@ -12,6 +12,8 @@ downstream -- losses, reconstructions, gradients, Adam-updated weights -- must a
 """
 import copy
 
+import numpy as np
+
 import pytest
 import torch
 import torch.nn as nn
@@ -281,3 +283,34 @@ def test_module_is_cuda_graph_capturable():
     assert torch.equal(enc, e2) and torch.equal(q.detach(), q2.detach())
     assert _rel(loss.detach(), l2.detach()) <= 1e-6 and _rel(perp, p2) <= 1e-6
     assert _rel(static_z.grad, z2.grad) <= 1e-6 and _rel(vq._embedding.weight.grad, eager._embedding.weight.grad) <= RTOL
+
+
+@pytest.mark.parametrize("B,D,T,K", [(32, 128, 500, 1024), (8, 64, 201, 256), (5, 32, 7, 64), (3, 10, 13, 37)])
+def test_time_mean_variant_in_front_of_the_quantizer(B, D, T, K):
+    """convolutional_vq_vae.py:96-98 with encoder_average_pooling=True: z = mean over time, then the quantizer on B rows.
+    The fused call must equal the two reference ops: the pooled z within fp32 summation-order rounding of torch.mean,
+    and -- GIVEN that z -- indices bit-exact vs the oracle, outputs and gradients within the north-star tolerance."""
+    import b200vq
+    from oracle import c_oracle
+    dev = torch.device("cuda:0")
+    torch.manual_seed(B + T)
+    vq = b200vq.VectorQuantizer(K, D, 0.25).to(dev)
+    vq._embedding.weight.data.normal_()
+    x = torch.randn(B, D, T, device=dev, requires_grad=True)
+    z = b200vq.time_mean(x)
+    assert z.shape == (B, D, 1)
+    ref_z = torch.mean(x.detach(), dim=2, keepdim=True)
+    assert float((z.detach() - ref_z).abs().max()) <= 4e-7 * max(1.0, float(ref_z.abs().max()))
+    loss, q, perp, enc = b200vq.time_mean_quantize(vq, x)
+    rows = z.detach().reshape(B, D).cpu().numpy()
+    E = vq._embedding.weight.detach().cpu().numpy()
+    idx = c_oracle.argmin(rows, E)
+    assert np.array_equal(vq.last_indices.cpu().numpy(), idx)
+    fwd = c_oracle.quantize(rows, E, idx, 0.25)
+    assert abs(float(loss) - fwd["loss"]) <= RTOL * fwd["loss"] and abs(float(perp) - fwd["perplexity"]) <= RTOL * fwd["perplexity"]
+    g = torch.randn(B, D, 1, device=dev)
+    (loss + (g * q).sum()).backward()
+    dz_ref, dE_ref = c_oracle.backward(g.reshape(B, D).cpu().numpy(), 1.0, rows, E, idx, 0.25, True)
+    dx_ref = np.repeat(dz_ref.reshape(B, D, 1), T, axis=2) / T                       # d mean / d x = 1 / T
+    assert _rel(x.grad, torch.from_numpy(dx_ref).to(dev)) <= RTOL
+    assert _rel(vq._embedding.weight.grad, torch.from_numpy(dE_ref).to(dev)) <= RTOL
