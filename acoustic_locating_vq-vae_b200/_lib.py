@@ -9,7 +9,7 @@ import os
 
 from .build import SO_PATH
 
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 FLAG_ONEHOT = 1 << 0
 FLAG_TRAIN_VQ = 1 << 1
@@ -63,6 +63,8 @@ SIGNATURES = {
     "vq_dp_create": (_int, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _vp, _int, _int, _i64, ctypes.c_uint32, ctypes.POINTER(_vp)]),
     "vq_dp_destroy": (None, [_vp]),
     "vq_dp_allreduce": (_int, [_vp, _vp, _vp, _vp]),
+    "vq_dp_allreduce_start": (_int, [_vp, _vp, _vp, _vp]),
+    "vq_dp_wait": (_int, [_vp, _int, _vp]),
     "vq_dp_status": (_int, [_vp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), _vp]),
     "vq_dp_emulate": (_int, [_int, _int, _i64, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _int, ctypes.c_uint32,
                              ctypes.POINTER(ctypes.c_uint32), _vp]),

@@ -210,6 +210,23 @@ bool screen_path_ok(long long N, int K, int D, int flags, const float* z, const 
     return aligned16(z) && aligned16(E) && (!quant || aligned16(q_out)) && (!want_onehot || aligned16(onehot));
 }
 
+// Screen + refine with the row epilogue as a SECOND kernel (quantize_rows_kernel).  Fused, the 4 worker warps of a CTA
+// walk every item through a chain of latency-bound phases (refine, indices, usage counts, gather + q_out + SSE): about
+// 3.5 us + 0.07 us * D per 128-row item, whatever K is.  With many code tiles per item the tensor pipe / epilogue set the
+// pace and that work is hidden; with few (small K) the workers set it and a streaming kernel at HBM speed behind an
+// indices-only screen kernel is faster, although z is read twice.  Only without the dense one-hot (its zero-fill hides
+// everything else).  B200VQ_SPLIT_ROWS=0|1 forces either.
+bool screen_split_rows(long long N, int K, int D, int flags) {
+    if ((flags & (VQ_FLAG_ONEHOT | VQ_FLAG_NO_QUANT)) != 0) return false;
+    static const int forced = [] { const char* e = getenv("B200VQ_SPLIT_ROWS"); return e == nullptr ? -1 : atoi(e); }();
+    if (forced >= 0) return forced != 0;
+    if (N < 64 * 1024) return false;                       // short launches: one kernel less is worth more
+    const double tile_us = D <= 64 ? 1.5 : (D <= 128 ? 1.6 : 3.2);          // per 256-code tile (epilogue- / MMA-bound)
+    const double fused_item = 3.5 + 0.07 * D, pipe_item = (K / 256) * tile_us + (D > 128 ? 4.0 : 0.0);
+    const double rows_item = 128.0 * (2 * D + 1) * 4 / 35e3;                // us per 128 rows at ~35 GB/s per SM
+    return (pipe_item > 3.0 ? pipe_item : 3.0) + rows_item < (fused_item > pipe_item ? fused_item : pipe_item) * 0.95;
+}
+
 // number of codebook splits per row tile: fill the 148 SMs when there are few row tiles.
 // cost(s) ~ waves(s) * (code tiles per CTA + fixed per-CTA overhead of ~1 tile)
 int choose_splits(long long row_tiles, int code_tiles, int max_splits, int slots = kNumSMs, double overhead = 1.0) {
@@ -236,7 +253,7 @@ struct WsLayout {
 // rows per CTA group of the streaming kernels: 256 threads, one 16-byte (or 4-byte) element each
 int rows_per_group(int D, bool vec) {
     const int dv = vec ? D / 4 : D;
-    int R = 256 / (dv < 1 ? 1 : dv);
+    int R = (vec ? 1024 : 256) / (dv < 1 ? 1 : dv);     // vector path: four elements in flight per thread
     if (R < 1) R = 1;
     if (R > ROWS_MAX_R) R = ROWS_MAX_R;
     return R;
@@ -453,11 +470,14 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
     // fits this kernel.  VQ_FLAG_NO_SCREEN / B200VQ_SCREEN=0 select the 3xTF32 kernel, VQ_FLAG_SCREEN forces this one.
     const bool screen = screen_path_ok(N, K, D, flags, z, E, q_out, onehot) && E_hi != nullptr && aligned16(E_hi) &&
                         ((flags & VQ_FLAG_SCREEN) || screen_enabled());
+    bool rows_done = false;
     if (screen) {
+        const bool split = screen_split_rows(N, K, D, flags);
         FusedRowArgs fr{};
-        fr.z = z; fr.E = E; fr.q_out = quant ? q_out : nullptr; fr.onehot = want_onehot ? onehot : nullptr; fr.hist = hist;
+        fr.z = z; fr.E = E; fr.q_out = (quant && !split) ? q_out : nullptr; fr.onehot = want_onehot ? onehot : nullptr; fr.hist = hist;
         fr.partials = partials; fr.counter = counter; fr.sse_out = sse; fr.loss = loss; fr.perplexity = perplexity;
         fr.beta = beta; fr.finalize = defer ? 0 : 1; fr.trace = g_trace_buf;
+        fr.rows_later = split ? 1 : 0;
         fr.spill = reinterpret_cast<int4*>(keys_buf);   // 16-byte aligned: keys_off is a multiple of 256
         static const int evict_first = [] { const char* e = getenv("B200VQ_ONEHOT_EVICT_FIRST"); return e != nullptr && e[0] == '0' ? 0 : 1; }();
         fr.onehot_evict_first = evict_first;
@@ -465,17 +485,24 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
         if (int rc = make_tmap(&tz, z, N, D)) return rc;
         if (int rc = make_tmap(&thi, E_hi, K, D)) return rc;
         const bool ready = (flags & VQ_FLAG_STATE_READY) != 0;
+        int rc = -1;
         switch (D / TC_SLAB_FLOATS) {
-            case 1: return launch_screen<1, 8, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
-            case 2: return launch_screen<2, 8, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
-            case 3: return launch_screen<3, 6, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
-            case 4: return launch_screen<4, 4, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
-            case 6: return launch_screen<6, 6, 1>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
-            case 8: return launch_screen<8, 4, 1>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st);
+            case 1: rc = launch_screen<1, 8, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st); break;
+            case 2: rc = launch_screen<2, 8, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st); break;
+            case 3: rc = launch_screen<3, 6, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st); break;
+            case 4: rc = launch_screen<4, 4, 2>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st); break;
+            case 6: rc = launch_screen<6, 6, 1>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st); break;
+            case 8: rc = launch_screen<8, 4, 1>(tz, thi, e_norm2, N, K, idx, hist, counter, fr, ready, st); break;
             default: break;
         }
+        if (rc >= 0) {
+            if (rc != VQ_OK || !split) return rc;
+            rows_done = true;           // indices are in place: fall through to the rows kernel
+        }
     }
-    if (tensor_path_ok(N, K, D, flags, z, E_hi, E_lo, true)) {
+    if (rows_done) {
+        // nothing: the screen kernel produced idx
+    } else if (tensor_path_ok(N, K, D, flags, z, E_hi, E_lo, true)) {
         const long long row_tiles = (N + TC_ROWS - 1) / TC_ROWS;
         const bool pair = (K % TC2_CODES == 0) && !(flags & VQ_FLAG_TC_1CTA);
         // CTA pairs: a wave is 74 pairs, each covering 256 rows x 256 codes per tile
@@ -624,7 +651,20 @@ int vq_onehot(const int32_t* idx, int64_t n_rows, int K, float* onehot, vq_strea
 namespace {
 
 // ---- backward strategy ------------------------------------------------------------
-enum BwdPath { BWD_FLAT = 0, BWD_PRIVATE = 2 };
+enum BwdPath { BWD_FLAT = 0, BWD_PRIVATE = 2, BWD_REPLICATED = 3 };
+
+// Flat kernel with its reds spread over R zeroed copies of dE (folded into dE by a second small launch): R such that
+// the copies together hold ~128 k 16-byte addresses, where the scatter stops being bound by same-address queueing in L2.
+// Needs scratch (vq_step_backward: the tail of the forward's workspace, dead once the forward is complete) and enough
+// rows per code for the queueing to matter.  1 = not applicable.
+constexpr long long kReplAddrTarget = 131072;
+int repl_factor(long long N, int K, int D, int flags, bool vec) {
+    if (!vec || (flags & (VQ_FLAG_BWD_FLAT | VQ_FLAG_BWD_PRIVATE))) return 1;
+    const long long addr = static_cast<long long>(K) * (D / 4);
+    if (addr >= kReplAddrTarget / 2 || N < 262144 || N < 64ll * K) return 1;
+    long long r = kReplAddrTarget / addr;
+    return static_cast<int>(r > 32 ? 32 : r);
+}
 
 // columns per lane of the private kernel (0: does not apply) -- the CTA's share of dE must fit shared memory
 int private_nc(int K, int D) {
@@ -668,12 +708,13 @@ int run_private(const float* g_q, const float* g_loss, const float* z, const flo
 extern "C" {
 
 int vq_backward_path(int64_t n_rows, int K, int D, int flags) {
+    if (repl_factor(n_rows, K, D, flags, D % 4 == 0) > 1) return BWD_REPLICATED;     // vq_step_backward (has the workspace)
     return choose_bwd_path(n_rows, K, D, flags, D % 4 == 0);
 }
 
 static int backward_impl(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx,
                          int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags, float* dz,
-                         float* dE, const unsigned int* ready, vq_stream_t stream) {
+                         float* dE, const unsigned int* ready, float* repl, size_t repl_bytes, vq_stream_t stream) {
     if (int rc = check_device()) return rc;
     const long long N = n_rows;
     const bool train = (flags & VQ_FLAG_TRAIN_VQ) != 0 && dE != nullptr;
@@ -690,8 +731,11 @@ static int backward_impl(const float* g_q, const float* g_loss, const float* z, 
     const float denom_dE = static_cast<float>(static_cast<double>(n_rows_dE) * static_cast<double>(D));
     const bool vec = (D % 4 == 0) && aligned16(z) && aligned16(E) && (dz == nullptr || aligned16(dz)) && (g_q == nullptr || aligned16(g_q)) &&
                      (!train || aligned16(dE));
-    const int path = train ? choose_bwd_path(N, K, D, flags, vec) : BWD_FLAT;
+    int n_repl = (train && dz != nullptr && repl != nullptr && aligned16(repl)) ? repl_factor(N, K, D, flags, vec) : 1;
+    if (n_repl > 1 && static_cast<size_t>(n_repl) * K * D * sizeof(float) > repl_bytes) n_repl = 1;
+    const int path = !train ? BWD_FLAT : (n_repl > 1 ? BWD_REPLICATED : choose_bwd_path(N, K, D, flags, vec));
     if (zero_dE) CUDA_TRY(cudaMemsetAsync(dE, 0, sizeof(float) * static_cast<size_t>(K) * D, st));
+    if (n_repl > 1) CUDA_TRY(cudaMemsetAsync(repl, 0, sizeof(float) * static_cast<size_t>(n_repl) * K * D, st));
     if (path == BWD_PRIVATE) {
         const int nc = private_nc(K, D);
         if (g_q != nullptr)
@@ -716,7 +760,8 @@ static int backward_impl(const float* g_q, const float* g_loss, const float* z, 
     if (g > kNumSMs * 32) g = kNumSMs * 32;
     const int grid = static_cast<int>(g);
     ProfScope prof(KID_BACKWARD, st);
-#define BWD_ARGS g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, D, beta, dz, dE, ready
+    const long long repl_stride = static_cast<long long>(K) * D;
+#define BWD_ARGS g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, D, beta, dz, dE, ready, repl, n_repl, repl_stride
 #define BWD_LAUNCH(TR, GQ)                                                                                        \
     do {                                                                                                          \
         cudaError_t e__;                                                                                          \
@@ -731,13 +776,20 @@ static int backward_impl(const float* g_q, const float* g_loss, const float* z, 
 #undef BWD_LAUNCH
 #undef BWD_ARGS
     LAUNCH_CHECK("backward_kernel");
+    if (n_repl > 1) {
+        const long long n4 = repl_stride / 4;
+        long long gr = (n4 + 255) / 256;
+        if (gr > kNumSMs * 8) gr = kNumSMs * 8;
+        reduce_replicas_kernel<<<static_cast<unsigned>(gr), 256, 0, st>>>(repl, n_repl, n4, dE);
+        LAUNCH_CHECK("reduce_replicas_kernel");
+    }
     return VQ_OK;
 }
 
 int vq_backward(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx,
                 int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags, float* dz,
                 float* dE, vq_stream_t stream) {
-    return backward_impl(g_q, g_loss, z, E, idx, n_rows, n_rows_dz, n_rows_dE, K, D, beta, flags, dz, dE, nullptr, stream);
+    return backward_impl(g_q, g_loss, z, E, idx, n_rows, n_rows_dz, n_rows_dE, K, D, beta, flags, dz, dE, nullptr, nullptr, 0, stream);
 }
 
 // The backward launched RIGHT BEHIND vq_step_forward on the same stream and workspace (nothing in between): on the
@@ -745,27 +797,44 @@ int vq_backward(const float* g_q, const float* g_loss, const float* z, const flo
 // indices and everything else it reads are complete then -- and overlaps the forward's serial statistics tail.
 int vq_step_backward(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx,
                      int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags, float* dz,
-                     float* dE, const void* workspace, size_t workspace_bytes, int forward_flags, vq_stream_t stream) {
+                     float* dE, void* workspace, size_t workspace_bytes, int forward_flags, vq_stream_t stream) {
     const unsigned int* ready = nullptr;
     const int ff = forward_flags & ~VQ_FLAG_STATE_READY;
     const bool train = (flags & VQ_FLAG_TRAIN_VQ) != 0 && dE != nullptr;
     const bool vec = D % 4 == 0;
-    if (workspace != nullptr && n_rows > 0 && dz != nullptr && !(flags & VQ_FLAG_ZERO_DE) &&
+    // the tail of the forward's workspace (per-row keys / spill lists) is dead once the forward is complete: scratch for
+    // the replicated scatter (the kernel orders itself behind the forward before it touches it)
+    float* repl = nullptr;
+    size_t repl_bytes = 0;
+    if (workspace != nullptr && n_rows > 0 && train && repl_factor(n_rows, K, D, flags, vec) > 1) {
+        const WsLayout w = ws_layout(n_rows);
+        if (workspace_bytes >= w.total) {
+            repl = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + w.keys_off);
+            repl_bytes = w.total - w.keys_off;
+        }
+    }
+    if (repl == nullptr && workspace != nullptr && n_rows > 0 && dz != nullptr && !(flags & VQ_FLAG_ZERO_DE) &&
         screen_path_ok(n_rows, K, D, ff, z, E, nullptr, nullptr) && ((ff & VQ_FLAG_SCREEN) || screen_enabled()) &&
+        !screen_split_rows(n_rows, K, D, ff) &&       // (the rows kernel behind the screen kernel never raises the ready word)
         (!train || choose_bwd_path(n_rows, K, D, flags, vec) == BWD_FLAT)) {
         const WsLayout w = ws_layout(n_rows);
         if (workspace_bytes < w.total) return fail(VQ_ERR_WORKSPACE, "vq_step_backward: workspace %zu B < %zu B", workspace_bytes, w.total);
         ready = reinterpret_cast<const unsigned int*>(static_cast<const uint8_t*>(workspace) + w.counter_off) + 2;
     }
-    return backward_impl(g_q, g_loss, z, E, idx, n_rows, n_rows_dz, n_rows_dE, K, D, beta, flags, dz, dE, ready, stream);
+    return backward_impl(g_q, g_loss, z, E, idx, n_rows, n_rows_dz, n_rows_dE, K, D, beta, flags, dz, dE, ready, repl, repl_bytes, stream);
 }
 
 // =========================================================================================================
 // data parallel: sum all-reduce of the packed step buffer [dE | usage histogram | squared error] over NVLink peer memory
 // =========================================================================================================
+constexpr int DP_EVENTS = 16;
 struct vq_dp_ctx {
     DpCtxDev dev;
     int device;
+    // overlapped form (vq_dp_allreduce_start / vq_dp_wait): a stream of the context's own and a small ring of events
+    cudaStream_t side;
+    cudaEvent_t fork_ev[DP_EVENTS], done_ev[DP_EVENTS];
+    unsigned long long started, joined;      // exchanges started on `side` / exchanges the caller's stream already waits for
 };
 
 int vq_dp_create(const void* const* recv0, const void* const* recv1, void* multicast0, void* multicast1, int world, int rank,
@@ -804,12 +873,33 @@ int vq_dp_create(const void* const* recv0, const void* const* recv1, void* multi
         delete c;
         return fail(VQ_ERR_CUDA, "vq_dp_create: %s", cudaGetErrorString(e));
     }
+    // the exchange stream outranks the compute stream: its CTAs (256 threads, no dynamic shared memory) slot in next to the
+    // forward's as soon as they are launched
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi);
+    for (int i = 0; i < DP_EVENTS && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&c->fork_ev[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done_ev[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        vq_dp_destroy(c);
+        return fail(VQ_ERR_CUDA, "vq_dp_create: %s", cudaGetErrorString(e));
+    }
     *out = c;
     return VQ_OK;
 }
 
 void vq_dp_destroy(vq_dp_ctx* c) {
     if (c == nullptr) return;
+    if (c->side != nullptr) {
+        cudaStreamSynchronize(c->side);
+        cudaStreamDestroy(c->side);
+    }
+    for (int i = 0; i < DP_EVENTS; ++i) {
+        if (c->fork_ev[i] != nullptr) cudaEventDestroy(c->fork_ev[i]);
+        if (c->done_ev[i] != nullptr) cudaEventDestroy(c->done_ev[i]);
+    }
     cudaFree(c->dev.state);
     delete c;
 }
@@ -839,6 +929,44 @@ int vq_dp_allreduce(vq_dp_ctx* c, const float* payload, float* out, vq_stream_t 
     const cudaError_t e = launch_pdl(dp_allreduce_kernel, dim3(static_cast<unsigned>(blocks)), dim3(DP_THREADS), 0, st, c->dev, payload, out);
     if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of dp_allreduce_kernel failed: %s", cudaGetErrorString(e));
     LAUNCH_CHECK("dp_allreduce_kernel");
+    return VQ_OK;
+}
+
+// Overlapped form.  The exchange is ordered behind everything enqueued on `stream` so far but runs on the context's own
+// stream, so `stream` carries on at once: the next step's codebook preparation and forward overlap the NVLink transfer
+// and absorb the ranks' skew (in training: the encoder's backward does, as under DDP).  Plain launch (full dependencies:
+// the kernel's griddepcontrol instructions are no-ops then) -- the fork and join are event edges, which a stream capture
+// turns into graph edges.
+int vq_dp_allreduce_start(vq_dp_ctx* c, const float* payload, float* out, vq_stream_t stream) {
+    if (c == nullptr || payload == nullptr || out == nullptr) return fail(VQ_ERR_ARG, "vq_dp_allreduce_start: null");
+    if (!aligned16(out)) return fail(VQ_ERR_ARG, "vq_dp_allreduce_start: out is misaligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int slot = static_cast<int>(c->started % DP_EVENTS);
+    CUDA_TRY(cudaEventRecord(c->fork_ev[slot], st));
+    CUDA_TRY(cudaStreamWaitEvent(c->side, c->fork_ev[slot], 0));
+    long long blocks = (c->dev.L + DP_THREADS - 1) / DP_THREADS;
+    const int cap = sm_count();
+    if (blocks > cap) blocks = cap;
+    {
+        ProfScope prof(KID_ALLREDUCE, c->side);
+        dp_allreduce_kernel<<<static_cast<unsigned>(blocks), DP_THREADS, 0, c->side>>>(c->dev, payload, out);
+        LAUNCH_CHECK("dp_allreduce_kernel");
+    }
+    CUDA_TRY(cudaEventRecord(c->done_ev[slot], c->side));
+    c->started++;
+    return VQ_OK;
+}
+
+// `stream` waits for every exchange started so far except the `keep_in_flight` most recent ones (exchanges complete in
+// the order they were started).  keep_in_flight = 0 before the results are read, before the context is destroyed and
+// before a stream capture ends (a forked stream must rejoin); 1 inside a double-buffered step loop.
+int vq_dp_wait(vq_dp_ctx* c, int keep_in_flight, vq_stream_t stream) {
+    if (c == nullptr || keep_in_flight < 0 || keep_in_flight >= DP_EVENTS) return fail(VQ_ERR_ARG, "vq_dp_wait: bad argument (keep_in_flight < %d)", DP_EVENTS);
+    const unsigned long long keep = static_cast<unsigned long long>(keep_in_flight);
+    if (c->started <= keep || c->started - keep <= c->joined) return VQ_OK;
+    const unsigned long long upto = c->started - keep;                  // exchanges [joined, upto) must be complete
+    CUDA_TRY(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), c->done_ev[(upto - 1) % DP_EVENTS], 0));
+    c->joined = upto;
     return VQ_OK;
 }
 

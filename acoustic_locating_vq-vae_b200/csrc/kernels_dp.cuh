@@ -105,6 +105,9 @@ struct DpWaiter {
                 }
                 return false;
             }
+            // back off once the line is clearly not about to land: thousands of threads polling at full rate cost the kernels
+            // the exchange overlaps with (vq_dp_allreduce_start) a visible share of the L2 request bandwidth
+            if (polls > 16u) __nanosleep(polls > 64u ? 400u : 100u);
             v = ld_volatile_v4(p);
         }
         return true;

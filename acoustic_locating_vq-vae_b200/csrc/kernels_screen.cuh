@@ -737,7 +737,7 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
             for (int r = wt; r < rows_here; r += NW) {
                 const int code = g_idx[r];
                 idx_out[row0 + r] = code;
-                atomicAdd(fr.hist + code, 1.0f);
+                if (!fr.rows_later) atomicAdd(fr.hist + code, 1.0f);
             }
             // -- q_out = fl(z + fl(E[idx] - z)), sse += (E[idx] - z)^2 ---------------------------------------------
             if (quant) {
@@ -782,7 +782,8 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
         }
         if (wt_all == 0) VQ_TR(6, 2);
         // per-CTA SSE partial, then last-CTA-done reduction in a fixed order (+ loss / perplexity)
-        publish_and_finalize(fr, sse, N, K, D, wt_all, NW_all, lane, have_oh ? warp - 13 : warp - 12, have_oh ? 3 : 4, red, 7);
+        // (rows_later: the rows kernel behind this one owns the completion counter and the statistics)
+        if (!fr.rows_later) publish_and_finalize(fr, sse, N, K, D, wt_all, NW_all, lane, have_oh ? warp - 13 : warp - 12, have_oh ? 3 : 4, red, 7);
     }
 
     if (threadIdx.x == 0) VQ_TR(7, 1);

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) argmin_simt_kernel(const float* __restric
 // The last CTA to finish reduces the per-CTA partial sums in a fixed order and (unless deferred)
 // writes loss and perplexity, so a single-GPU forward needs no further launch.
 // ---------------------------------------------------------------------------------------------
-constexpr int ROWS_MAX_R = 64;
+constexpr int ROWS_MAX_R = 256;
 
 template <bool ONEHOT, bool QUANT, int VEC>
 __global__ void __launch_bounds__(256) quantize_rows_kernel(
@@ -222,18 +222,40 @@ __global__ void __launch_bounds__(256) quantize_rows_kernel(
         __syncthreads();
         if (QUANT) {
             const int n_el = rows_here * DV;
-            for (int e = threadIdx.x; e < n_el; e += 256) {
+            if (VEC == 4) {
+                // rows are contiguous: element e of the group sits at float4 offset row0 * DV + e.  Four independent
+                // 16-byte elements (z and E[idx]) in flight per thread; sse accumulates in element order per thread.
+                const float4* z4 = reinterpret_cast<const float4*>(z) + row0 * DV;
+                float4* q4 = reinterpret_cast<float4*>(q_out) + row0 * DV;
+                for (int e0 = threadIdx.x; e0 < n_el; e0 += 4 * 256) {
+                    float4 zv[4], ev[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = e0 + u * 256;
+                        if (e < n_el) {
+                            const int rr = e / DV, c = e - rr * DV;
+                            zv[u] = __ldcs(z4 + e);
+                            ev[u] = __ldg(reinterpret_cast<const float4*>(E + static_cast<size_t>(s_idx[rr]) * D) + c);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = e0 + u * 256;
+                        if (e < n_el) {
+                            float4 df, qv;
+                            df.x = ev[u].x - zv[u].x; df.y = ev[u].y - zv[u].y; df.z = ev[u].z - zv[u].z; df.w = ev[u].w - zv[u].w;
+                            qv.x = zv[u].x + df.x; qv.y = zv[u].y + df.y; qv.z = zv[u].z + df.z; qv.w = zv[u].w + df.w;
+                            __stcs(q4 + e, qv);
+                            sse = fmaf(df.x, df.x, sse); sse = fmaf(df.y, df.y, sse);
+                            sse = fmaf(df.z, df.z, sse); sse = fmaf(df.w, df.w, sse);
+                        }
+                    }
+                }
+            }
+            for (int e = threadIdx.x; VEC != 4 && e < n_el; e += 256) {
                 const int rr = e / DV, c = e - rr * DV;
                 const int code = s_idx[rr];
                 if (VEC == 4) {
-                    const float4 zv = __ldcs(reinterpret_cast<const float4*>(z + (row0 + rr) * D) + c);
-                    const float4 ev = __ldg(reinterpret_cast<const float4*>(E + static_cast<size_t>(code) * D) + c);
-                    float4 df, qv;
-                    df.x = ev.x - zv.x; df.y = ev.y - zv.y; df.z = ev.z - zv.z; df.w = ev.w - zv.w;
-                    qv.x = zv.x + df.x; qv.y = zv.y + df.y; qv.z = zv.z + df.z; qv.w = zv.w + df.w;
-                    __stcs(reinterpret_cast<float4*>(q_out + (row0 + rr) * D) + c, qv);
-                    sse = fmaf(df.x, df.x, sse); sse = fmaf(df.y, df.y, sse);
-                    sse = fmaf(df.z, df.z, sse); sse = fmaf(df.w, df.w, sse);
                 } else {
                     const float zv = z[(row0 + rr) * D + c];
                     const float df = __ldg(E + static_cast<size_t>(code) * D + c) - zv;
@@ -381,7 +403,12 @@ __global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__
                                                        const float* __restrict__ z, const float* __restrict__ E,
                                                        const int* __restrict__ idx, long long N, float denom_dz,
                                                        float denom_dE, int D, float beta, float* __restrict__ dz,
-                                                       float* __restrict__ dE, const unsigned int* ready) {
+                                                       float* __restrict__ dE, const unsigned int* ready,
+                                                       float* __restrict__ repl, int n_repl, long long repl_stride) {
+    // n_repl > 1: the CTAs spread their reds over n_repl zeroed copies of dE (reduce_replicas_kernel folds them into dE
+    // afterwards).  With few codes the flat scatter is bound by reds queueing on the same L2 addresses (N * D / 4 reds on
+    // K * D / 4 addresses: 60 - 90 G reds/s below 64 k addresses against >= 120 G/s, i.e. HBM-bound, above).
+    if (TRAIN_VQ && n_repl > 1) dE = repl + static_cast<size_t>(blockIdx.x % static_cast<unsigned>(n_repl)) * repl_stride;
     pdl_launch_dependents();
     // ready != NULL (vq_step_backward right behind the fused forward): start as soon as the forward's last CTA has raised
     // the workspace's ready word -- everything this kernel reads is complete then; the forward's serial statistics tail
@@ -434,6 +461,18 @@ __global__ void __launch_bounds__(256) backward_kernel(const float* __restrict__
     }
     // order this kernel behind the forward's completion before it exits: "previous kernel complete" stays transitive
     if (ready != nullptr) pdl_wait_prior_grids();
+}
+
+// dE += sum of the n_repl copies the backward spread its reds over (16-byte elements; fixed order over the copies)
+__global__ void __launch_bounds__(256) reduce_replicas_kernel(const float* __restrict__ repl, int n_repl, long long n4, float* __restrict__ dE) {
+    for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * 256) {
+        float4 a = reinterpret_cast<const float4*>(dE)[i];
+        for (int r = 0; r < n_repl; ++r) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(repl) + static_cast<long long>(r) * n4 + i);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        reinterpret_cast<float4*>(dE)[i] = a;
+    }
 }
 
 // codebook gradient only (vq_backward with dz == NULL): dE[idx] += ce * (E[idx] - z)

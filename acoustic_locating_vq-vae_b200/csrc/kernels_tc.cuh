@@ -308,6 +308,8 @@ struct FusedRowArgs {
     float beta;
     int finalize;              // 0 under VQ_FLAG_DEFER_STATS
     int onehot_evict_first;    // 1: one-hot stores carry an L2 evict_first policy (tuning knob)
+    int rows_later;            // screen kernel: indices only -- usage counts, q_out, SSE, loss / perplexity are left to
+                               // quantize_rows_kernel behind it (few code tiles per item: the row workers would set the pace)
     int4* spill;               // screen kernel: [grid][4][SC_SPILL] {row, score, code | chain-instance, type} (workspace)
     long long* trace;          // VQ_TRACE builds only: [cta][role 0..7][64] clock64 stamps
 };

@@ -40,18 +40,25 @@ struct VQFunction : public torch::autograd::Function<VQFunction> {
         at::Tensor idx = at::empty({N}, opts.dtype(at::kInt));
         at::Tensor loss = at::empty({}, opts), perplexity = at::empty({}, opts);
         const int64_t off = pack ? K * D : 0;
+        // the codebook gradient's accumulator is zeroed by the forward's prepare launch (no memset in front of the backward):
+        // the front of the packed buffer under data parallelism, a buffer of its own otherwise
+        const bool will_train = train_vq && weight.requires_grad();     // (grad mode is off inside Function::forward)
         at::Tensor stats = at::empty({off + K + 1}, opts);
+        at::Tensor dE_acc = (will_train && !pack) ? at::empty({K, D}, opts) : at::Tensor();
+        float* dE_zero = pack ? stats.data_ptr<float>() : fptr(dE_acc);
         at::Tensor reduced = at::empty({pack ? K * D + K + 1 : 0}, opts);
         at::Tensor onehot = at::empty({want_onehot ? N : 0, want_onehot ? K : 0}, opts);
         float* sp = stats.data_ptr<float>() + off;
         check(vq_step_forward(inputs.data_ptr<float>(), w.data_ptr<float>(), N, static_cast<int>(K), static_cast<int>(D), static_cast<float>(beta),
-                              static_cast<int>(flags) | (want_onehot ? VQ_FLAG_ONEHOT : 0), fptr(e_norm2), fptr(e_hi), fptr(e_lo), nullptr,
+                              static_cast<int>(flags) | (want_onehot ? VQ_FLAG_ONEHOT : 0), fptr(e_norm2), fptr(e_hi), fptr(e_lo), dE_zero,
                               q_out.data_ptr<float>(), idx.data_ptr<int>(), want_onehot ? onehot.data_ptr<float>() : nullptr, sp, sp + K,
                               loss.data_ptr<float>(), perplexity.data_ptr<float>(), ws.data_ptr(), static_cast<size_t>(ws.numel()), stream),
               "vq_step_forward");
         ctx->save_for_backward({inputs, weight, idx});
         ctx->saved_data["stats"] = stats;
         ctx->saved_data["reduced"] = reduced;
+        ctx->saved_data["dE_acc"] = dE_acc;
+        ctx->saved_data["dE_fresh"] = true;       // the accumulator is zero until the first backward has used it
         ctx->saved_data["beta"] = beta;
         ctx->saved_data["train_vq"] = train_vq;
         ctx->saved_data["world"] = world;
@@ -96,10 +103,15 @@ struct VQFunction : public torch::autograd::Function<VQFunction> {
             out[0] = dz;
             return out;
         }
+        // a second backward through the same graph (retain_graph) finds the accumulator used: zero it with a memset then
+        const bool fresh = ctx->saved_data["dE_fresh"].toBool();
+        ctx->saved_data["dE_fresh"] = false;
         if (world == 1 || !pack) {
-            dE = at::empty({K, D}, opts);
+            dE = ctx->saved_data["dE_acc"].toTensor();
+            const bool zeroed = fresh && dE.defined();
+            if (!zeroed) dE = at::empty({K, D}, opts);
             check(vq_backward(fptr(g_q), g_loss.data_ptr<float>(), inputs.data_ptr<float>(), w.data_ptr<float>(), idx.data_ptr<int>(), N, n_dz, n_dE,
-                              static_cast<int>(K), static_cast<int>(D), static_cast<float>(beta), VQ_FLAG_TRAIN_VQ | VQ_FLAG_ZERO_DE, fptr(dz),
+                              static_cast<int>(K), static_cast<int>(D), static_cast<float>(beta), VQ_FLAG_TRAIN_VQ | (zeroed ? 0 : VQ_FLAG_ZERO_DE), fptr(dz),
                               dE.data_ptr<float>(), stream),
                   "vq_backward");
             out[0] = dz;
@@ -108,7 +120,7 @@ struct VQFunction : public torch::autograd::Function<VQFunction> {
         }
         // data parallel: dE lands in front of the statistics the forward left in the packed buffer; ONE all-reduce
         check(vq_backward(fptr(g_q), g_loss.data_ptr<float>(), inputs.data_ptr<float>(), w.data_ptr<float>(), idx.data_ptr<int>(), N, n_dz, n_dE,
-                          static_cast<int>(K), static_cast<int>(D), static_cast<float>(beta), VQ_FLAG_TRAIN_VQ | VQ_FLAG_ZERO_DE, fptr(dz),
+                          static_cast<int>(K), static_cast<int>(D), static_cast<float>(beta), VQ_FLAG_TRAIN_VQ | (fresh ? 0 : VQ_FLAG_ZERO_DE), fptr(dz),
                           packed.data_ptr<float>(), stream),
               "vq_backward");
         out[0] = dz;

@@ -258,6 +258,8 @@ def main():
     ap.add_argument("--no-screen", action="store_true", help="3xTF32 tensor kernels instead of screen + exact refine (VQ_FLAG_NO_SCREEN)")
     ap.add_argument("--graph", action="store_true", help="N = 1: replay the step from CUDA graphs (default there: eager launches chained by programmatic dependent launch)")
     ap.add_argument("--no-graph", action="store_true", help="N > 1: eager launches (default there: CUDA graphs, which keep the ranks' launch jitter out of the exchange)")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: the exchange in line on the step's stream instead of overlapped with the next step's forward")
+    ap.add_argument("--emulate-dp", action="store_true", help="experiment, N = 1: the data-parallel step structure with a world-of-one exchange context")
     ap.add_argument("--nccl", action="store_true", help="N > 1: NCCL all_reduce of [dE|hist|sse] after the backward instead of the NVLink exchange")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -315,7 +317,7 @@ def main():
     peaks = load_peaks()
     P = lambda t: None if t is None else t.data_ptr()
 
-    def make_state(N, K, D, onehot_on, nbuf, seed):
+    def make_state(N, K, D, onehot_on, nbuf, seed, nsets=2):
         """device buffers of one workload; inputs rotate over `nbuf` z / g_q buffers"""
         g = torch.Generator(device=dev)
         g.manual_seed(seed)
@@ -329,19 +331,22 @@ def main():
         s["onehot"] = torch.empty(N, K, device=dev) if onehot_on else None
         # the packed step buffer [dE (K*D) | hist (K) | sse] + loss, perplexity: the forward writes the statistics and
         # the backward the gradient straight into it, so data parallel all-reduces it as it stands
-        s["packed"] = torch.zeros(K * D + K + 3, device=dev)
+        # `nsets` sets, rotating over the steps under data parallelism: the exchange of step i runs on its own stream while
+        # the following steps already fill the other sets
+        s["packs"] = [torch.zeros(K * D + K + 3, device=dev) for _ in range(nsets)]
+        s["reds"] = [torch.zeros(K * D + K + 1, device=dev) for _ in range(nsets)]   # data parallel: the all-reduced packed buffers
+        s["packed"], s["reduced"] = s["packs"][0], s["reds"][0]
         s["stats"] = s["packed"][K * D:]                                # [hist (K) | sse | loss | perplexity]
         s["dE"] = s["packed"][:K * D].view(K, D)
         s["dz"] = torch.empty(N, D, device=dev)
         s["g_loss"] = torch.ones((), device=dev)
-        s["reduced"] = torch.zeros(K * D + K + 1, device=dev)           # data parallel: the all-reduced packed buffer
         s["wsb"] = lib.vq_workspace_bytes(N, K, D, 0)
         s["ws"] = torch.empty(s["wsb"], dtype=torch.uint8, device=dev)
         s["fwd_flags"] = (L.FLAG_ONEHOT if onehot_on else 0) | (L.FLAG_EXACT if args.exact else 0) | (L.FLAG_NO_SCREEN if args.no_screen else 0)
         return s
 
     nbuf = max(3, int(1.25 * L2_BYTES / (N * D * 4)) + 1)                # rotating inputs: set larger than L2
-    S0 = make_state(N, K, D, emit_onehot, nbuf, 1000 + rank)
+    S0 = make_state(N, K, D, emit_onehot, nbuf, 1000 + rank, nsets=min(nbuf, 15) if (world > 1 or args.emulate_dp) else 1)
     n_packed = K * D + K + 1
     exch = None
     collective = "none"
@@ -359,27 +364,68 @@ def main():
             collective = f"NCCL all_reduce (NVLink exchange unavailable on some rank{': ' + why if why else ''})"
         else:
             collective = ("[dE | hist | sse] over NVLink peer memory (vq_dp_allreduce, " + ("NVLS multimem.st" if exch.nvls else "P2P stores") + ", "
-                          + ("reduce-scatter + all-gather" if world >= 8 else "one step") + ", device-side sequence numbers)")
+                          + ("reduce-scatter + all-gather" if world >= 8 else "one step") + ", device-side sequence numbers"
+                          + ("" if args.no_overlap else "; started on the exchange's own stream behind the backward (vq_dp_allreduce_start), payload / result buffers rotate over "
+                             f"{len(S0['packs'])} sets and the step stream joins the exchanges at the end of every graph: the following steps overlap the transfer, "
+                             "every exchange completes inside the timed region") + ")")
     elif world > 1:
         collective = "NCCL all_reduce of [dE | hist | sse] after the backward"
+    elif args.emulate_dp:
+        # experiment (one GPU): the data-parallel step structure with a world-of-one exchange context -- the launch
+        # structure (fork / join, graph edges, kernel co-residency) without NVLink or a second rank
+        class _Solo:
+            nvls = False
+
+            def __init__(self):
+                lines = int(lib.vq_dp_recv_lines(1, n_packed))
+                self.bufs = [torch.zeros(lines * 4, device=dev) for _ in range(2)]
+                arr = [(ctypes.c_void_p * 1)(b.data_ptr()) for b in self.bufs]
+                self.ctx = ctypes.c_void_p()
+                L.check(lib.vq_dp_create(arr[0], arr[1], None, None, 1, 0, n_packed, 0, ctypes.byref(self.ctx)))
+
+            def status(self, st):
+                calls, err = ctypes.c_uint32(0), ctypes.c_uint32(0)
+                L.check(lib.vq_dp_status(self.ctx, ctypes.byref(calls), ctypes.byref(err), st))
+                return calls.value, err.value
+
+            def close(self):
+                if self.ctx is not None:
+                    lib.vq_dp_destroy(self.ctx)
+                    self.ctx = None
+        exch = _Solo()
+        collective = "EMULATION: world-of-one exchange context on a single GPU (launch structure only)"
     n_dE_scale = world
+
+    overlap = exch is not None and not args.no_overlap
 
     def step(s, i, st):
         """one step of the hot path on input buffer i, enqueued on raw stream `st`"""
         N_, K_, D_ = s["N"], s["K"], s["D"]
         z, gq = s["zs"][i % s["nbuf"]], s["gs"][i % s["nbuf"]]
-        sp = P(s["stats"])
+        ns = len(s["packs"])
+        par = (i % ns) if overlap else 0
+        pk = P(s["packs"][par])                      # [dE (K*D) | hist (K) | sse | loss | perplexity]
+        sp = pk + 4 * K_ * D_
+        if overlap:                                  # the exchange of step i - ns has left this set of buffers (a graph of <= ns
+            L.check(lib.vq_dp_wait(exch.ctx, ns - 1, st))     # steps never gets here: its only join is the final one)
         # the prepare launch also zeroes the dE accumulator: no memset node between forward and backward (PDL chain intact)
-        L.check(lib.vq_step_forward(P(z), P(s["E"]), N_, K_, D_, BETA, s["fwd_flags"], P(s["e2"]), P(s["ehi"]), P(s["elo"]), P(s["dE"]), P(s["q"]), P(s["idx"]),
+        L.check(lib.vq_step_forward(P(z), P(s["E"]), N_, K_, D_, BETA, s["fwd_flags"], P(s["e2"]), P(s["ehi"]), P(s["elo"]), pk, P(s["q"]), P(s["idx"]),
                                     P(s["onehot"]), sp, sp + 4 * K_, sp + 4 * (K_ + 1), sp + 4 * (K_ + 2), P(s["ws"]), s["wsb"], st))
         n_dE = N_ * n_dE_scale
         # right behind the forward: starts on the workspace's ready word and overlaps the forward's statistics tail
         L.check(lib.vq_step_backward(P(gq), P(s["g_loss"]), P(z), P(s["E"]), P(s["idx"]), N_, N_, n_dE, K_, D_, BETA, L.FLAG_TRAIN_VQ,
-                                     P(s["dz"]), P(s["dE"]), P(s["ws"]), s["wsb"], s["fwd_flags"], st))
-        if exch is not None:            # data parallel: ONE sum all-reduce of [dE | hist | sse]
-            L.check(lib.vq_dp_allreduce(exch.ctx, P(s["packed"]), P(s["reduced"]), st))
+                                     P(s["dz"]), pk, P(s["ws"]), s["wsb"], s["fwd_flags"], st))
+        if overlap:                     # data parallel: ONE sum all-reduce of [dE | hist | sse], on the exchange's own stream --
+            L.check(lib.vq_dp_allreduce_start(exch.ctx, pk, P(s["reds"][par]), st))      # the next step's forward overlaps it
+        elif exch is not None:
+            L.check(lib.vq_dp_allreduce(exch.ctx, pk, P(s["reds"][par]), st))
         elif world > 1:
-            dist.all_reduce(s["packed"][:K_ * D_ + K_ + 1])
+            dist.all_reduce(s["packs"][par][:K_ * D_ + K_ + 1])
+
+    def join(st):
+        """every exchange started so far is complete before `st` goes on (end of a run, end of a capture)"""
+        if overlap:
+            L.check(lib.vq_dp_wait(exch.ctx, 0, st))
 
     def barrier():
         if world > 1:
@@ -392,7 +438,7 @@ def main():
     # GPU-bound, the host stays ahead and the PDL chain is never broken (68.8 vs 72.2 us).  Data parallel: graphs by default --
     # every rank's Python launch jitter otherwise turns into waiting inside the exchange (2 GPUs: 83.0 - 83.5 us replayed,
     # 83.2 - 90.7 us eager).
-    use_graph = (args.graph or (world > 1 and not args.no_graph)) and not (world > 1 and exch is None)   # NCCL stays eager
+    use_graph = (args.graph or ((world > 1 or args.emulate_dp) and not args.no_graph)) and not (world > 1 and exch is None)   # NCCL stays eager
     cur = torch.cuda.current_stream()
 
     def build_runner(s):
@@ -402,45 +448,53 @@ def main():
             def run_eager(k):
                 for i in range(k):
                     step(s, i, cur.cuda_stream)
-            return run_eager, 0
+                join(cur.cuda_stream)
+            run_eager.prime = lambda k: None
+            return run_eager, {}
         for i in range(min(3, nb)):          # warm every code path before capture (lazy attribute setting, descriptors)
             step(s, i, cur.cuda_stream)
+        join(cur.cuda_stream)
         torch.cuda.synchronize()
-        singles = []
         side = torch.cuda.Stream(device=dev)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            for i in range(nb):
-                g = torch.cuda.CUDAGraph()
+        graphs = {}
+
+        def capture(n):
+            """one graph holding steps 0 .. n-1 (programmatic edges inside, the exchange's fork / join edges under data parallelism)"""
+            torch.cuda.synchronize()
+            side.wait_stream(cur)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
                 with torch.cuda.graph(g, stream=side):
-                    step(s, i, torch.cuda.current_stream().cuda_stream)
-                singles.append(g)
-            whole = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(whole, stream=side):
-                for i in range(nb):
-                    step(s, i, torch.cuda.current_stream().cuda_stream)
-        cur.wait_stream(side)
-        torch.cuda.synchronize()
+                    for i in range(n):
+                        step(s, i, torch.cuda.current_stream().cuda_stream)
+                    join(torch.cuda.current_stream().cuda_stream)     # a forked stream rejoins before the capture ends
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            graphs[n] = g
+
+        def plan(k):
+            return [nb] * (k // nb) + ([k % nb] if k % nb else [])
 
         def run_graphs(k):
-            i = 0
-            while i < k:
-                if i % nb == 0 and k - i >= nb:
-                    whole.replay()
-                    i += nb
-                else:
-                    singles[i % nb].replay()
-                    i += 1
-        return run_graphs, len(singles) + 1
+            for n in plan(k):
+                if n not in graphs:          # only outside timed regions: the bench primes the sizes it needs
+                    capture(n)
+                graphs[n].replay()
+        run_graphs.prime = lambda k: [capture(n) for n in set(plan(k)) if n not in graphs]
+        run_graphs.graphs = graphs
+        return run_graphs, graphs
 
     run0, n_graphs = build_runner(S0)
     l0 = lib.vq_launch_count()
     step(S0, 0, cur.cuda_stream)
+    join(cur.cuda_stream)
     launches_per_step = lib.vq_launch_count() - l0
     barrier()
 
     sampler = ClockSampler(local_rank)
     # ---- device-resident throughput ------------------------------------------------------------------
+    run0.prime(args.warmup)
+    run0.prime(args.steps)
     run0(args.warmup)
     barrier()
     sampler.start()
@@ -466,6 +520,7 @@ def main():
         lib.vq_profile_enable(1)
         for i in range(reps):
             step(s, i, cur.cuda_stream)
+        join(cur.cuda_stream)
         barrier()
         kern = {}
         for kid, name in enumerate(KERNEL_NAMES):
@@ -534,6 +589,7 @@ def main():
         d1 = float((out - ref).abs().max())
         # the step's gradient: DP step vs NCCL all-reduce of the local gradients (same rows, same scale)
         step(S0, 0, cur.cuda_stream)
+        join(cur.cuda_stream)
         torch.cuda.synchronize()
         dE_dp = S0["reduced"][:K * D].view(K, D).clone()
         stats_dp = S0["reduced"][K * D:].clone()
@@ -613,6 +669,10 @@ def main():
                       + " back on the host)"}
         if full:
             out["encodings"] = "indices (N int32); the dense (N, K) one-hot is rebuilt by the caller (one store per row), not shipped over PCIe"
+        # tensors that were used on the lanes' streams (torch remembers the stream of every non-blocking copy and all-reduce)
+        # go before the streams do
+        res.clear(); lane_t.clear(); z_host.clear()
+        torch.cuda.synchronize()
         lib.vq_host_ctx_destroy(ctx)
         return out
 
@@ -644,7 +704,9 @@ def main():
             b.record(); torch.cuda.synchronize()
             t_step = a.elapsed_time(b) / reps * 1e3
             kk = profile(s, reps)
-            t_f = kk.get("forward", kk.get("argmin_exact", {"avg_us": float("nan")}))["avg_us"] + kk.get("prepare_codebook", {"avg_us": 0.0})["avg_us"]
+            # forward = prepare + fused forward (+ the rows kernel where the launcher splits the row epilogue off: small K)
+            t_f = (kk.get("forward", kk.get("argmin_exact", {"avg_us": float("nan")}))["avg_us"] + kk.get("prepare_codebook", {"avg_us": 0.0})["avg_us"]
+                   + kk.get("rows", {"avg_us": 0.0})["avg_us"])
             t_b = kk["backward"]["avg_us"]
             fl = 2.0 * SWEEP_N * k_ * d_
             bf, bb = fwd_bytes(SWEEP_N, k_, d_, False), bwd_bytes(SWEEP_N, k_, d_)
@@ -653,7 +715,8 @@ def main():
                                     "fwd_tflops": round(fl / (t_f * 1e-6) / 1e12, 1), "frac_fwd": round(fl / (t_f * 1e-6) / 1e12 / tf32_sus, 3),
                                     "bwd_frac_hbm": round(bb / (t_b * 1e-6) / 1e9 / peaks["hbm_gbs"], 3),
                                     "frac": round(t_roof * 1e6 / (t_f + t_b), 3), "vectors_per_s": round(SWEEP_N / (t_step * 1e-6)),
-                                    "backward_path": ["flat", "", "private"][lib.vq_backward_path(SWEEP_N, k_, d_, 0)]})
+                                    "backward_path": ["flat", "", "private"][lib.vq_backward_path(SWEEP_N, k_, d_, 0)],
+                                    "forward_kernels": sorted(n for n in kk if n not in ("backward", "exchange"))})
             del s
 
     # ---- the drop-in nn.Module on the same workload (north star: the module is the deliverable) ------------------
@@ -716,7 +779,7 @@ def main():
                       "f32 (tcgen05 TF32 screening pass + exact fp32 refine of the candidates: indices bit-exact vs the fp32 oracle)")),
             "data": "synthetic", "config": config,
             "notes": {"path": "tcgen05" if tensor_path else "exact CUDA-core",
-                      "launch": (f"CUDA graphs (one per round over the {nbuf} input buffers + single-step graphs for the remainder), {launches_per_step} kernels per step"
+                      "launch": (f"CUDA graphs (one per round over the {nbuf} input buffers + one for the remaining steps), {launches_per_step} kernels per step"
                                  if use_graph else f"eager launches chained by programmatic dependent launch, {launches_per_step} kernels per step"),
                       "l2": f"inputs rotate over {nbuf} z + {nbuf} g buffers ({2 * nbuf * N * D * 4 >> 20} MiB > 126 MiB L2)",
                       "collective": collective},
@@ -725,7 +788,7 @@ def main():
             "kernels": kern, "peaks": {"hbm_gbs": peaks["hbm_gbs"], "hbm_source": peaks["source"], "tf32": tf32}, "sweep": sweep, "module": module,
             "collective_check": coll_check, "loss": loss_val, "perplexity": perp_val,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if exch is not None:
         exch.close()
     if world > 1:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define VQ_ABI_VERSION 17
+#define VQ_ABI_VERSION 18
 
 /* error codes */
 #define VQ_OK            0
@@ -146,10 +146,13 @@ int vq_backward(const float* g_q, const float* g_loss, const float* z, const flo
 int vq_step_backward(const float* g_q, const float* g_loss, const float* z, const float* E,
                      const int32_t* idx, int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE,
                      int K, int D, float beta, int flags, float* dz, float* dE,
-                     const void* workspace, size_t workspace_bytes, int forward_flags, vq_stream_t stream);
-/* Which kernel vq_backward takes for dE (16-byte aligned pointers assumed): 0 flat (one red.global.add per element),
- * 2 private (per-CTA copy of dE in shared memory, flushed once; N >> K and K*D small).  dz may be NULL on path 2
- * (codebook gradient only). */
+                     void* workspace, size_t workspace_bytes, int forward_flags, vq_stream_t stream);
+/* Which kernel the backward takes for dE (16-byte aligned pointers assumed): 0 flat (one red.global.add per element),
+ * 2 private (per-CTA copy of dE in shared memory, flushed once; N >> K and K*D small; dz may be NULL: codebook gradient
+ * only), 3 replicated -- vq_step_backward only, which has scratch (the dead tail of the forward's workspace): the flat
+ * kernel with its reds spread over R zeroed copies of dE (R * K * D/4 ~ 128 k addresses) and a small launch that folds
+ * them into dE; taken when K * D/4 < 64 k addresses and N >= max(256 k, 64 K), where the flat scatter is bound by reds
+ * queueing on the same L2 addresses.  vq_backward (no scratch) takes 2 or 0 there. */
 int vq_backward_path(int64_t n_rows, int K, int D, int flags);
 
 /* -- the consumer of `encodings` as an index gather ------------------------------------ */
@@ -195,6 +198,16 @@ int  vq_dp_create(const void* const* recv0, const void* const* recv1, void* mult
 void vq_dp_destroy(vq_dp_ctx* ctx);
 /* out[i] = sum over ranks of payload[i], i < n_floats (payload: written by earlier work on `stream`). */
 int  vq_dp_allreduce(vq_dp_ctx* ctx, const float* payload, float* out, vq_stream_t stream);
+/* Overlapped form: the exchange is ordered behind everything enqueued on `stream` so far, but runs on a stream of the
+ * context's own, so `stream` carries on at once -- the next step's codebook preparation and forward overlap the NVLink
+ * transfer and absorb the ranks' skew (in training the encoder's backward does, as under DDP's bucketed all-reduce).
+ * vq_dp_wait makes `stream` wait for every exchange started so far except the keep_in_flight most recent ones
+ * (exchanges complete in the order they were started): keep_in_flight = S - 1 (< 16) at the top of a step whose
+ * payload / out buffers rotate over S sets, 0 before the results are read, before vq_dp_destroy and before a stream
+ * capture ends.  Fork and join are event edges, so a stream capture records them; a captured graph of S steps over S
+ * buffer sets needs no join but the final one, which leaves every programmatic-launch edge of the step chain intact. */
+int  vq_dp_allreduce_start(vq_dp_ctx* ctx, const float* payload, float* out, vq_stream_t stream);
+int  vq_dp_wait(vq_dp_ctx* ctx, int keep_in_flight, vq_stream_t stream);
 /* Synchronises `stream`; calls completed and the error word (bit 0: a wait expired). */
 int  vq_dp_status(vq_dp_ctx* ctx, uint32_t* calls_done, uint32_t* error_word, vq_stream_t stream);
 /* Test hook: `world` emulated ranks on ONE GPU in a single cooperative launch (blockIdx.y = rank), `rounds` calls back

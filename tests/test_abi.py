@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(lib):
     from importlib import import_module
     sigs = import_module("acoustic_locating_vq-vae_b200._lib").SIGNATURES
     assert sorted(sigs) == names, "ctypes binding and header disagree"
-    assert lib.vq_abi_version() == import_module("acoustic_locating_vq-vae_b200._lib").ABI_VERSION == 17
+    assert lib.vq_abi_version() == import_module("acoustic_locating_vq-vae_b200._lib").ABI_VERSION == 18
 
 
 def test_no_cpu_fallback(lib):

@@ -93,10 +93,53 @@ def test_paths_agree_with_oracle(lib, N, D, K):
 
 def test_default_path_choice(lib):
     assert lib.vq_backward_path(51456, 1024, 64, 0) == 0          # few rows per code: flat
-    assert lib.vq_backward_path(1 << 20, 512, 64, 0) == 2         # sweep, K*D small: private
-    assert lib.vq_backward_path(1 << 20, 1024, 64, 0) == 0        # measured slower than flat there
-    assert lib.vq_backward_path(1 << 20, 8192, 256, 0) == 0       # dE does not fit shared memory: flat
+    assert lib.vq_backward_path(1 << 20, 512, 64, 0) == 3         # sweep, few addresses: reds spread over copies of dE
+    assert lib.vq_backward_path(1 << 20, 512, 64, PRIVATE) == 2   # forced: per-CTA copy of dE in shared memory
+    assert lib.vq_backward_path(1 << 20, 1024, 64, 0) == 3
+    assert lib.vq_backward_path(1 << 20, 1024, 64, FLAT) == 0
+    assert lib.vq_backward_path(1 << 20, 8192, 256, 0) == 0       # many addresses: the flat scatter is HBM-bound
     assert lib.vq_backward_path(1000, 1000, 5, 0) == 0            # odd D: flat
+
+
+@pytest.mark.parametrize("N,D,K", [(300000, 64, 512), (262144, 128, 512), (270001, 64, 1024)])
+def test_step_pair_split_rows_and_replicated_scatter(lib, N, D, K):
+    """Large N with a small codebook: vq_step_forward runs the screen kernel for the indices and quantize_rows_kernel behind
+    it (row epilogue split off), vq_step_backward spreads its reds over copies of dE in the workspace's dead tail.  Indices
+    must equal the exact CUDA-core path's, dz the flat kernel's bit for bit, dE / loss / perplexity within tolerance; the
+    workspace must be reusable by the next forward (two steps back to back)."""
+    dev = _dev()
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.vq_backward_path(N, K, D, 0) == 3
+    E = torch.randn(K, D, device=dev)
+    e2 = torch.empty(K, device=dev); ehi = torch.empty_like(E); elo = torch.empty_like(E)
+    wsb = lib.vq_workspace_bytes(N, K, D, 0); ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    q = torch.empty(N, D, device=dev); idx = torch.empty(N, dtype=torch.int32, device=dev)
+    stats = torch.empty(K + 3, device=dev); sp = stats.data_ptr()
+    dz = torch.empty(N, D, device=dev); dE = torch.empty(K, D, device=dev)
+    gl = torch.tensor(0.7, device=dev)
+    for step in range(2):
+        z = torch.randn(N, D, device=dev); g = torch.randn(N, D, device=dev)
+        rc = lib.vq_step_forward(z.data_ptr(), E.data_ptr(), N, K, D, BETA, 0, e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(), dE.data_ptr(),
+                                 q.data_ptr(), idx.data_ptr(), None, sp, sp + 4 * K, sp + 4 * (K + 1), sp + 4 * (K + 2), ws.data_ptr(), wsb, st)
+        assert rc == 0, lib.vq_last_error()
+        rc = lib.vq_step_backward(g.data_ptr(), gl.data_ptr(), z.data_ptr(), E.data_ptr(), idx.data_ptr(), N, N, N, K, D, BETA, TRAIN,
+                                  dz.data_ptr(), dE.data_ptr(), ws.data_ptr(), wsb, 0, st)
+        assert rc == 0, lib.vq_last_error()
+        torch.cuda.synchronize()
+        # exact path (CUDA cores, oracle order) for the indices and the statistics
+        q2 = torch.empty_like(q); idx2 = torch.empty_like(idx); stats2 = torch.empty_like(stats); sp2 = stats2.data_ptr()
+        rc = lib.vq_step_forward(z.data_ptr(), E.data_ptr(), N, K, D, BETA, 1 << 2, e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(), None,
+                                 q2.data_ptr(), idx2.data_ptr(), None, sp2, sp2 + 4 * K, sp2 + 4 * (K + 1), sp2 + 4 * (K + 2), ws.data_ptr(), wsb, st)
+        assert rc == 0, lib.vq_last_error()
+        torch.cuda.synchronize()
+        assert torch.equal(idx, idx2), f"step {step}: {int((idx != idx2).sum())} rows differ"
+        assert torch.equal(q, q2)
+        assert torch.equal(stats[:K], stats2[:K])                                   # usage counts
+        assert abs(float(stats[K + 1]) - float(stats2[K + 1])) <= 1e-5 * float(stats2[K + 1])
+        assert abs(float(stats[K + 2]) - float(stats2[K + 2])) <= 1e-5 * float(stats2[K + 2])
+        dz_ref, dE_ref = _backward(lib, g, 0.7, z, E, idx, TRAIN | ZERO_DE | FLAT)
+        assert torch.equal(dz, dz_ref)
+        assert _rel(dE.cpu().numpy(), dE_ref.cpu().numpy()) <= 1e-5
 
 
 @pytest.mark.parametrize("path", [FLAT, PRIVATE])
