@@ -63,6 +63,7 @@ SIGNATURES = {
     "vq_dp_create": (_int, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _vp, _int, _int, _i64, ctypes.c_uint32, ctypes.POINTER(_vp)]),
     "vq_dp_destroy": (None, [_vp]),
     "vq_dp_allreduce": (_int, [_vp, _vp, _vp, _vp]),
+    "vq_step_backward_dp": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _int, _int, _f32, _int, _vp, _vp, _vp, _vp, _vp, _sz, _int, _vp]),
     "vq_dp_allreduce_start": (_int, [_vp, _vp, _vp, _vp]),
     "vq_dp_wait": (_int, [_vp, _int, _vp]),
     "vq_dp_status": (_int, [_vp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32), _vp]),

@@ -210,21 +210,17 @@ bool screen_path_ok(long long N, int K, int D, int flags, const float* z, const 
     return aligned16(z) && aligned16(E) && (!quant || aligned16(q_out)) && (!want_onehot || aligned16(onehot));
 }
 
-// Screen + refine with the row epilogue as a SECOND kernel (quantize_rows_kernel).  Fused, the 4 worker warps of a CTA
-// walk every item through a chain of latency-bound phases (refine, indices, usage counts, gather + q_out + SSE): about
-// 3.5 us + 0.07 us * D per 128-row item, whatever K is.  With many code tiles per item the tensor pipe / epilogue set the
-// pace and that work is hidden; with few (small K) the workers set it and a streaming kernel at HBM speed behind an
-// indices-only screen kernel is faster, although z is read twice.  Only without the dense one-hot (its zero-fill hides
-// everything else).  B200VQ_SPLIT_ROWS=0|1 forces either.
+// Screen + refine with the row epilogue as a SECOND kernel (quantize_rows_kernel behind an indices-only screen kernel):
+// an experiment, OFF unless B200VQ_SPLIT_ROWS=1.  The idea was that with few code tiles per item (small K) the four worker
+// warps set the pace; the per-role trace (tools/trace_fused.py, N = 1M, K = 512, D = 64) shows they do not -- a worker group
+// is done with an item 4.5 - 6.5 us after it gets it and the two groups alternate, while the epilogue publishes an item
+// every 5.2 - 6.2 us (2 x 1.45 us of scanning + ~1.1 us of per-item merge / handoff / barriers).  Measured: 393 vs 404 us
+// at (512, 64), slower everywhere else (z is read twice).
 bool screen_split_rows(long long N, int K, int D, int flags) {
+    (void)N; (void)K; (void)D;
     if ((flags & (VQ_FLAG_ONEHOT | VQ_FLAG_NO_QUANT)) != 0) return false;
-    static const int forced = [] { const char* e = getenv("B200VQ_SPLIT_ROWS"); return e == nullptr ? -1 : atoi(e); }();
-    if (forced >= 0) return forced != 0;
-    if (N < 64 * 1024) return false;                       // short launches: one kernel less is worth more
-    const double tile_us = D <= 64 ? 1.5 : (D <= 128 ? 1.6 : 3.2);          // per 256-code tile (epilogue- / MMA-bound)
-    const double fused_item = 3.5 + 0.07 * D, pipe_item = (K / 256) * tile_us + (D > 128 ? 4.0 : 0.0);
-    const double rows_item = 128.0 * (2 * D + 1) * 4 / 35e3;                // us per 128 rows at ~35 GB/s per SM
-    return (pipe_item > 3.0 ? pipe_item : 3.0) + rows_item < (fused_item > pipe_item ? fused_item : pipe_item) * 0.95;
+    static const bool forced = [] { const char* e = getenv("B200VQ_SPLIT_ROWS"); return e != nullptr && atoi(e) != 0; }();
+    return forced;
 }
 
 // number of codebook splits per row tile: fill the 148 SMs when there are few row tiles.
@@ -585,7 +581,10 @@ int vq_forward(const float* z, const float* E, const float* e_norm2, const float
     const int oh_vec_ok = want_onehot && (K % 4 == 0) && aligned16(onehot);
     const int fin = defer ? 0 : 1;
     const int R = rows_per_group(D, vec);
-    const int rgrid = rows_grid_for(N, R);
+    int rgrid = rows_grid_for(N, R);
+    // K <= 2048: the kernel keeps the usage counts per CTA in shared memory and flushes them once -- fewer, longer-lived
+    // CTAs mean fewer reds per code (four resident CTAs per SM still keep > 100 KB of loads in flight)
+    if (K <= 2048 && rgrid > kNumSMs * 4) rgrid = kNumSMs * 4;
     ProfScope prof_rows(KID_ROWS, st);
 #define ROWS_ARGS z, E, idx, keys, N, K, D, beta, q_out, idx, onehot, hist, partials, counter, sse, loss, perplexity, fin, R, oh_vec_ok
 #define ROWS_LAUNCH(OH, QU)                                                                      \
@@ -661,8 +660,8 @@ constexpr long long kReplAddrTarget = 131072;
 int repl_factor(long long N, int K, int D, int flags, bool vec) {
     if (!vec || (flags & (VQ_FLAG_BWD_FLAT | VQ_FLAG_BWD_PRIVATE))) return 1;
     const long long addr = static_cast<long long>(K) * (D / 4);
-    if (addr >= kReplAddrTarget / 2 || N < 262144 || N < 64ll * K) return 1;
-    long long r = kReplAddrTarget / addr;
+    if (addr >= kReplAddrTarget || N < 262144 || N < 256ll * K) return 1;
+    long long r = 2 * kReplAddrTarget / addr;            // >= 2; e.g. K = 1024, D = 256: 64 k addresses, 1024 reds each -> 4 copies
     return static_cast<int>(r > 32 ? 32 : r);
 }
 
@@ -749,8 +748,8 @@ static int backward_impl(const float* g_q, const float* g_loss, const float* z, 
         long long gb = (n_e + 255) / 256;
         if (gb > kNumSMs * 32) gb = kNumSMs * 32;
         ProfScope prof(KID_BACKWARD, st);
-        const cudaError_t e = vec ? launch_pdl(backward_dE_kernel<4>, dim3(static_cast<unsigned>(gb)), dim3(256), 0, st, g_loss, z, E, idx, N, denom_dE, D, dE)
-                                  : launch_pdl(backward_dE_kernel<1>, dim3(static_cast<unsigned>(gb)), dim3(256), 0, st, g_loss, z, E, idx, N, denom_dE, D, dE);
+        const cudaError_t e = vec ? launch_pdl(backward_dE_kernel<4>, dim3(static_cast<unsigned>(gb)), dim3(256), 0, st, g_loss, z, E, idx, N, denom_dE, D, dE, static_cast<const unsigned int*>(nullptr))
+                                  : launch_pdl(backward_dE_kernel<1>, dim3(static_cast<unsigned>(gb)), dim3(256), 0, st, g_loss, z, E, idx, N, denom_dE, D, dE, static_cast<const unsigned int*>(nullptr));
         if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of backward_dE_kernel failed: %s", cudaGetErrorString(e));
         LAUNCH_CHECK("backward_dE_kernel");
         return VQ_OK;
@@ -827,7 +826,7 @@ int vq_step_backward(const float* g_q, const float* g_loss, const float* z, cons
 // =========================================================================================================
 // data parallel: sum all-reduce of the packed step buffer [dE | usage histogram | squared error] over NVLink peer memory
 // =========================================================================================================
-constexpr int DP_EVENTS = 16;
+constexpr int DP_EVENTS = 32;
 struct vq_dp_ctx {
     DpCtxDev dev;
     int device;
@@ -873,11 +872,14 @@ int vq_dp_create(const void* const* recv0, const void* const* recv1, void* multi
         delete c;
         return fail(VQ_ERR_CUDA, "vq_dp_create: %s", cudaGetErrorString(e));
     }
-    // the exchange stream outranks the compute stream: its CTAs (256 threads, no dynamic shared memory) slot in next to the
-    // forward's as soon as they are launched
+    // The overlapped exchange's own stream.  Lowest priority by default: the fused forward needs whole SMs (all registers
+    // and shared memory), so an exchange CTA that slips onto an SM first holds the forward's CTA there up for as long as it
+    // polls; at low priority the exchange yields to whatever the step's stream has pending and runs next to small CTAs
+    // (the backward's, or in training the encoder's).  B200VQ_DP_SIDE_PRIORITY=high reverses it.
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi);
+    static const bool side_high = [] { const char* v = getenv("B200VQ_DP_SIDE_PRIORITY"); return v != nullptr && v[0] == 'h'; }();
+    e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, side_high ? prio_hi : prio_lo);
     for (int i = 0; i < DP_EVENTS && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&c->fork_ev[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done_ev[i], cudaEventDisableTiming);
@@ -929,6 +931,54 @@ int vq_dp_allreduce(vq_dp_ctx* c, const float* payload, float* out, vq_stream_t 
     const cudaError_t e = launch_pdl(dp_allreduce_kernel, dim3(static_cast<unsigned>(blocks)), dim3(DP_THREADS), 0, st, c->dev, payload, out);
     if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of dp_allreduce_kernel failed: %s", cudaGetErrorString(e));
     LAUNCH_CHECK("dp_allreduce_kernel");
+    return VQ_OK;
+}
+
+// Data-parallel backward with the exchange in the backward kernel's TAIL (backward_dp_kernel, kernels_dp.cuh): one launch
+// produces dz, the codebook gradient and the summed packed buffer.  Shapes the flat 16-byte path does not cover take the
+// fused backward followed by the exchange kernel.
+int vq_step_backward_dp(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx, int64_t n_rows,
+                        int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags, float* dz, float* packed,
+                        vq_dp_ctx* ctx, float* out, void* workspace, size_t workspace_bytes, int forward_flags, vq_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    if (ctx == nullptr || packed == nullptr || out == nullptr || z == nullptr || E == nullptr || idx == nullptr || K < 1 || D < 1 || n_rows < 0 ||
+        n_rows_dz < 1 || n_rows_dE < 1)
+        return fail(VQ_ERR_ARG, "vq_step_backward_dp: bad argument");
+    if (ctx->dev.n < static_cast<long long>(K) * D) return fail(VQ_ERR_ARG, "vq_step_backward_dp: the context's payload is smaller than K * D");
+    const long long N = n_rows;
+    const bool vec = (D % 4 == 0) && aligned16(z) && aligned16(E) && aligned16(packed) && aligned16(out) && (dz == nullptr || aligned16(dz)) &&
+                     (g_q == nullptr || aligned16(g_q));
+    static const bool tail_off = [] { const char* e = getenv("B200VQ_DP_TAIL"); return e != nullptr && e[0] == '0'; }();
+    if (tail_off || !(flags & VQ_FLAG_TRAIN_VQ) || dz == nullptr || !vec || N == 0 || (flags & VQ_FLAG_ZERO_DE) ||
+        repl_factor(N, K, D, flags, vec) > 1) {
+        if (int rc = vq_step_backward(g_q, g_loss, z, E, idx, n_rows, n_rows_dz, n_rows_dE, K, D, beta, flags, dz, packed, workspace,
+                                      workspace_bytes, forward_flags, stream))
+            return rc;
+        return vq_dp_allreduce(ctx, packed, out, stream);
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int ff = forward_flags & ~VQ_FLAG_STATE_READY;
+    const unsigned int* ready = nullptr;
+    if (workspace != nullptr && screen_path_ok(n_rows, K, D, ff, z, E, nullptr, nullptr) && ((ff & VQ_FLAG_SCREEN) || screen_enabled()) &&
+        !screen_split_rows(n_rows, K, D, ff)) {
+        const WsLayout w = ws_layout(n_rows);
+        if (workspace_bytes < w.total) return fail(VQ_ERR_WORKSPACE, "vq_step_backward_dp: workspace %zu B < %zu B", workspace_bytes, w.total);
+        ready = reinterpret_cast<const unsigned int*>(static_cast<const uint8_t*>(workspace) + w.counter_off) + 2;
+    }
+    const float denom_dz = static_cast<float>(static_cast<double>(n_rows_dz) * static_cast<double>(D));
+    const float denom_dE = static_cast<float>(static_cast<double>(n_rows_dE) * static_cast<double>(D));
+    const long long n_el = N * (D / 4);
+    long long g = (n_el + 1023) / 1024;                    // four elements per thread and pass
+    static const int ctas_per_sm = [] { const char* e = getenv("B200VQ_DP_TAIL_CTAS_PER_SM"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
+    if (g > kNumSMs * ctas_per_sm) g = kNumSMs * ctas_per_sm;
+    ProfScope prof(KID_BACKWARD, st);
+    const cudaError_t e =
+        g_q != nullptr ? launch_pdl(backward_dp_kernel<true>, dim3(static_cast<unsigned>(g)), dim3(256), 0, st, g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, D,
+                                    beta, dz, packed, ready, ctx->dev, out)
+                       : launch_pdl(backward_dp_kernel<false>, dim3(static_cast<unsigned>(g)), dim3(256), 0, st, g_q, g_loss, z, E, idx, N, denom_dz, denom_dE, D,
+                                    beta, dz, packed, ready, ctx->dev, out);
+    if (e != cudaSuccess) return fail(VQ_ERR_CUDA, "launch of backward_dp_kernel failed: %s", cudaGetErrorString(e));
+    LAUNCH_CHECK("backward_dp_kernel");
     return VQ_OK;
 }
 

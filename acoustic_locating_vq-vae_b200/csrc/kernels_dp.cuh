@@ -205,9 +205,7 @@ __device__ __forceinline__ void dp_gather(const DpCtxDev& c, const DpCall& k, co
 
 // body shared by the production kernel (one rank per launch) and the single-GPU emulation (one rank per blockIdx.y)
 __device__ __forceinline__ void dp_allreduce_body(const DpCtxDev& c, const DpCall& k, const float* __restrict__ payload, float* __restrict__ out,
-                                                  int* s_abort) {
-    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    const long long first = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+                                                  int* s_abort, long long first, long long stride) {
     const DpWaiter w{c, s_abort};
     for (long long i = first; i < c.L; i += stride) {
         const float d0 = __ldcg(payload + 2 * i);
@@ -223,12 +221,13 @@ __device__ __forceinline__ void dp_allreduce_body(const DpCtxDev& c, const DpCal
 }
 
 // the last CTA to finish advances the call counter (the next call -- or graph replay -- uses the other buffer)
-__device__ __forceinline__ void dp_end(const DpCtxDev& c) {
+__device__ __forceinline__ void dp_end(const DpCtxDev& c, unsigned int n_ctas) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(c.state + 2, 1u) == gridDim.x - 1) {
+        if (atomicAdd(c.state + 2, 1u) == n_ctas - 1) {
             c.state[2] = 0u;
+            c.state[3] = 0u;     // (backward_dp_kernel's completion tickets)
             __threadfence();
             atomicAdd(c.state, 1u);
         }
@@ -244,8 +243,9 @@ __global__ void __launch_bounds__(DP_THREADS) dp_allreduce_kernel(const __grid_c
     __syncthreads();
     pdl_wait_prior_grids();      // the local contribution is complete -- and so is a previous exchange (its counter update)
     const DpCall k = dp_begin(c);
-    dp_allreduce_body(c, k, payload, out, &s_abort);
-    dp_end(c);
+    dp_allreduce_body(c, k, payload, out, &s_abort, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x,
+                      static_cast<long long>(gridDim.x) * blockDim.x);
+    dp_end(c, gridDim.x);
 }
 
 // single-GPU emulation of `world` ranks (tests): blockIdx.y is the rank, launched cooperatively so that all ranks'
@@ -260,8 +260,109 @@ __global__ void __launch_bounds__(DP_THREADS) dp_emulate_kernel(const DpCtxDev* 
     }
     __syncthreads();
     const DpCall k = dp_begin(c);
-    dp_allreduce_body(c, k, payloads[blockIdx.y], outs[blockIdx.y], &s_abort);
-    dp_end(c);
+    dp_allreduce_body(c, k, payloads[blockIdx.y], outs[blockIdx.y], &s_abort, static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x,
+                      static_cast<long long>(gridDim.x) * blockDim.x);
+    dp_end(c, gridDim.x);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The data-parallel backward: backward_kernel's flat pass (dz, scatter-add of dE into the front of the packed step
+// buffer) with the exchange in its TAIL -- no second launch.  A kernel of its own costs ~7 us on the step's critical path
+// even when nothing has to cross NVLink (kernel boundary, the serial round trips for sequence number, payload, fence,
+// counter); here every CTA takes a completion ticket when its reds are out, and the last DP_TAIL_CTAS CTAs to finish
+// become the exchange: they wait (resident, so nobody is blocked) until all tickets are drawn -- the gradient is
+// complete in L2 then -- and push / collect / sum their share of the lines exactly as dp_allreduce_kernel does.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr unsigned int DP_TAIL_CTAS = 128;
+
+template <bool HAS_GQ>
+__global__ void __launch_bounds__(256) backward_dp_kernel(const float* __restrict__ g_q, const float* __restrict__ g_loss,
+                                                          const float* __restrict__ z, const float* __restrict__ E,
+                                                          const int* __restrict__ idx, long long N, float denom_dz, float denom_dE, int D,
+                                                          float beta, float* __restrict__ dz, float* __restrict__ packed,
+                                                          const unsigned int* ready, const __grid_constant__ DpCtxDev c,
+                                                          float* __restrict__ out) {
+    __shared__ int s_ok, s_abort;
+    __shared__ unsigned int s_ticket;
+    pdl_launch_dependents();
+    if (ready != nullptr) {          // right behind the fused forward: start on its ready word (see backward_kernel)
+        if (threadIdx.x == 0) {
+            unsigned int polls = 0;
+            while (ld_acquire_gpu_u32(ready) != 1u && ++polls < 4096u) {
+            }
+            s_ok = polls < 4096u ? 1 : 0;
+        }
+        __syncthreads();
+        if (!s_ok) pdl_wait_prior_grids();
+    } else {
+        pdl_wait_prior_grids();
+    }
+    const float gl = g_loss != nullptr ? __ldg(g_loss) : 1.0f;
+    const float cz = gl * beta * 2.0f / denom_dz;
+    const float ce = gl * 2.0f / denom_dE;
+    const int DV = D >> 2;
+    const long long n_el = N * DV;
+    // a few hundred long-lived CTAs (4 independent 16-byte elements in flight per thread) instead of one element per
+    // thread: the completion ticket below costs every CTA a fence (its reds must have been performed) and an atomic on
+    // ONE address -- with 3 216 one-shot CTAs that alone took 23 us
+    const long long gstride = static_cast<long long>(gridDim.x) * 256;
+    for (long long e0 = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; e0 < n_el; e0 += 4 * gstride) {
+        float4 zv[4], ev[4], gv[4];
+        int code[4], cc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long e = e0 + u * gstride;
+            if (e < n_el) {
+                const long long r = e / DV;
+                cc[u] = static_cast<int>(e - r * DV);
+                code[u] = __ldg(idx + r);
+                zv[u] = __ldcs(reinterpret_cast<const float4*>(z) + e);
+                ev[u] = __ldg(reinterpret_cast<const float4*>(E + static_cast<size_t>(code[u]) * D) + cc[u]);
+                gv[u] = HAS_GQ ? __ldcs(reinterpret_cast<const float4*>(g_q) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long e = e0 + u * gstride;
+            if (e < n_el) {
+                float4 df, o, a;
+                df.x = ev[u].x - zv[u].x; df.y = ev[u].y - zv[u].y; df.z = ev[u].z - zv[u].z; df.w = ev[u].w - zv[u].w;
+                o.x = fmaf(-cz, df.x, gv[u].x); o.y = fmaf(-cz, df.y, gv[u].y);
+                o.z = fmaf(-cz, df.z, gv[u].z); o.w = fmaf(-cz, df.w, gv[u].w);
+                __stcs(reinterpret_cast<float4*>(dz) + e, o);
+                a.x = ce * df.x; a.y = ce * df.y; a.z = ce * df.z; a.w = ce * df.w;
+                atomicAdd(reinterpret_cast<float4*>(packed + static_cast<size_t>(code[u]) * D) + cc[u], a);
+            }
+        }
+    }
+    // ---- tail: completion ticket; the last DP_TAIL_CTAS finishers are the exchange ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                                    // this CTA's reds are performed before the ticket is drawn
+        s_ticket = atomicAdd(c.state + 3, 1u);
+        s_abort = 0;
+    }
+    __syncthreads();
+    const unsigned int total = gridDim.x;
+    const unsigned int helpers = total < DP_TAIL_CTAS ? total : DP_TAIL_CTAS;
+    if (s_ticket + helpers >= total) {
+        const unsigned int h = s_ticket - (total - helpers);
+        if (threadIdx.x == 0) {                              // everybody else is running or done: a bounded, deadlock-free wait
+            unsigned int polls = 0;
+            while (ld_acquire_gpu_u32(c.state + 3) < total) {
+                if (++polls > c.spin_limit) {
+                    atomicOr(c.state + 1, 2u);
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        const DpCall k = dp_begin(c);
+        dp_allreduce_body(c, k, packed, out, &s_abort, static_cast<long long>(h) * 256 + threadIdx.x, static_cast<long long>(helpers) * 256);
+        dp_end(c, helpers);
+    }
+    // order this kernel behind the forward's completion before it exits: "previous kernel complete" stays transitive
+    if (ready != nullptr) pdl_wait_prior_grids();
 }
 
 }  // namespace b200vq

@@ -596,6 +596,11 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
         int* const g_ocount = ovf_count + grp;
         unsigned long long* const g_okey = ovf_key + grp;
         float sse = 0.0f;
+        // Usage counts.  Reds on the same address queue up in L2 (~0.1 - 0.2 us apiece: N / K of them per code), which at
+        // K = 512, N = 1M is longer than the rest of the kernel.  Without the dense one-hot the zero row is idle: it holds
+        // a per-CTA histogram (shared-memory integer atomics), flushed with one red per used code when the CTA is done.
+        int* const s_hist = reinterpret_cast<int*>(zero_row);
+        const bool smem_hist = !have_oh && K <= TC2_ZERO_BYTES / 4;
         for (int w = pair + grp * n_pairs, it = grp; w < n_items; w += groups * n_pairs, it += groups) {
             const long long row0 = static_cast<long long>(2 * w + static_cast<int>(cta_rank)) * TC_ROWS;
             const long long left = N - row0;
@@ -737,7 +742,10 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
             for (int r = wt; r < rows_here; r += NW) {
                 const int code = g_idx[r];
                 idx_out[row0 + r] = code;
-                if (!fr.rows_later) atomicAdd(fr.hist + code, 1.0f);
+                if (!fr.rows_later) {
+                    if (smem_hist) atomicAdd(s_hist + code, 1);
+                    else atomicAdd(fr.hist + code, 1.0f);
+                }
             }
             // -- q_out = fl(z + fl(E[idx] - z)), sse += (E[idx] - z)^2 ---------------------------------------------
             if (quant) {
@@ -782,6 +790,13 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
         }
         if (wt_all == 0) VQ_TR(6, 2);
         // per-CTA SSE partial, then last-CTA-done reduction in a fixed order (+ loss / perplexity)
+        if (smem_hist && !fr.rows_later) {
+            named_bar_sync(7, NW_all);                      // both worker groups are through their items
+            for (int k = wt_all; k < K; k += NW_all) {
+                const int c = s_hist[k];
+                if (c != 0) atomicAdd(fr.hist + k, static_cast<float>(c));     // integers below 2^24: exact in any order
+            }
+        }
         // (rows_later: the rows kernel behind this one owns the completion counter and the statistics)
         if (!fr.rows_later) publish_and_finalize(fr, sse, N, K, D, wt_all, NW_all, lane, have_oh ? warp - 13 : warp - 12, have_oh ? 3 : 4, red, 7);
     }

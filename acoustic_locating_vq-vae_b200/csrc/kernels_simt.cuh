@@ -200,6 +200,15 @@ __global__ void __launch_bounds__(256) quantize_rows_kernel(
     __shared__ double red[8];
     __shared__ bool is_last;
     __shared__ int s_idx[ROWS_MAX_R];
+    // small codebooks: reds on the same address queue up in L2 (N / K per code), so the counts are kept per CTA in shared
+    // memory and flushed once (integers: exact in any order)
+    constexpr int ROWS_SMEM_HIST = 2048;
+    __shared__ int s_hist[ROWS_SMEM_HIST];
+    const bool smem_hist = K <= ROWS_SMEM_HIST;
+    if (smem_hist) {
+        for (int k = threadIdx.x; k < K; k += 256) s_hist[k] = 0;
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int DV = D / VEC;                 // elements (of VEC floats) per row
     const long long n_groups = (N + R - 1) / R;
@@ -217,7 +226,11 @@ __global__ void __launch_bounds__(256) quantize_rows_kernel(
                 code = idx_in[r];
             }
             s_idx[threadIdx.x] = code;
-            atomicAdd(hist + code, 1.0f);
+            if (smem_hist) {
+                if (static_cast<unsigned>(code) < static_cast<unsigned>(K)) atomicAdd(s_hist + code, 1);
+            } else {
+                atomicAdd(hist + code, 1.0f);
+            }
         }
         __syncthreads();
         if (QUANT) {
@@ -289,6 +302,12 @@ __global__ void __launch_bounds__(256) quantize_rows_kernel(
             }
         }
         __syncthreads();   // s_idx is reused by the next group
+    }
+    if (smem_hist) {
+        for (int k = threadIdx.x; k < K; k += 256) {
+            const int c = s_hist[k];
+            if (c != 0) atomicAdd(hist + k, static_cast<float>(c));
+        }
     }
     // block partial (double), then last-CTA-done reduction in a fixed order
     double s = warp_sum_d(static_cast<double>(sse));
@@ -479,9 +498,21 @@ __global__ void __launch_bounds__(256) reduce_replicas_kernel(const float* __res
 template <int VEC>
 __global__ void __launch_bounds__(256) backward_dE_kernel(const float* __restrict__ g_loss, const float* __restrict__ z,
                                                           const float* __restrict__ E, const int* __restrict__ idx, long long N,
-                                                          float denom_dE, int D, float* __restrict__ dE) {
+                                                          float denom_dE, int D, float* __restrict__ dE, const unsigned int* ready) {
     pdl_launch_dependents();
-    pdl_wait_prior_grids();
+    if (ready != nullptr) {          // right behind the fused forward: start on its ready word (see backward_kernel)
+        __shared__ int s_ok;
+        if (threadIdx.x == 0) {
+            unsigned int polls = 0;
+            while (ld_acquire_gpu_u32(ready) != 1u && ++polls < 4096u) {
+            }
+            s_ok = polls < 4096u ? 1 : 0;
+        }
+        __syncthreads();
+        if (!s_ok) pdl_wait_prior_grids();
+    } else {
+        pdl_wait_prior_grids();
+    }
     const float gl = g_loss != nullptr ? __ldg(g_loss) : 1.0f;
     const float ce = gl * 2.0f / denom_dE;
     const int DV = D / VEC;
@@ -501,6 +532,7 @@ __global__ void __launch_bounds__(256) backward_dE_kernel(const float* __restric
             atomicAdd(dE + static_cast<size_t>(code) * D + c, ce * (__ldg(E + static_cast<size_t>(code) * D + c) - z[e]));
         }
     }
+    if (ready != nullptr) pdl_wait_prior_grids();      // behind the forward's completion before it exits (transitivity)
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -117,6 +117,7 @@ class _VQFunction(torch.autograd.Function):
             ctx.mark_non_differentiable(perplexity, idx, onehot)
         else:
             ctx.mark_non_differentiable(perplexity, idx)
+        ctx.set_materialize_grads(False)            # no zero tensors for the outputs that carry no gradient (the one-hot: 211 MB)
         module.__dict__["_last_stats"] = scal       # plain attribute: skip nn.Module.__setattr__ on the eager path
         return loss, q_out, perplexity, onehot, idx
 

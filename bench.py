@@ -258,7 +258,9 @@ def main():
     ap.add_argument("--no-screen", action="store_true", help="3xTF32 tensor kernels instead of screen + exact refine (VQ_FLAG_NO_SCREEN)")
     ap.add_argument("--graph", action="store_true", help="N = 1: replay the step from CUDA graphs (default there: eager launches chained by programmatic dependent launch)")
     ap.add_argument("--no-graph", action="store_true", help="N > 1: eager launches (default there: CUDA graphs, which keep the ranks' launch jitter out of the exchange)")
-    ap.add_argument("--no-overlap", action="store_true", help="N > 1: the exchange in line on the step's stream instead of overlapped with the next step's forward")
+    ap.add_argument("--dp-mode", default="inline", choices=["inline", "side", "tail", "deferred"], help="N > 1: how the step's exchange is scheduled (see step())")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: same as --dp-mode inline")
+    ap.add_argument("--strong", action="store_true", help="N > 1: strong scaling -- the workload's batch is split over the ranks (default: every rank runs the whole workload, weak scaling)")
     ap.add_argument("--emulate-dp", action="store_true", help="experiment, N = 1: the data-parallel step structure with a world-of-one exchange context")
     ap.add_argument("--nccl", action="store_true", help="N > 1: NCCL all_reduce of [dE|hist|sse] after the backward instead of the NVLink exchange")
     ap.add_argument("--skip-cpu", action="store_true")
@@ -273,10 +275,16 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     B, D, T, K, desc = WORKLOADS[args.workload]
+    if args.strong and world > 1:          # total work fixed: the workload's batch items are split over the ranks
+        if B % world:
+            raise SystemExit(f"--strong: batch {B} does not divide over {world} ranks")
+        B //= world
     N = B * T
     # configs[3] (the sweep) is indices-only by definition (a dense one-hot would be up to 34 GB)
     emit_onehot = not args.no_onehot and not args.workload.startswith("sweep")
     config = make_config(args.workload, max(world, args.gpus))
+    if args.strong and world > 1:
+        config.update({"B": B, "rows_per_gpu": N, "parallelism": f"dp{world} (strong scaling: the workload's batch split over the ranks)"})
     if args.no_onehot:
         config["encodings"] = "indices only"
 
@@ -346,7 +354,7 @@ def main():
         return s
 
     nbuf = max(3, int(1.25 * L2_BYTES / (N * D * 4)) + 1)                # rotating inputs: set larger than L2
-    S0 = make_state(N, K, D, emit_onehot, nbuf, 1000 + rank, nsets=min(nbuf, 15) if (world > 1 or args.emulate_dp) else 1)
+    S0 = make_state(N, K, D, emit_onehot, nbuf, 1000 + rank, nsets=min(2 * nbuf, 31) if (world > 1 or args.emulate_dp) else 1)
     n_packed = K * D + K + 1
     exch = None
     collective = "none"
@@ -365,9 +373,10 @@ def main():
         else:
             collective = ("[dE | hist | sse] over NVLink peer memory (vq_dp_allreduce, " + ("NVLS multimem.st" if exch.nvls else "P2P stores") + ", "
                           + ("reduce-scatter + all-gather" if world >= 8 else "one step") + ", device-side sequence numbers"
-                          + ("" if args.no_overlap else "; started on the exchange's own stream behind the backward (vq_dp_allreduce_start), payload / result buffers rotate over "
-                             f"{len(S0['packs'])} sets and the step stream joins the exchanges at the end of every graph: the following steps overlap the transfer, "
-                             "every exchange completes inside the timed region") + ")")
+                          + "; schedule: " + {"tail": "in the tail of the backward kernel (vq_step_backward_dp): the last CTAs to finish push / collect / sum, no second launch",
+                                             "inline": "after the fused backward, nothing overlaps it",
+                                             "deferred": "one step late, between the next step's forward and backward (overlaps that backward)",
+                                             "side": "on the context's own low-priority stream, started behind the next step's prepare launch"}["inline" if args.no_overlap else args.dp_mode] + ")")
     elif world > 1:
         collective = "NCCL all_reduce of [dE | hist | sse] after the backward"
     elif args.emulate_dp:
@@ -396,35 +405,75 @@ def main():
         collective = "EMULATION: world-of-one exchange context on a single GPU (launch structure only)"
     n_dE_scale = world
 
-    overlap = exch is not None and not args.no_overlap
+    # how the one exchange of a data-parallel step is scheduled (N > 1):
+    #   inline    (default) fused backward, then the exchange kernel, chained by programmatic dependent launch
+    #   tail      inside the backward kernel (vq_step_backward_dp): the last CTAs to finish ARE the exchange (no second launch;
+    #             measured slower: the serial round trips of the exchange stay, and the long-lived CTAs stream slower)
+    #   deferred  the exchange of step i sits between forward and backward of step i + 1 (one step late; two buffer sets)
+    #   side      the exchange of step i on the context's own low-priority stream, started behind step i + 1's prepare launch,
+    #             joined at the end of every graph
+    # Measured: nothing overlaps the exchange with the fused forward, which owns every SM's registers
+    # and shared memory -- a co-scheduled exchange either holds the forward's CTAs up or starves until the graph's end.
+    dp_mode = "none" if exch is None else ("inline" if args.no_overlap else args.dp_mode)
+    sched = {"mode": dp_mode}                         # (the per-kernel profile pass runs the exchange in line)
+    pending = []                                     # deferred / side: the previous step's (payload, result), exchange not started yet
 
     def step(s, i, st):
         """one step of the hot path on input buffer i, enqueued on raw stream `st`"""
         N_, K_, D_ = s["N"], s["K"], s["D"]
         z, gq = s["zs"][i % s["nbuf"]], s["gs"][i % s["nbuf"]]
         ns = len(s["packs"])
-        par = (i % ns) if overlap else 0
+        par = (i % ns) if sched["mode"] in ("side", "deferred") else 0
         pk = P(s["packs"][par])                      # [dE (K*D) | hist (K) | sse | loss | perplexity]
+        red = P(s["reds"][par])
         sp = pk + 4 * K_ * D_
-        if overlap:                                  # the exchange of step i - ns has left this set of buffers (a graph of <= ns
-            L.check(lib.vq_dp_wait(exch.ctx, ns - 1, st))     # steps never gets here: its only join is the final one)
-        # the prepare launch also zeroes the dE accumulator: no memset node between forward and backward (PDL chain intact)
-        L.check(lib.vq_step_forward(P(z), P(s["E"]), N_, K_, D_, BETA, s["fwd_flags"], P(s["e2"]), P(s["ehi"]), P(s["elo"]), pk, P(s["q"]), P(s["idx"]),
-                                    P(s["onehot"]), sp, sp + 4 * K_, sp + 4 * (K_ + 1), sp + 4 * (K_ + 2), P(s["ws"]), s["wsb"], st))
+        if sched["mode"] == "side":
+            # the exchange that last used this set of buffers (step i - ns) is complete (a graph of <= ns steps never waits
+            # here: its only join is the final one)
+            L.check(lib.vq_dp_wait(exch.ctx, max(ns - 2, 0), st))
+            # codebook preparation (also zeroes the dE accumulator) ...
+            need_elo = args.no_screen or not (K_ % 256 == 0 and D_ in (32, 64, 96, 128, 192, 256))     # as vq_step_forward decides
+            L.check(lib.vq_prepare_step(P(s["E"]), K_, D_, P(s["e2"]), None if args.exact else P(s["ehi"]), P(s["elo"]) if (need_elo and not args.exact) else None,
+                                        sp, P(s["ws"]), s["wsb"], pk, st))
+            # ... then the PREVIOUS step's exchange is started, behind this step's prepare launch: the fused forward owns
+            # every SM's registers and shared memory, so an exchange that gets its CTAs onto the SMs first would hold the
+            # forward up; started here (on a lower-priority stream) it yields to the forward, which is already being placed
+            if pending:
+                L.check(lib.vq_dp_allreduce_start(exch.ctx, pending[0], pending[1], st))
+                del pending[:]
+            L.check(lib.vq_forward(P(z), P(s["E"]), P(s["e2"]), P(s["ehi"]), P(s["elo"]), N_, K_, D_, BETA, s["fwd_flags"] | L.FLAG_STATE_READY, P(s["q"]), P(s["idx"]),
+                                   P(s["onehot"]), sp, sp + 4 * K_, sp + 4 * (K_ + 1), sp + 4 * (K_ + 2), P(s["ws"]), s["wsb"], st))
+        else:
+            # the prepare launch also zeroes the dE accumulator: no memset node between forward and backward (PDL chain intact)
+            L.check(lib.vq_step_forward(P(z), P(s["E"]), N_, K_, D_, BETA, s["fwd_flags"], P(s["e2"]), P(s["ehi"]), P(s["elo"]), pk, P(s["q"]), P(s["idx"]),
+                                        P(s["onehot"]), sp, sp + 4 * K_, sp + 4 * (K_ + 1), sp + 4 * (K_ + 2), P(s["ws"]), s["wsb"], st))
         n_dE = N_ * n_dE_scale
+        if sched["mode"] == "tail":           # data parallel: ONE sum all-reduce of [dE | hist | sse], in the backward kernel's tail
+            L.check(lib.vq_step_backward_dp(P(gq), P(s["g_loss"]), P(z), P(s["E"]), P(s["idx"]), N_, N_, n_dE, K_, D_, BETA, L.FLAG_TRAIN_VQ,
+                                            P(s["dz"]), pk, exch.ctx, red, P(s["ws"]), s["wsb"], s["fwd_flags"], st))
+            return
+        if sched["mode"] == "deferred" and pending:          # the previous step's exchange: overlaps this step's backward
+            L.check(lib.vq_dp_allreduce(exch.ctx, pending[0], pending[1], st))
+            del pending[:]
         # right behind the forward: starts on the workspace's ready word and overlaps the forward's statistics tail
         L.check(lib.vq_step_backward(P(gq), P(s["g_loss"]), P(z), P(s["E"]), P(s["idx"]), N_, N_, n_dE, K_, D_, BETA, L.FLAG_TRAIN_VQ,
                                      P(s["dz"]), pk, P(s["ws"]), s["wsb"], s["fwd_flags"], st))
-        if overlap:                     # data parallel: ONE sum all-reduce of [dE | hist | sse], on the exchange's own stream --
-            L.check(lib.vq_dp_allreduce_start(exch.ctx, pk, P(s["reds"][par]), st))      # the next step's forward overlaps it
-        elif exch is not None:
-            L.check(lib.vq_dp_allreduce(exch.ctx, pk, P(s["reds"][par]), st))
+        if sched["mode"] in ("side", "deferred"):
+            pending[:] = [pk, red]                                                        # started by the next step (or the join)
+        elif sched["mode"] == "inline":
+            L.check(lib.vq_dp_allreduce(exch.ctx, pk, red, st))
         elif world > 1:
             dist.all_reduce(s["packs"][par][:K_ * D_ + K_ + 1])
 
     def join(st):
-        """every exchange started so far is complete before `st` goes on (end of a run, end of a capture)"""
-        if overlap:
+        """every exchange is started and complete before `st` goes on (end of a run, end of a capture)"""
+        if pending:
+            if sched["mode"] == "side":
+                L.check(lib.vq_dp_allreduce_start(exch.ctx, pending[0], pending[1], st))
+            else:
+                L.check(lib.vq_dp_allreduce(exch.ctx, pending[0], pending[1], st))
+            del pending[:]
+        if sched["mode"] == "side":
             L.check(lib.vq_dp_wait(exch.ctx, 0, st))
 
     def barrier():
@@ -455,7 +504,7 @@ def main():
             step(s, i, cur.cuda_stream)
         join(cur.cuda_stream)
         torch.cuda.synchronize()
-        side = torch.cuda.Stream(device=dev)
+        side = torch.cuda.Stream(device=dev, priority=-1)     # the step's kernels outrank the exchange's (captured with the nodes)
         graphs = {}
 
         def capture(n):
@@ -472,15 +521,27 @@ def main():
             torch.cuda.synchronize()
             graphs[n] = g
 
+        # steps per graph: one round over the input buffers; data parallel: as many steps as there are payload / result sets
+        # (two rounds), so that no join but the final one sits inside a graph and a 20-step run is ONE launch
+        chunk = len(s["packs"]) if exch is not None else nb
+
         def plan(k):
-            return [nb] * (k // nb) + ([k % nb] if k % nb else [])
+            return [chunk] * (k // chunk) + ([k % chunk] if k % chunk else [])
 
         def run_graphs(k):
             for n in plan(k):
                 if n not in graphs:          # only outside timed regions: the bench primes the sizes it needs
                     capture(n)
                 graphs[n].replay()
-        run_graphs.prime = lambda k: [capture(n) for n in set(plan(k)) if n not in graphs]
+        def prime(k):
+            """capture the graphs a k-step run needs and replay each once, untimed: the first launch of an instantiated graph
+            uploads it to the device (tens of microseconds for 100 kernel nodes), which a 20-step region would count"""
+            for n in set(plan(k)):
+                if n not in graphs:
+                    capture(n)
+                    graphs[n].replay()
+            torch.cuda.synchronize()
+        run_graphs.prime = prime
         run_graphs.graphs = graphs
         return run_graphs, graphs
 
@@ -499,6 +560,10 @@ def main():
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if exch is not None and world > 1:
+        # the host barrier leaves the ranks tens of microseconds apart, which a 20-step region (1.4 ms) would count as
+        # exchange time: one untimed exchange lines the DEVICE timelines up (nobody leaves it before everybody has entered)
+        L.check(lib.vq_dp_allreduce(exch.ctx, P(S0["packs"][0]), P(S0["reds"][0]), cur.cuda_stream))
     ev0.record()
     run0(args.steps)
     ev1.record()
@@ -517,11 +582,15 @@ def main():
 
     # ---- per-kernel timing (CUDA events on the launching stream, eager launches) for the roofline ---------
     def profile(s, reps):
+        keep_mode = sched["mode"]
+        if keep_mode in ("side", "deferred"):        # time the exchange where it has the SMs to itself, not while it queues behind the forward
+            sched["mode"] = "inline"
         lib.vq_profile_enable(1)
         for i in range(reps):
             step(s, i, cur.cuda_stream)
         join(cur.cuda_stream)
         barrier()
+        sched["mode"] = keep_mode
         kern = {}
         for kid, name in enumerate(KERNEL_NAMES):
             tot, cnt = ctypes.c_double(0), ctypes.c_int64(0)
@@ -715,7 +784,7 @@ def main():
                                     "fwd_tflops": round(fl / (t_f * 1e-6) / 1e12, 1), "frac_fwd": round(fl / (t_f * 1e-6) / 1e12 / tf32_sus, 3),
                                     "bwd_frac_hbm": round(bb / (t_b * 1e-6) / 1e9 / peaks["hbm_gbs"], 3),
                                     "frac": round(t_roof * 1e6 / (t_f + t_b), 3), "vectors_per_s": round(SWEEP_N / (t_step * 1e-6)),
-                                    "backward_path": ["flat", "", "private"][lib.vq_backward_path(SWEEP_N, k_, d_, 0)],
+                                    "backward_path": ["flat", "", "private", "replicated"][lib.vq_backward_path(SWEEP_N, k_, d_, 0)],
                                     "forward_kernels": sorted(n for n in kk if n not in ("backward", "exchange"))})
             del s
 
@@ -774,12 +843,12 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "vectors/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None,
             "dtype": ("f32" if args.exact or not tensor_path else ("f32 (tcgen05 3xTF32 contraction, fp32 accumulate)" if not screen_used else
                       "f32 (tcgen05 TF32 screening pass + exact fp32 refine of the candidates: indices bit-exact vs the fp32 oracle)")),
             "data": "synthetic", "config": config,
             "notes": {"path": "tcgen05" if tensor_path else "exact CUDA-core",
-                      "launch": (f"CUDA graphs (one per round over the {nbuf} input buffers + one for the remaining steps), {launches_per_step} kernels per step"
+                      "launch": (f"CUDA graphs ({len(S0['packs']) if exch is not None else nbuf} steps per graph + one for the remaining steps; inputs rotate over {nbuf} buffers), {launches_per_step} kernels per step"
                                  if use_graph else f"eager launches chained by programmatic dependent launch, {launches_per_step} kernels per step"),
                       "l2": f"inputs rotate over {nbuf} z + {nbuf} g buffers ({2 * nbuf * N * D * 4 >> 20} MiB > 126 MiB L2)",
                       "collective": collective},

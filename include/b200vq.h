@@ -150,9 +150,9 @@ int vq_step_backward(const float* g_q, const float* g_loss, const float* z, cons
 /* Which kernel the backward takes for dE (16-byte aligned pointers assumed): 0 flat (one red.global.add per element),
  * 2 private (per-CTA copy of dE in shared memory, flushed once; N >> K and K*D small; dz may be NULL: codebook gradient
  * only), 3 replicated -- vq_step_backward only, which has scratch (the dead tail of the forward's workspace): the flat
- * kernel with its reds spread over R zeroed copies of dE (R * K * D/4 ~ 128 k addresses) and a small launch that folds
- * them into dE; taken when K * D/4 < 64 k addresses and N >= max(256 k, 64 K), where the flat scatter is bound by reds
- * queueing on the same L2 addresses.  vq_backward (no scratch) takes 2 or 0 there. */
+ * kernel with its reds spread over R zeroed copies of dE (R * K * D/4 ~ 256 k addresses, R <= 32) and a small launch
+ * that folds them into dE; taken when K * D/4 < 128 k addresses and N >= max(256 k, 256 K), where the flat scatter is
+ * bound by reds queueing on the same L2 addresses.  vq_backward (no scratch) takes 2 or 0 there. */
 int vq_backward_path(int64_t n_rows, int K, int D, int flags);
 
 /* -- the consumer of `encodings` as an index gather ------------------------------------ */
@@ -198,11 +198,22 @@ int  vq_dp_create(const void* const* recv0, const void* const* recv1, void* mult
 void vq_dp_destroy(vq_dp_ctx* ctx);
 /* out[i] = sum over ranks of payload[i], i < n_floats (payload: written by earlier work on `stream`). */
 int  vq_dp_allreduce(vq_dp_ctx* ctx, const float* payload, float* out, vq_stream_t stream);
+/* The data-parallel backward: vq_step_backward and the exchange of the packed step buffer as ONE launch.  Every CTA of the
+ * backward takes a completion ticket when its share of the codebook gradient is out; the last 128 CTAs to finish become
+ * the exchange (push / collect / sum, as vq_dp_allreduce) the moment the gradient is complete -- no second kernel, whose
+ * launch boundary and serial round trips cost ~7 us per step even with nothing to send.  `packed` = [dE (K*D) | hist (K) |
+ * sse] with the forward's statistics already in place and the dE slot zeroed (vq_step_forward's dE_zero); out = the summed
+ * buffer, complete when the call's kernel is.  Falls back to vq_step_backward + vq_dp_allreduce for shapes the 16-byte
+ * flat pass does not cover (and under B200VQ_DP_TAIL=0). */
+int  vq_step_backward_dp(const float* g_q, const float* g_loss, const float* z, const float* E, const int32_t* idx,
+                         int64_t n_rows, int64_t n_rows_dz, int64_t n_rows_dE, int K, int D, float beta, int flags,
+                         float* dz, float* packed, vq_dp_ctx* ctx, float* out,
+                         void* workspace, size_t workspace_bytes, int forward_flags, vq_stream_t stream);
 /* Overlapped form: the exchange is ordered behind everything enqueued on `stream` so far, but runs on a stream of the
  * context's own, so `stream` carries on at once -- the next step's codebook preparation and forward overlap the NVLink
  * transfer and absorb the ranks' skew (in training the encoder's backward does, as under DDP's bucketed all-reduce).
  * vq_dp_wait makes `stream` wait for every exchange started so far except the keep_in_flight most recent ones
- * (exchanges complete in the order they were started): keep_in_flight = S - 1 (< 16) at the top of a step whose
+ * (exchanges complete in the order they were started): keep_in_flight = S - 1 (< 32) at the top of a step whose
  * payload / out buffers rotate over S sets, 0 before the results are read, before vq_dp_destroy and before a stream
  * capture ends.  Fork and join are event edges, so a stream capture records them; a captured graph of S steps over S
  * buffer sets needs no join but the final one, which leaves every programmatic-launch edge of the step chain intact. */

@@ -102,9 +102,10 @@ def test_default_path_choice(lib):
 
 
 @pytest.mark.parametrize("N,D,K", [(300000, 64, 512), (262144, 128, 512), (270001, 64, 1024)])
-def test_step_pair_split_rows_and_replicated_scatter(lib, N, D, K):
-    """Large N with a small codebook: vq_step_forward runs the screen kernel for the indices and quantize_rows_kernel behind
-    it (row epilogue split off), vq_step_backward spreads its reds over copies of dE in the workspace's dead tail.  Indices
+def test_step_pair_small_codebook_large_n(lib, N, D, K):
+    """Large N with a small codebook: vq_step_forward keeps the usage counts per CTA in shared memory (and, under
+    B200VQ_SPLIT_ROWS=1, runs quantize_rows_kernel behind an indices-only screen kernel), vq_step_backward spreads its reds
+    over copies of dE in the workspace's dead tail.  Indices
     must equal the exact CUDA-core path's, dz the flat kernel's bit for bit, dE / loss / perplexity within tolerance; the
     workspace must be reusable by the next forward (two steps back to back)."""
     dev = _dev()
@@ -312,3 +313,54 @@ def test_step_backward_behind_the_forward(lib):
             assert float((ix.long() != d.argmin(1)).float().mean()) < 1e-3          # same codes as the plain torch argmin (up to near-ties)
             m = float(((E[ix.long()] - zs[i]) ** 2).mean())
             assert abs(float(st_i[K + 1]) - 1.25 * m) <= 1e-5 * 1.25 * m and float(st_i[K + 2]) > 1.0
+
+
+def test_step_backward_dp_world_of_one(lib):
+    """vq_step_backward_dp = dE pass -> exchange -> dz pass on one stream.  With a world-of-one exchange context (this GPU's own
+    receive buffers) the summed buffer must equal the packed buffer, dz the fused kernel's bit for bit, dE the flat kernel's
+    within tolerance -- over several back-to-back steps (sequence numbers, buffer parity, the ready word) and for shapes
+    that take the fallback (odd D)."""
+    import ctypes
+    dev = _dev()
+    st = torch.cuda.current_stream().cuda_stream
+    for (N, D, K, onehot) in ((51456, 64, 1024, True), (16000, 128, 1024, False), (1003, 30, 37, False)):
+        n = K * D + K + 1
+        lines = int(lib.vq_dp_recv_lines(1, n))
+        bufs = [torch.zeros(lines * 4, device=dev) for _ in range(2)]
+        arr = [(ctypes.c_void_p * 1)(b.data_ptr()) for b in bufs]
+        ctx = ctypes.c_void_p()
+        assert lib.vq_dp_create(arr[0], arr[1], None, None, 1, 0, n, 0, ctypes.byref(ctx)) == 0, lib.vq_last_error()
+        E = torch.randn(K, D, device=dev)
+        e2 = torch.empty(K, device=dev); ehi = torch.empty_like(E); elo = torch.empty_like(E)
+        wsb = lib.vq_workspace_bytes(N, K, D, 0); ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        q = torch.empty(N, D, device=dev); idx = torch.empty(N, dtype=torch.int32, device=dev)
+        oh = torch.empty(N, K, device=dev) if onehot else None
+        packed = torch.zeros(n + 2, device=dev); out = torch.zeros(n, device=dev)
+        pk = packed.data_ptr(); sp = pk + 4 * K * D
+        dz = torch.empty(N, D, device=dev)
+        gl = torch.tensor(0.7, device=dev)
+        fl = 1 if onehot else 0
+        res = []
+        zs = [torch.randn(N, D, device=dev) for _ in range(4)]
+        gs = [torch.randn(N, D, device=dev) for _ in range(4)]
+        for i in range(4):
+            rc = lib.vq_step_forward(zs[i].data_ptr(), E.data_ptr(), N, K, D, BETA, fl, e2.data_ptr(), ehi.data_ptr(), elo.data_ptr(), pk,
+                                     q.data_ptr(), idx.data_ptr(), None if oh is None else oh.data_ptr(), sp, sp + 4 * K, sp + 4 * (K + 1),
+                                     sp + 4 * (K + 2), ws.data_ptr(), wsb, st)
+            assert rc == 0, lib.vq_last_error()
+            rc = lib.vq_step_backward_dp(gs[i].data_ptr(), gl.data_ptr(), zs[i].data_ptr(), E.data_ptr(), idx.data_ptr(), N, N, 2 * N, K, D, BETA, TRAIN,
+                                         dz.data_ptr(), pk, ctx, out.data_ptr(), ws.data_ptr(), wsb, fl, st)
+            assert rc == 0, lib.vq_last_error()
+            res.append((idx.clone(), dz.clone(), packed[:n].clone(), out.clone()))
+        torch.cuda.synchronize()
+        calls, err = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        assert lib.vq_dp_status(ctx, ctypes.byref(calls), ctypes.byref(err), st) == 0
+        assert calls.value == 4 and err.value == 0
+        for i, (ix, dz_i, pk_i, out_i) in enumerate(res):
+            assert torch.equal(pk_i, out_i), f"N={N} step {i}: world-of-one sum differs from the payload"
+            dz_ref, dE_ref = _backward(lib, gs[i], 0.7, zs[i], E, ix, TRAIN | ZERO_DE | FLAT, n_dE=2 * N)
+            assert torch.equal(dz_i, dz_ref), f"N={N} step {i}"
+            assert _rel(out_i[:K * D].view(K, D).cpu().numpy(), dE_ref.cpu().numpy()) <= 1e-5, f"N={N} step {i}"
+            hist = torch.bincount(ix.long(), minlength=K).float()
+            assert torch.equal(out_i[K * D:K * D + K], hist)
+        lib.vq_dp_destroy(ctx)

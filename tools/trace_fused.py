@@ -9,7 +9,11 @@ from importlib import import_module
 B = import_module("acoustic_locating_vq-vae_b200.build")
 L = import_module("acoustic_locating_vq-vae_b200._lib")
 so = os.path.join(B.CSRC, "libb200vq_trace.so")
-subprocess.run([B._nvcc(), *B.NVCC_FLAGS, "-DVQ_TRACE", "-o", so, os.path.join(B.CSRC, "b200vq.cu")], check=True)
+srcs = [os.path.join(B.CSRC, f) for f in B.SOURCES + B.HEADERS]
+if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in srcs) or "--build-only" in sys.argv:
+    subprocess.run([B._nvcc(), *B.NVCC_FLAGS, "-DVQ_TRACE", "-o", so, os.path.join(B.CSRC, "b200vq.cu")], check=True)
+if "--build-only" in sys.argv:       # (cross-compile in the authoring container; the .so travels to the GPU box)
+    sys.exit(0)
 lib = ctypes.CDLL(so)
 for name, (res, args) in L.SIGNATURES.items():
     fn = getattr(lib, name); fn.restype = res; fn.argtypes = args
