@@ -620,12 +620,13 @@ def main():
     }
     work = alg.get(dom, {"flops": 0.0, "bytes": 0.0})
     dur_s = kern[dom]["avg_us"] * 1e-6
+    # The TF32 peak (cuBLAS 8192^3, back to back for ~1.5 s) is measured AFTER the sweep: the sustained GEMM drives the GPU
+    # into its power cap, and sweep points timed right behind it ran up to 1.7x slower on some boxes.  Until then the
+    # bound decision uses bf16 / 2; a tensor-bound roofline is re-based on the measured burst peak below.
     tf32 = None
-    if world == 1 and not args.no_sweep:
-        tf32 = measure_tf32_peak(torch, dev)
-    tf32_burst = tf32["tf32_tflops_burst"] if tf32 else peaks["bf16_tflops"] / 2.0
-    tf32_sus = tf32["tf32_tflops_sustained"] if tf32 else peaks["bf16_sustained"] / 2.0
-    tf32_src = "measured here (cuBLAS TF32 8192^3)" if tf32 else peaks["source"] + " bf16 / 2"
+    tf32_burst = peaks["bf16_tflops"] / 2.0
+    tf32_sus = peaks["bf16_sustained"] / 2.0
+    tf32_src = peaks["source"] + " bf16 / 2"
     t_tensor = work["flops"] / (tf32_burst * 1e12)
     t_hbm = work["bytes"] / (peaks["hbm_gbs"] * 1e9)
     if t_tensor >= t_hbm:                                          # whichever roofline binds this launch
@@ -751,43 +752,6 @@ def main():
         e2e_lean = run_e2e(False)
     sampler.stop()
 
-    # ---- configs[3]: sweep corner points (N = 1M rows, indices only), single GPU ----------------------------
-    sweep = None
-    if world == 1 and not args.no_sweep and not args.workload.startswith("sweep"):
-        sweep = {"n_rows": SWEEP_N, "encodings": "indices only", "tf32_peak_tflops": {"burst": tf32_burst, "sustained": tf32_sus, "source": tf32_src},
-                 "note": "frac_fwd = algorithmic 2NKD / t_fwd over the sustained TF32 peak; frac = T_roof / (t_fwd + t_bwd), "
-                         "T_roof = max(2NKD / P_tf32, bytes_fwd / BW) + bytes_bwd / BW (SURVEY.md 8d)", "points": []}
-        pts = [(k, d) for k in SWEEP_K for d in SWEEP_D] if args.sweep_all else SWEEP_CORNERS
-        del S0["zs"][1:], S0["gs"][1:]
-        for (k_, d_) in pts:
-            torch.cuda.empty_cache()
-            s = make_state(SWEEP_N, k_, d_, False, 1 if d_ >= 128 else 2, 5)
-            for i in range(2):
-                step(s, i, cur.cuda_stream)
-            torch.cuda.synchronize()
-            reps = 4
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for i in range(reps):
-                step(s, i, cur.cuda_stream)
-            b.record(); torch.cuda.synchronize()
-            t_step = a.elapsed_time(b) / reps * 1e3
-            kk = profile(s, reps)
-            # forward = prepare + fused forward (+ the rows kernel where the launcher splits the row epilogue off: small K)
-            t_f = (kk.get("forward", kk.get("argmin_exact", {"avg_us": float("nan")}))["avg_us"] + kk.get("prepare_codebook", {"avg_us": 0.0})["avg_us"]
-                   + kk.get("rows", {"avg_us": 0.0})["avg_us"])
-            t_b = kk["backward"]["avg_us"]
-            fl = 2.0 * SWEEP_N * k_ * d_
-            bf, bb = fwd_bytes(SWEEP_N, k_, d_, False), bwd_bytes(SWEEP_N, k_, d_)
-            t_roof = max(fl / (tf32_sus * 1e12), bf / (peaks["hbm_gbs"] * 1e9)) + bb / (peaks["hbm_gbs"] * 1e9)
-            sweep["points"].append({"K": k_, "D": d_, "fwd_us": round(t_f, 1), "bwd_us": round(t_b, 1), "step_us": round(t_step, 1),
-                                    "fwd_tflops": round(fl / (t_f * 1e-6) / 1e12, 1), "frac_fwd": round(fl / (t_f * 1e-6) / 1e12 / tf32_sus, 3),
-                                    "bwd_frac_hbm": round(bb / (t_b * 1e-6) / 1e9 / peaks["hbm_gbs"], 3),
-                                    "frac": round(t_roof * 1e6 / (t_f + t_b), 3), "vectors_per_s": round(SWEEP_N / (t_step * 1e-6)),
-                                    "backward_path": ["flat", "", "private", "replicated"][lib.vq_backward_path(SWEEP_N, k_, d_, 0)],
-                                    "forward_kernels": sorted(n for n in kk if n not in ("backward", "exchange"))})
-            del s
-
     # ---- the drop-in nn.Module on the same workload (north star: the module is the deliverable) ------------------
     module = None
     if world == 1 and not args.no_module:
@@ -831,6 +795,54 @@ def main():
         except Exception as e:
             module["graph_us_per_step"] = None
             module["graph_error"] = f"{type(e).__name__}: {e}"[:200]
+
+    # ---- configs[3]: sweep corner points (N = 1M rows, indices only), single GPU ----------------------------
+    sweep = None
+    if world == 1 and not args.no_sweep and not args.workload.startswith("sweep"):
+        raw = []
+        pts = [(k, d) for k in SWEEP_K for d in SWEEP_D] if args.sweep_all else SWEEP_CORNERS
+        del S0["zs"][1:], S0["gs"][1:]
+        for (k_, d_) in pts:
+            torch.cuda.empty_cache()
+            s = make_state(SWEEP_N, k_, d_, False, 1 if d_ >= 128 else 2, 5)
+            for i in range(3):
+                step(s, i, cur.cuda_stream)
+            torch.cuda.synchronize()
+            reps = 5
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(reps):
+                step(s, i, cur.cuda_stream)
+            b.record(); torch.cuda.synchronize()
+            t_step = a.elapsed_time(b) / reps * 1e3
+            kk = profile(s, reps)
+            # forward = prepare + fused forward (+ the rows kernel where the launcher splits the row epilogue off: small K)
+            t_f = (kk.get("forward", kk.get("argmin_exact", {"avg_us": float("nan")}))["avg_us"] + kk.get("prepare_codebook", {"avg_us": 0.0})["avg_us"]
+                   + kk.get("rows", {"avg_us": 0.0})["avg_us"])
+            t_b = kk["backward"]["avg_us"]
+            raw.append((k_, d_, t_f, t_b, t_step, ["flat", "", "private", "replicated"][lib.vq_backward_path(SWEEP_N, k_, d_, 0)],
+                        sorted(n for n in kk if n not in ("backward", "exchange"))))
+            del s
+        torch.cuda.empty_cache()
+        tf32 = measure_tf32_peak(torch, dev)
+        tf32_burst, tf32_sus, tf32_src = tf32["tf32_tflops_burst"], tf32["tf32_tflops_sustained"], "measured here (cuBLAS TF32 8192^3), after the sweep"
+        sweep = {"n_rows": SWEEP_N, "encodings": "indices only", "tf32_peak_tflops": {"burst": tf32_burst, "sustained": tf32_sus, "source": tf32_src},
+                 "note": "frac_fwd = algorithmic 2NKD / t_fwd over the sustained TF32 peak; frac = T_roof / (t_fwd + t_bwd), "
+                         "T_roof = max(2NKD / P_tf32, bytes_fwd / BW) + bytes_bwd / BW (SURVEY.md 8d)", "points": []}
+        for (k_, d_, t_f, t_b, t_step, bpath, fkern) in raw:
+            fl = 2.0 * SWEEP_N * k_ * d_
+            bf, bb = fwd_bytes(SWEEP_N, k_, d_, False), bwd_bytes(SWEEP_N, k_, d_)
+            t_roof = max(fl / (tf32_sus * 1e12), bf / (peaks["hbm_gbs"] * 1e9)) + bb / (peaks["hbm_gbs"] * 1e9)
+            sweep["points"].append({"K": k_, "D": d_, "fwd_us": round(t_f, 1), "bwd_us": round(t_b, 1), "step_us": round(t_step, 1),
+                                    "fwd_tflops": round(fl / (t_f * 1e-6) / 1e12, 1), "frac_fwd": round(fl / (t_f * 1e-6) / 1e12 / tf32_sus, 3),
+                                    "bwd_frac_hbm": round(bb / (t_b * 1e-6) / 1e9 / peaks["hbm_gbs"], 3),
+                                    "frac": round(t_roof * 1e6 / (t_f + t_b), 3), "vectors_per_s": round(SWEEP_N / (t_step * 1e-6)),
+                                    "backward_path": bpath, "forward_kernels": fkern})
+    elif world == 1 and not args.no_sweep:      # a sweep point is the main workload: its roofline wants the measured peak
+        tf32 = measure_tf32_peak(torch, dev)
+        tf32_burst, tf32_sus, tf32_src = tf32["tf32_tflops_burst"], tf32["tf32_tflops_sustained"], "measured here (cuBLAS TF32 8192^3), after the timed regions"
+    if tf32 is not None and roofline["bound"] == "tensor":
+        roofline.update({"peak": round(tf32_burst, 1), "frac": round(roofline["achieved"] / tf32_burst, 4), "peak_source": tf32_src})
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ------------------------------------
     cpu = None
