@@ -40,8 +40,9 @@ extern "C" {
 /* flags for vq_forward / vq_backward */
 #define VQ_FLAG_ONEHOT     (1 << 0)  /* forward: also write the dense (N,K) one-hot (vector_quantizer.py:39-40) */
 #define VQ_FLAG_TRAIN_VQ   (1 << 1)  /* backward: produce dE (vector_quantizer.py:47-50 `_train_vq`) */
-#define VQ_FLAG_EXACT      (1 << 2)  /* forward: CUDA-core distances in the oracle's fp32 FMA-chain order
-                                        (bit-exact vs oracle/vq_oracle.c) instead of the tcgen05 3xTF32 path */
+#define VQ_FLAG_EXACT      (1 << 2)  /* forward: every distance on CUDA cores in the oracle's fp32 FMA-chain order instead of
+                                        the tcgen05 path (default there: one TF32 screening pass + exact fp32 refine of the
+                                        candidates, also bit-exact vs oracle/vq_oracle.c; 3xTF32 for the other shapes) */
 #define VQ_FLAG_DEFER_STATS (1 << 3) /* forward: leave loss/perplexity to vq_finalize_stats (data parallel) */
 #define VQ_FLAG_NO_QUANT   (1 << 4)  /* forward: indices/hist only; q_out, sse, loss are not produced */
 #define VQ_FLAG_TC_1CTA    (1 << 6)  /* forward: single-CTA tensor kernel (M=128,N=128) even when the CTA-pair kernel applies */
