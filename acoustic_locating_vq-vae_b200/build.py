@@ -40,8 +40,19 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into csrc/libb200vq.so for sm_100a (cross-compiles without a GPU)."""
+DEBUG_SO_PATH = os.path.join(CSRC, "libb200vq_debug.so")
+
+
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> str:
+    """Compile csrc/*.cu into csrc/libb200vq.so for sm_100a (cross-compiles without a GPU).
+    debug=True builds csrc/libb200vq_debug.so with -DVQ_DEBUG (device-side bounds checks, common.cuh); run a test with it as
+    `B200VQ_SO=<that path> B200VQ_PY_AUTOGRAD=1 python -m pytest tests/test_gpu_properties.py -m gpu`."""
+    if debug:
+        cmd = [_nvcc(), *NVCC_FLAGS, "-DVQ_DEBUG", "-o", DEBUG_SO_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        return DEBUG_SO_PATH
     if not force and not needs_build():
         return SO_PATH
     cmd = [_nvcc(), *NVCC_FLAGS, "-o", SO_PATH] + [os.path.join(CSRC, s) for s in SOURCES]

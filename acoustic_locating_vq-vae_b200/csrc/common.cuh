@@ -10,6 +10,25 @@
 #endif
 #endif
 
+// -DVQ_DEBUG (build.py: build(debug=True) -> libb200vq_debug.so, selected with B200VQ_SO): device-side bounds checks on the
+// indices the warp-specialised forward computes for its shared-memory lists (candidate logs, handoff slots, pair lists,
+// spill lists, full-rescan lists) and on every code it emits.  A failed check prints its location and traps, which the
+// host sees as a launch failure.  Compiled out of the production library.
+#ifdef VQ_DEBUG
+#include <cstdio>
+#define VQ_ASSERT(cond)                                                                        \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            printf("VQ_ASSERT failed: %s (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, static_cast<int>(blockIdx.x), static_cast<int>(threadIdx.x)); \
+            __trap();                                                                          \
+        }                                                                                      \
+    } while (0)
+#else
+#define VQ_ASSERT(cond) \
+    do {                \
+    } while (0)
+#endif
+
 namespace b200vq {
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs

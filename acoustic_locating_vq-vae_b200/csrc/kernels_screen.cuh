@@ -369,6 +369,7 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
             auto spill = [&](float v, int x, int type) -> bool {
                 const int pos = atomicAdd(spill_cnt + (it & 3), 1);
                 if (pos >= SC_SPILL) return false;
+                VQ_ASSERT(pos >= 0 && row >= 0 && row < TC_ROWS);
                 fr.spill[(static_cast<size_t>(blockIdx.x) * 4 + (it & 3)) * SC_SPILL + pos] = make_int4(row, __float_as_int(v), x, type);
                 spilled = true;
                 return true;
@@ -455,6 +456,8 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                     if (n <= SC_LOG) {              // the common case: predicated appends
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
+                            VQ_ASSERT(!(m1[q] <= t) || (slot[q] >= 0 && slot[q] < SC_LOG));
+                            VQ_ASSERT(i1f[q] >= 0.0f && i1f[q] < 128.0f);
                             if (m1[q] <= t)
                                 my_log[slot[q] * 256] = make_float2(m1[q], __int_as_float(k0 + half * 128 + static_cast<int>(i1f[q])));
                         }
@@ -476,6 +479,7 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                             }
                         }
                         n = m;
+                        VQ_ASSERT(n >= 0 && n <= SC_LOG);
                     }
                     const float w = fminf(fminf(m2[0], m2[1]), fminf(m2[2], m2[3]));
                     if (w <= t) {                   // a chain's runner-up is hidden behind its best: remember the 32 columns
@@ -541,6 +545,7 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                     if (l1 >= 0) locs[nloc++] = l1; else full = true;
                 }
                 if (nc == 0) full = true;
+                VQ_ASSERT(nc >= 0 && nc <= 4 && nloc >= 0 && nloc <= 2);
                 h_nc[(it & 1) * TC_ROWS + row] = full ? SC_NC_OVERFLOW : (nc | (nloc << 4) | (spilled ? 0x40 : 0));
                 h_an[(it & 1) * TC_ROWS + row] = a_n;
                 h_thr[(it & 1) * TC_ROWS + row] = thr;
@@ -621,10 +626,12 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                     return false;
                 }
                 int p = base;
+                VQ_ASSERT(base >= 0 && base + cnt <= pmax && r >= 0 && r < TC_ROWS && code < K);
                 if (code >= 0) g_pair[p++] = (r << 20) | code;
                 for (int l = 0; l < nloc_entries; ++l) {
                     const int loc = l == 0 ? loc0 : loc1;
                     const int kb = (loc >> 3) * TC2_CODES + ((loc >> 2) & 1) * 128 + (loc & 3);
+                    VQ_ASSERT(loc >= 0 && kb + 4 * 31 < K);
                     for (int j = 0; j < 32; ++j) g_pair[p++] = (r << 20) | (kb + 4 * j);
                 }
                 return true;
@@ -646,7 +653,11 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                         if (state == 1 && nloc > 0 && !push_pairs(r, -1, nloc, locs[r * 2], locs[r * 2 + 1])) state = 2;   // list full: rescan the row
                     }
                 }
-                if (state == 2) g_ovf[atomicAdd(g_ocount, 1)] = r;
+                if (state == 2) {
+                    const int o = atomicAdd(g_ocount, 1);
+                    VQ_ASSERT(o >= 0 && o < TC_ROWS);
+                    g_ovf[o] = r;
+                }
                 g_rng[r] = state;
             }
             named_bar_sync(gbar, NW);
@@ -669,6 +680,7 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
                     const int rc = g_pair[p];
                     if (rc >= 0) {
                         const int r = rc >> 20, k = rc & 0xfffff;
+                        VQ_ASSERT(r >= 0 && r < rows_here && k < K);
                         const float c = dot_chain_exact<D>(fr.z + (row0 + r) * D, fr.E + static_cast<size_t>(k) * D);
                         atomicMin(g_key + r, pack_key(fmaf(-2.0f, c, ans[r] + __ldg(e_norm2 + k)), k));
                     }
@@ -741,6 +753,7 @@ vq_screen_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant
             // -- indices, usage histogram -----------------------------------------------------------------------
             for (int r = wt; r < rows_here; r += NW) {
                 const int code = g_idx[r];
+                VQ_ASSERT(code >= 0 && code < K);
                 idx_out[row0 + r] = code;
                 if (!fr.rows_later) {
                     if (smem_hist) atomicAdd(s_hist + code, 1);

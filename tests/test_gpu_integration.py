@@ -314,3 +314,26 @@ def test_time_mean_variant_in_front_of_the_quantizer(B, D, T, K):
     dx_ref = np.repeat(dz_ref.reshape(B, D, 1), T, axis=2) / T                       # d mean / d x = 1 / T
     assert _rel(x.grad, torch.from_numpy(dx_ref).to(dev)) <= RTOL
     assert _rel(vq._embedding.weight.grad, torch.from_numpy(dE_ref).to(dev)) <= RTOL
+
+
+def test_module_on_a_second_device_in_the_same_process():
+    """The kernels' shared-memory opt-in (cudaFuncSetAttribute) is per device: a module on cuda:1 after one on cuda:0 in the
+    same process must launch and give the same indices on the same data.  Needs two visible GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    import b200vq
+    torch.manual_seed(3)
+    E = torch.randn(1024, 64)
+    z = torch.randn(8, 64, 201)
+    outs = []
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        vq = b200vq.VectorQuantizer(1024, 64, 0.25).to(dev)
+        vq._embedding.weight.data.copy_(E)
+        zz = z.to(dev).requires_grad_(True)
+        loss, q, perp, enc = vq(zz)
+        (loss + q.sum()).backward()
+        torch.cuda.synchronize(dev)
+        outs.append((vq.last_indices.cpu(), float(loss), zz.grad.cpu(), vq._embedding.weight.grad.cpu()))
+    for o in outs[1:]:
+        assert torch.equal(o[0], outs[0][0]) and abs(o[1] - outs[0][1]) <= 1e-6 * abs(outs[0][1])
+        assert torch.equal(o[2], outs[0][2]) and torch.allclose(o[3], outs[0][3], rtol=1e-5, atol=1e-9)
