@@ -865,7 +865,10 @@ def main():
                       "launch": (f"CUDA graphs ({len(S0['packs']) if exch is not None else nbuf} steps per graph + one for the remaining steps; inputs rotate over {nbuf} buffers), {launches_per_step} kernels per step"
                                  if use_graph else f"eager launches chained by programmatic dependent launch, {launches_per_step} kernels per step"),
                       "l2": f"inputs rotate over {nbuf} z + {nbuf} g buffers ({2 * nbuf * N * D * 4 >> 20} MiB > 126 MiB L2)",
-                      "collective": collective},
+                      "collective": collective,
+                      "kernel_timing": "kernels.*: CUDA events around every launch on its own stream (eager, profile pass). The backward is launched early (programmatic dependent "
+                                       "launch) and starts on the forward's ready word, so its figure includes that wait; stand-alone it takes 11 us back to back "
+                                       "(14.5 - 15.6 us cold and serialised under ncu: profiles/r2_launches_rir256_s1.csv)"},
             "clocks": sampler.summary(),
             "e2e": e2e, "e2e_lean": e2e_lean, "gpu_launches": int(launches_per_step * args.steps), "roofline": roofline, "cpu_baseline": cpu,
             "kernels": kern, "peaks": {"hbm_gbs": peaks["hbm_gbs"], "hbm_source": peaks["source"], "tf32": tf32}, "sweep": sweep, "module": module,
